@@ -1,0 +1,36 @@
+"""atlite_b200 -- B200-native convert+aggregate hot path of PyPSA/atlite.
+
+Drop-in for ``Cutout.convert_and_aggregate`` / ``pv`` / ``wind`` /
+``heat_demand`` (reference: atlite/convert.py, atlite/aggregate.py), backed by
+hand-written sm_100a CUDA kernels in ``libatlite_b200.so``.
+"""
+
+from . import resource
+from .convert import (
+    convert_and_aggregate,
+    convert_heat_demand,
+    convert_pv,
+    convert_wind,
+    heat_demand,
+    pv,
+    wind,
+)
+from .cutout import Cutout
+from .labelled import DataArray, Dataset
+from .orientation import get_orientation
+from .resource import (
+    get_solarpanelconfig,
+    get_windturbineconfig,
+    solarpanels,
+    windturbine_smooth,
+    windturbines,
+)
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "Cutout", "Dataset", "DataArray", "convert_and_aggregate", "convert_pv", "convert_wind",
+    "convert_heat_demand", "pv", "wind", "heat_demand", "get_orientation",
+    "get_windturbineconfig", "get_solarpanelconfig", "windturbine_smooth", "windturbines",
+    "solarpanels", "resource",
+]

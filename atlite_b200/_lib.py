@@ -1,0 +1,200 @@
+"""ctypes binding of ``libatlite_b200.so`` (C ABI in ``include/atlite_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a compute entry
+point fails (e.g. no CUDA device) an exception is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatlite_b200.so")
+
+ATL_OK = 0
+
+# enums (mirror include/atlite_b200.h)
+TRACKING = {None: 0, "horizontal": 1, "tilted_horizontal": 2, "vertical": 3, "dual": 4}
+TRIGON_SIMPLE, TRIGON_HAY_DAVIES = 0, 1
+CLEARSKY = {"simple": 0, "enhanced": 1}
+IRR_DIRECT_DIFFUSE, IRR_INFLUX = 0, 1
+ALBEDO_VAR, ALBEDO_OUTFLUX = 0, 1
+SOLAR_COMPUTED, SOLAR_STORED_F32, SOLAR_STORED_F64 = 0, 1, 2
+PANEL = {"huld": 0, "bofinger": 1}
+WIND_NONE, WIND_LOG, WIND_POWER = 0, 1, 2
+
+
+class AtlError(RuntimeError):
+    pass
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("n_bus", C.c_int32),
+        ("nnz", C.c_int64),
+        ("n_tiles", C.c_int32),
+        ("n_active_tiles", C.c_int32),
+        ("n_slots", C.c_int64),
+        ("slots_per_active_tile", C.c_double),
+        ("fused", C.c_int32),
+    ]
+
+
+class PvConfig(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("nt", C.c_int64),
+        ("time_ns", C.c_void_p),
+        ("time_shift_ns", C.c_int64),
+        ("lon_deg", C.c_void_p),
+        ("lat_deg", C.c_void_p),
+        ("slope_rad", C.c_void_p),
+        ("azimuth_rad", C.c_void_p),
+        ("tracking", C.c_int32),
+        ("trigon_model", C.c_int32),
+        ("clearsky_model", C.c_int32),
+        ("irr_branch", C.c_int32),
+        ("albedo_src", C.c_int32),
+        ("solar_src", C.c_int32),
+        ("panel_model", C.c_int32),
+        ("altitude_threshold_deg", C.c_double),
+        ("panel", C.c_double * 16),
+    ]
+
+
+class PvFields(C.Structure):
+    _fields_ = [
+        (n, C.c_void_p)
+        for n in (
+            "influx_toa",
+            "influx_direct",
+            "influx_diffuse",
+            "influx",
+            "albedo",
+            "outflux",
+            "temperature",
+            "humidity",
+            "solar_altitude",
+            "solar_azimuth",
+        )
+    ]
+
+
+class WindConfig(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("method", C.c_int32),
+        ("from_height", C.c_double),
+        ("to_height", C.c_double),
+        ("n_knots", C.c_int32),
+        ("V", C.c_void_p),
+        ("POW_norm", C.c_void_p),
+    ]
+
+
+class WindFields(C.Structure):
+    _fields_ = [("wnd", C.c_void_p), ("aux", C.c_void_p)]
+
+
+class HeatConfig(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("threshold_c", C.c_double),
+        ("a", C.c_double),
+        ("constant", C.c_double),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/atlite_b200.h
+_P = C.c_void_p
+_SIGNATURES = {
+    "atl_abi_version": (C.c_int, []),
+    "atl_last_error": (C.c_char_p, []),
+    "atl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "atl_launch_count": (C.c_int64, []),
+    "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
+    "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "atl_plan_destroy": (None, [_P]),
+    "atl_spmm": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "atl_pv_create": (C.c_int, [C.c_int, C.POINTER(PvConfig), C.POINTER(_P)]),
+    "atl_pv_destroy": (None, [_P]),
+    "atl_pv_reduce": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_pv_cells": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_pv_timesum": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
+    "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
+    "atl_wind_create": (C.c_int, [C.c_int, C.POINTER(WindConfig), C.POINTER(_P)]),
+    "atl_wind_destroy": (None, [_P]),
+    "atl_wind_reduce": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, _P]),
+    "atl_wind_cells": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),
+    "atl_wind_timesum": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),
+    "atl_wind_reduce_host": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, C.c_int64]),
+    "atl_wind_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
+    "atl_heat_create": (C.c_int, [C.c_int, C.POINTER(HeatConfig), C.POINTER(_P)]),
+    "atl_heat_destroy": (None, [_P]),
+    "atl_heat_reduce": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
+    "atl_heat_cells": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "atl_heat_timesum": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "atl_heat_reduce_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int64]),
+    "atl_heat_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AtlError(
+            f"{LIB_PATH} not found: build the CUDA library first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or make -C atlite_b200/csrc). "
+            "atlite_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != ATL_OK:
+        msg = load().atl_last_error()
+        raise AtlError(f"libatlite_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(load().atl_launch_count())
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().atl_device_count(C.byref(n))
+    return n.value if rc == ATL_OK else 0
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous NumPy array (kept alive by the caller)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))

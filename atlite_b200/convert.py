@@ -1,0 +1,589 @@
+"""Reference-facing API of the hot path: ``convert_and_aggregate`` and the
+``pv`` / ``wind`` / ``heat_demand`` wrappers, with the reference's signatures,
+argument meaning, warnings and errors (convert.py:59-276, 421-471, 665-744,
+857-936), executing on the GPU through ``libatlite_b200.so``.
+
+Instead of building a lazy dask graph of ~60 ufunc passes and a per-chunk
+``dense * csr.T`` product, a known ``convert_func`` is mapped to a fused
+operator (physics + shape reduce in one kernel).  Unknown ``convert_func``
+callables keep the reference's plugin protocol: they are evaluated by the
+caller's code and only the aggregation runs on the GPU (``atl_spmm``).
+"""
+
+from __future__ import annotations
+
+import logging
+import re
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+from . import _lib, engine
+from .labelled import HAVE_XARRAY, DataArray, is_dataarray, make_dataarray
+from .orientation import get_orientation
+from .resource import get_solarpanelconfig, get_windturbineconfig, windturbine_smooth
+
+if HAVE_XARRAY:  # pragma: no cover
+    import xarray as xr
+
+logger = logging.getLogger(__name__)
+
+_SOLAR_WARNING = """The calculation method and handling of solar position variables will change.
+    The solar position will in the future be a permanent variables of a cutout.
+    Recreate your cutout to remove this warning and permanently include the solar position variables into your cutout."""
+
+
+# --------------------------------------------------------------------------
+# dataset access helpers (xarray.Dataset or atlite_b200.labelled.Dataset)
+# --------------------------------------------------------------------------
+
+
+def _has(ds, name):
+    return name in ds
+
+
+def _coord(ds, name):
+    v = ds[name]
+    return np.asarray(getattr(v, "values", v))
+
+
+def _raw(ds, name):
+    """(time, y, x) array of a variable: torch CUDA tensor for a device-resident
+    cutout, else a NumPy array."""
+    if hasattr(ds, "raw"):
+        arr = ds.raw(name)
+        dims = ds.dims_of(name)
+        if dims != ("time", "y", "x")[-len(dims):]:
+            raise ValueError(f"variable {name!r} must have dims (time, y, x), has {dims}")
+        return arr
+    da = ds[name]
+    if da.ndim == 3:
+        da = da.transpose("time", "y", "x")
+    return np.asarray(da.values)
+
+
+def _grid_shape(ds):
+    return len(_coord(ds, "y")), len(_coord(ds, "x"))
+
+
+def _is_dask_backed(ds):
+    if not HAVE_XARRAY or hasattr(ds, "raw"):
+        return False
+    try:
+        from dask.array.core import Array
+
+        return any(isinstance(ds[v].data, Array) for v in ds.data_vars)
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _to_host(a):
+    if engine._is_torch(a):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+# --------------------------------------------------------------------------
+# fused operator specs
+# --------------------------------------------------------------------------
+
+
+class _Spec:
+    """A known conversion bound to a cutout: can reduce to buses, or produce
+    per-cell values / their time sum."""
+
+    time_labels = None  # output time coordinate
+    name = None
+    units = None
+
+    def _device_fields(self, fields):
+        """Host arrays -> device tensors (per-cell output paths only)."""
+        torch = engine._torch()
+        dev = f"cuda:{engine.current_device()}"
+        return {
+            k: (v if v is None or engine._is_torch(v) else torch.from_numpy(np.ascontiguousarray(v)).to(dev))
+            for k, v in fields.items()
+        }
+
+
+class _PvSpec(_Spec):
+    name = "specific generation"
+
+    def __init__(self, ds, panel, orientation, tracking=None, trigon_model="simple",
+                 clearsky_model="simple"):
+        ny, nx = _grid_shape(ds)
+        self.ds = ds
+        self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
+        lon, lat = _coord(ds, "lon").astype(np.float64), _coord(ds, "lat").astype(np.float64)
+
+        # SolarPosition: getter vs computation (pv/solar_position.py:54-67)
+        if _has(ds, "solar_azimuth") and _has(ds, "solar_altitude"):
+            dt = np.dtype(str(_raw(ds, "solar_altitude").dtype).replace("torch.", ""))
+            solar_src = _lib.SOLAR_STORED_F64 if dt == np.float64 else _lib.SOLAR_STORED_F32
+        else:
+            warnings.warn(_SOLAR_WARNING, DeprecationWarning)
+            solar_src = _lib.SOLAR_COMPUTED
+
+        # SurfaceOrientation (pv/orientation.py:104-109, 177-183)
+        if tracking not in _lib.TRACKING:
+            raise AssertionError(
+                "Values describing tracking system must be None for no tracking,"
+                "'horizontal' for 1-axis horizontal tracking,"
+                "tilted_horizontal' for 1-axis horizontal tracking of tilted panle,"
+                "vertical' for 1-axis vertical tracking, or 'dual' for 2-axis tracking"
+            )
+        lon_r = DataArray(np.radians(lon), {"x": _coord(ds, "x")}, ("x",), "lon")
+        lat_r = DataArray(np.radians(lat), {"y": _coord(ds, "y")}, ("y",), "lat")
+        o = orientation(lon_r, lat_r, None)
+        slope = np.asarray(getattr(o["slope"], "values", o["slope"]), dtype=np.float64)
+        azimuth = np.asarray(getattr(o["azimuth"], "values", o["azimuth"]), dtype=np.float64)
+        for nm, arr in (("slope", slope), ("azimuth", azimuth)):
+            if arr.ndim > 1 or (arr.ndim == 1 and arr.shape[0] != ny):
+                raise NotImplementedError(
+                    f"orientation {nm} must be a scalar or vary with latitude (y) only; "
+                    f"got shape {arr.shape}"
+                )
+
+        # TiltedIrradiation inputs (pv/irradiation.py:202-213)
+        if _has(ds, "influx"):
+            irr_branch = _lib.IRR_INFLUX
+            cm = clearsky_model
+            if cm is None:
+                cm = "enhanced" if _has(ds, "temperature") and _has(ds, "humidity") else "simple"
+            if cm not in _lib.CLEARSKY:
+                raise KeyError("`clearsky model` must be chosen from 'simple' and 'enhanced'")
+            clearsky = _lib.CLEARSKY[cm]
+        elif _has(ds, "influx_direct") and _has(ds, "influx_diffuse"):
+            irr_branch, clearsky = _lib.IRR_DIRECT_DIFFUSE, 0
+        else:
+            raise AssertionError(
+                "Need either influx or influx_direct and influx_diffuse in the "
+                "dataset. Check your cutout and dataset module."
+            )
+        if _has(ds, "albedo"):
+            albedo_src = _lib.ALBEDO_VAR
+        elif _has(ds, "outflux"):
+            albedo_src = _lib.ALBEDO_OUTFLUX
+        else:
+            raise AssertionError(
+                "Need either albedo or outflux as a variable in the dataset. "
+                "Check your cutout and dataset module."
+            )
+        trigon = _lib.TRIGON_SIMPLE if trigon_model == "simple" else _lib.TRIGON_HAY_DAVIES
+
+        names = ["influx_toa", "temperature"]
+        names += ["influx"] if irr_branch == _lib.IRR_INFLUX else ["influx_direct", "influx_diffuse"]
+        if irr_branch == _lib.IRR_INFLUX and clearsky == 1:
+            names.append("humidity")
+        names.append("albedo" if albedo_src == _lib.ALBEDO_VAR else "outflux")
+        if solar_src != _lib.SOLAR_COMPUTED:
+            names += ["solar_altitude", "solar_azimuth"]
+        self.fields = {n: _raw(ds, n) for n in names}
+        self.op = engine.PvOp(
+            ny=ny, nx=nx, time=self.time_labels, lon=lon, lat=lat, slope=slope, azimuth=azimuth,
+            tracking=tracking, trigon_model=trigon, clearsky_model=clearsky,
+            irr_branch=irr_branch, albedo_src=albedo_src, solar_src=solar_src, panel=panel,
+        )
+
+    def reduce(self, plan):
+        return self.op.reduce(plan, self.fields)
+
+    def cells(self, timesum=False):
+        return self.op.cells(self._device_fields(self.fields), timesum=timesum)
+
+
+class _WindSpec(_Spec):
+    name = "specific generation"
+    units = "MWh/MWp"
+
+    def __init__(self, ds, turbine, interpolation_method="logarithmic"):
+        ny, nx = _grid_shape(ds)
+        self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
+        V, POW, hub_height, P = (turbine[k] for k in ("V", "POW", "hub_height", "P"))
+        to_name = f"wnd{int(hub_height):0d}m"
+        aux = None
+        from_height = hub_height
+        if _has(ds, to_name):  # fast lane, wind.py:75-78
+            method = _lib.WIND_NONE
+            wnd = _raw(ds, to_name)
+        else:
+            names = list(ds.data_vars) if hasattr(ds, "data_vars") else list(ds)
+            heights = np.asarray([int(s[3:-1]) for s in names if re.match(r"wnd\d+m", str(s))])
+            if len(heights) == 0:
+                raise AssertionError("Wind speed is not in dataset")
+            from_height = heights[np.argmin(np.abs(heights - hub_height))]
+            wnd = _raw(ds, f"wnd{int(from_height):0d}m")
+            if interpolation_method == "logarithmic":
+                if not _has(ds, "roughness"):
+                    raise RuntimeError(
+                        "The logarithmic interpolation method requires surface roughness (roughness);\n"
+                        "make sure you choose a compatible dataset like ERA5"
+                    )
+                method, aux = _lib.WIND_LOG, _raw(ds, "roughness")
+            elif interpolation_method == "power":
+                if not _has(ds, "wnd_shear_exp"):
+                    raise RuntimeError(
+                        "The power law interpolation method requires a wind shear exponent (wnd_shear_exp);\n"
+                        "make sure you choose a compatible dataset like ERA5 and update your cutout"
+                    )
+                method, aux = _lib.WIND_POWER, _raw(ds, "wnd_shear_exp")
+            else:
+                raise ValueError(
+                    f"Interpolation method must be 'logarithmic' or 'power',  but is: {interpolation_method}"
+                )
+        self.wnd, self.aux = wnd, aux
+        self.op = engine.WindOp(
+            ny=ny, nx=nx, V=np.asarray(V, float), POW_norm=np.asarray(POW, float) / P,
+            method=method, from_height=from_height, to_height=hub_height,
+        )
+
+    def reduce(self, plan):
+        return self.op.reduce(plan, self.wnd, self.aux)
+
+    def cells(self, timesum=False):
+        f = self._device_fields({"wnd": self.wnd, "aux": self.aux})
+        return self.op.cells(f["wnd"], f["aux"], timesum=timesum)
+
+
+def day_bins(time, hour_shift):
+    """Calendar-day bins of ``time + hour_shift`` (``resample(time="1D")``,
+    convert.py:408-412).  Returns (day labels, offsets[n_days+1] into time)."""
+    t = pd.DatetimeIndex(time) + pd.Timedelta(hours=hour_shift)
+    if len(t) == 0:
+        return pd.DatetimeIndex([]), np.zeros(1, dtype=np.int64)
+    if not t.is_monotonic_increasing:
+        raise ValueError("time axis must be sorted for the daily heat-demand bins")
+    days = t.floor("D")
+    labels = pd.date_range(days[0], days[-1], freq="D")
+    offsets = np.searchsorted(days.values, labels.values, side="left")
+    offsets = np.append(offsets, len(t)).astype(np.int64)
+    return labels, offsets
+
+
+class _HeatSpec(_Spec):
+    name = "heat_demand"
+
+    def __init__(self, ds, threshold, a, constant, hour_shift):
+        ny, nx = _grid_shape(ds)
+        self.temp = _raw(ds, "temperature")
+        self.time_labels, self.day_start = day_bins(_coord(ds, "time"), hour_shift)
+        self.op = engine.HeatOp(ny=ny, nx=nx, threshold=threshold, a=a, constant=constant)
+
+    def reduce(self, plan):
+        return self.op.reduce(plan, self.temp, self.day_start)
+
+    def cells(self, timesum=False):
+        f = self._device_fields({"t": self.temp})
+        return self.op.cells(f["t"], self.day_start, timesum=timesum)
+
+
+# --------------------------------------------------------------------------
+# convert_* callables (plugin protocol, convert.py:198)
+# --------------------------------------------------------------------------
+
+
+def _wrap_cells(ds, spec, values):
+    coords = {"time": spec.time_labels, "y": _coord(ds, "y"), "x": _coord(ds, "x")}
+    attrs = {"units": spec.units} if spec.units else {}
+    return make_dataarray(_to_host(values), ("time", "y", "x"), coords, attrs, spec.name)
+
+
+def convert_pv(ds, panel, orientation, tracking=None, trigon_model="simple", clearsky_model="simple"):
+    """Per-cell PV capacity factors (time, y, x); convert.py:840-854."""
+    spec = _PvSpec(ds, panel, orientation, tracking, trigon_model, clearsky_model)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_wind(ds, turbine, interpolation_method="logarithmic"):
+    """Per-cell wind capacity factors (time, y, x); convert.py:634-662."""
+    spec = _WindSpec(ds, turbine, interpolation_method)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_heat_demand(ds, threshold, a, constant, hour_shift):
+    """Per-cell daily heat demand (day, y, x); convert.py:405-418."""
+    spec = _HeatSpec(ds, threshold, a, constant, hour_shift)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+_SPECS = {"convert_pv": _PvSpec, "convert_wind": _WindSpec, "convert_heat_demand": _HeatSpec}
+
+
+def _known_spec(convert_func):
+    name = getattr(convert_func, "__name__", "")
+    mod = getattr(convert_func, "__module__", "") or ""
+    if name in _SPECS and (mod.startswith("atlite_b200") or mod.startswith("atlite")):
+        return _SPECS[name]
+    return None
+
+
+# --------------------------------------------------------------------------
+# orchestration
+# --------------------------------------------------------------------------
+
+
+def _aggregate_time_np(values, method, axis):
+    if method == "sum":
+        return np.nansum(values, axis=axis)
+    if method == "mean":
+        return np.nanmean(values, axis=axis)
+    return values
+
+
+def _ensure_index(index, n):
+    """utils.py:22-36 ensure_coords: pandas Index -> (dim name, Index)."""
+    if index is None:
+        index = pd.RangeIndex(n)
+    if isinstance(index, pd.MultiIndex):
+        return index.name or "dim_0", index
+    if isinstance(index, pd.Index):
+        return index.name or "dim_0", index
+    if HAVE_XARRAY and isinstance(index, xr.Coordinates):
+        if len(index.dims) > 1:
+            raise ValueError(f"index must have a single dimension, not: {index.dims}")
+        d = list(index.dims)[0]
+        return d, index.to_index()
+    raise ValueError(f"index must be a pandas index or xarray coordinates, not: {index}")
+
+
+def _layout_values(layout, ds):
+    """layout.reindex_like(cutout.data).stack(spatial=[y, x])  (convert.py:244)."""
+    y, x = _coord(ds, "y"), _coord(ds, "x")
+    if HAVE_XARRAY and isinstance(layout, xr.DataArray):
+        lay = layout.reindex(y=y, x=x).transpose("y", "x")
+        return np.asarray(lay.values, dtype=np.float64).reshape(-1)
+    lay = layout.transpose("y", "x")
+    iy = pd.Index(np.asarray(lay.coords["y"])).get_indexer(y)
+    ix = pd.Index(np.asarray(lay.coords["x"])).get_indexer(x)
+    vals = np.asarray(lay.values, dtype=np.float64)
+    out = vals[np.clip(iy, 0, None)][:, np.clip(ix, 0, None)]
+    out[iy < 0, :] = np.nan
+    out[:, ix < 0] = np.nan
+    return out.reshape(-1)
+
+
+def convert_and_aggregate(
+    cutout,
+    convert_func,
+    matrix=None,
+    index=None,
+    layout=None,
+    shapes=None,
+    shapes_crs=4326,
+    per_unit=False,
+    return_capacity=False,
+    aggregate_time="legacy",
+    capacity_factor=False,
+    capacity_factor_timeseries=False,
+    show_progress=False,
+    dask_kwargs={},
+    **convert_kwds,
+):
+    """Convert and aggregate a weather-based renewable generation time-series.
+
+    Same contract as the reference (convert.py:59-276): ``matrix`` (N x S, in
+    ``cutout.grid`` order), ``shapes`` or ``layout`` select spatial
+    aggregation; ``per_unit`` / ``return_capacity``; ``aggregate_time`` in
+    {"sum", "mean", "legacy", None}; deprecated ``capacity_factor*`` flags.
+    ``show_progress`` and ``dask_kwargs`` are accepted and ignored (the result
+    is computed eagerly on the GPU and returned loaded).
+    """
+    if aggregate_time not in ("sum", "mean", "legacy", None):
+        raise ValueError(
+            f"aggregate_time must be 'sum', 'mean', 'legacy', or None, got {aggregate_time!r}"
+        )
+    if aggregate_time == "legacy":
+        warnings.warn(
+            "aggregate_time='legacy' is deprecated and will be removed in a "
+            "future release. Pass 'sum', 'mean', or None explicitly.",
+            FutureWarning,
+            stacklevel=2,
+        )
+    if capacity_factor or capacity_factor_timeseries:
+        if aggregate_time != "legacy":
+            raise ValueError(
+                "Cannot use 'aggregate_time' together with deprecated "
+                "'capacity_factor' or 'capacity_factor_timeseries'."
+            )
+        if capacity_factor:
+            warnings.warn(
+                "capacity_factor is deprecated. Use aggregate_time='mean' instead.",
+                FutureWarning,
+                stacklevel=2,
+            )
+            aggregate_time = "mean"
+        if capacity_factor_timeseries:
+            warnings.warn(
+                "capacity_factor_timeseries is deprecated. Use aggregate_time=None instead.",
+                FutureWarning,
+                stacklevel=2,
+            )
+            aggregate_time = None
+
+    func_name = convert_func.__name__.replace("convert_", "")
+    logger.info(f"Convert and aggregate '{func_name}'.")
+    ds = cutout.data
+    ny, nx = _grid_shape(ds)
+    spec_cls = _known_spec(convert_func)
+    if spec_cls is not None:
+        spec, da = spec_cls(ds, **convert_kwds), None
+    else:  # plugin protocol: the callable produces the (time, y, x) field itself
+        spec, da = None, convert_func(ds, **convert_kwds)
+
+    shard = getattr(cutout, "time_shard", None)  # multi-GPU time sharding (dist.py)
+    no_args = all(v is None for v in [layout, shapes, matrix])
+
+    if no_args:
+        if per_unit or return_capacity:
+            raise ValueError(
+                "One of `matrix`, `shapes` and `layout` must be "
+                "given for `per_unit` or `return_capacity`"
+            )
+        agg = "sum" if aggregate_time == "legacy" else aggregate_time
+        if spec is None:
+            if agg == "sum":
+                return da.sum("time", keep_attrs=True)
+            if agg == "mean":
+                return da.mean("time", keep_attrs=True)
+            return da
+        coords_yx = {"y": _coord(ds, "y"), "x": _coord(ds, "x")}
+        attrs = {"units": spec.units} if spec.units else {}
+        if agg is None:
+            vals = _to_host(spec.cells())
+            labels = spec.time_labels
+            if shard is not None:
+                vals, labels = shard.gather_time(vals, labels)
+            return make_dataarray(vals, ("time", "y", "x"), {"time": labels, **coords_yx}, attrs, spec.name)
+        total = spec.cells(timesum=True)
+        n_t = len(spec.time_labels)
+        if shard is not None:
+            total, n_t = shard.sum_over_ranks(total, n_t)
+        vals = _to_host(total).astype(np.float64)
+        if agg == "mean":
+            vals = vals / n_t
+        return make_dataarray(vals, ("y", "x"), coords_yx, attrs, spec.name)
+
+    if matrix is not None:
+        if shapes is not None:
+            raise ValueError("Passing matrix and shapes is ambiguous. Pass only one of them.")
+        if is_dataarray(matrix):
+            coords = matrix.indexes[matrix.dims[1]].to_frame(index=False)
+            if not np.array_equal(coords[["x", "y"]], cutout.grid[["x", "y"]]):
+                raise ValueError(
+                    "Matrix spatial coordinates not aligned with cutout spatial coordinates."
+                )
+            if index is None:
+                index = matrix
+            matrix = matrix.values
+        if not matrix.ndim == 2:
+            raise ValueError("Matrix not 2-dimensional.")
+        matrix = sp.csr_matrix(matrix)
+
+    if shapes is not None:
+        if isinstance(shapes, pd.Series) or hasattr(shapes, "geometry"):
+            if index is None:
+                index = shapes.index
+        matrix = cutout.indicatormatrix(shapes, shapes_crs).tocsr()
+
+    if layout is not None:
+        assert is_dataarray(layout)
+        lay = _layout_values(layout, ds)
+        if matrix is None:
+            matrix = sp.csr_matrix(lay[None, :])
+        else:
+            matrix = sp.csr_matrix(matrix) * sp.diags(lay, format="csr")
+
+    assert isinstance(matrix, sp.csr_matrix)
+    dim, idx = _ensure_index(index, matrix.shape[0])
+
+    plan = engine.get_plan(matrix, ny, nx)
+    if spec is not None:
+        res = spec.reduce(plan)  # (time, bus) float32
+        time_labels, name = spec.time_labels, spec.name
+    else:
+        vals = getattr(da, "values", da)
+        res = plan.spmm(np.asarray(vals) if not engine._is_torch(vals) else vals)
+        time_labels = pd.Index(np.asarray(da.coords["time"])) if hasattr(da, "coords") else pd.RangeIndex(len(vals))
+        name = getattr(da, "name", None)
+    if shard is not None:
+        res, time_labels = shard.gather_time(res, time_labels)
+    results = _to_host(res).astype(np.float64)
+
+    capacity = None
+    if per_unit or return_capacity:
+        caps = np.asarray(matrix.sum(-1)).flatten()
+        capacity = make_dataarray(caps, (dim,), {dim: idx}, {"units": "MW"})
+    if per_unit:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            results = results / np.where(caps != 0, caps, np.nan)[None, :]
+        results = np.where(np.isnan(results), 0.0, results)
+        units = "p.u."
+    else:
+        units = "MW"
+
+    # dim order mirrors aggregate.py: (time, bus) for dask-backed cutouts
+    # (:24-32), (bus, time) for NumPy-backed ones (:34-35)
+    if aggregate_time != "legacy" and aggregate_time is not None:
+        out = make_dataarray(
+            _aggregate_time_np(results, aggregate_time, 0), (dim,), {dim: idx}, {"units": units}, name
+        )
+    elif _is_dask_backed(ds):
+        out = make_dataarray(results, ("time", dim), {"time": time_labels, dim: idx}, {"units": units}, name)
+    else:
+        out = make_dataarray(
+            np.ascontiguousarray(results.T), (dim, "time"), {dim: idx, "time": time_labels},
+            {"units": units}, name,
+        )
+    if return_capacity:
+        return out, capacity
+    return out
+
+
+# --------------------------------------------------------------------------
+# technology wrappers
+# --------------------------------------------------------------------------
+
+
+def heat_demand(cutout, threshold=15.0, a=1.0, constant=0.0, hour_shift=0.0, **params):
+    """Daily heat demand by the degree-day approximation (convert.py:421-471)."""
+    return cutout.convert_and_aggregate(
+        convert_func=convert_heat_demand,
+        threshold=threshold,
+        a=a,
+        constant=constant,
+        hour_shift=hour_shift,
+        **params,
+    )
+
+
+def wind(cutout, turbine, smooth=False, add_cutout_windspeed=False,
+         interpolation_method="logarithmic", **params):
+    """Wind generation time-series (convert.py:665-744)."""
+    turbine = get_windturbineconfig(turbine, add_cutout_windspeed=add_cutout_windspeed)
+    if smooth:
+        turbine = windturbine_smooth(turbine, params=smooth)
+    return cutout.convert_and_aggregate(
+        convert_func=convert_wind,
+        turbine=turbine,
+        interpolation_method=interpolation_method,
+        **params,
+    )
+
+
+def pv(cutout, panel, orientation, tracking=None, clearsky_model=None, **params):
+    """PV generation time-series (convert.py:857-936)."""
+    if isinstance(panel, (str, Path)):
+        panel = get_solarpanelconfig(panel)
+    if not callable(orientation):
+        orientation = get_orientation(orientation)
+    return cutout.convert_and_aggregate(
+        convert_func=convert_pv,
+        panel=panel,
+        orientation=orientation,
+        tracking=tracking,
+        clearsky_model=clearsky_model,
+        **params,
+    )

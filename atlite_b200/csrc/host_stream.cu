@@ -1,0 +1,266 @@
+// host_stream.cu -- host-buffer entry points: the cutout lives in host memory
+// (NumPy arrays / NetCDF-backed), time slabs are streamed through a
+// double-buffered device ring so H2D copies overlap the fused kernels, and the
+// (time, bus) result is returned in host memory.  This is the call behind the
+// reference-facing `Cutout.pv/wind/heat_demand(...)` when no device-resident
+// copy of the cutout exists (bench.py "e2e").
+//
+// Pinned (cudaHostAlloc / cudaHostRegister'ed) inputs are DMA'd directly;
+// pageable inputs go through a pinned staging ring (memcpy -> async H2D).
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace atl {
+
+constexpr int NBUF = 2;
+
+struct SlabField {
+  const char* host;  // nullptr = unused
+  size_t elem;       // bytes per element
+};
+
+using SlabLaunch =
+    std::function<int(const std::vector<void*>& dev, int64_t t_rel, int64_t n, float* out_dev,
+                      cudaStream_t st)>;
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static void pool_keep_memory(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[device] = true;
+}
+
+// Stream `n_units` time units (steps, or days for heat demand) whose unit u
+// starts at step unit_start(u) through the device ring.
+static int stream_slabs(int device, const std::vector<SlabField>& fields, int64_t S,
+                        int64_t n_units, const int64_t* unit_start /* n_units+1 or NULL */,
+                        int64_t chunk_units, int32_t n_bus, float* out_host,
+                        const SlabLaunch& launch) {
+  ATL_REQUIRE(out_host, "NULL output");
+  if (n_units <= 0) return ATL_OK;
+  ATL_CUDA(cudaSetDevice(device));
+  pool_keep_memory(device);
+  auto ustart = [&](int64_t u) { return unit_start ? unit_start[u] : u; };
+  const int64_t total_steps = ustart(n_units) - ustart(0);
+  size_t bytes_per_step = 0;
+  for (const auto& f : fields)
+    if (f.host) bytes_per_step += (size_t)S * f.elem;
+  ATL_REQUIRE(bytes_per_step > 0, "no input fields");
+  if (chunk_units <= 0) {
+    // ~192 MiB of input per slab: long enough to amortise launch + copy setup,
+    // short enough that the first kernel starts early
+    const double steps_per_unit = (double)total_steps / (double)n_units;
+    chunk_units = (int64_t)((192.0 * (1 << 20)) / ((double)bytes_per_step * steps_per_unit));
+    if (chunk_units < 2) chunk_units = 2;
+  }
+  if (chunk_units > n_units) chunk_units = n_units;
+  // widest slab in steps
+  int64_t max_steps = 0;
+  for (int64_t u = 0; u < n_units; u += chunk_units) {
+    const int64_t e = u + chunk_units < n_units ? u + chunk_units : n_units;
+    const int64_t n = ustart(e) - ustart(u);
+    if (n > max_steps) max_steps = n;
+  }
+
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_copied[NBUF] = {nullptr}, ev_done[NBUF] = {nullptr}, ev_staged[NBUF] = {nullptr};
+  std::vector<std::vector<void*>> dev(NBUF, std::vector<void*>(fields.size(), nullptr));
+  std::vector<std::vector<char*>> stage(NBUF, std::vector<char*>(fields.size(), nullptr));
+  float* out_dev = nullptr;
+  int rc = ATL_OK;
+  std::vector<bool> pinned(fields.size(), false);
+
+#define SS_CUDA(call)                      \
+  do {                                     \
+    cudaError_t _e = (call);               \
+    if (_e != cudaSuccess) {               \
+      rc = cuda_fail(_e, #call);           \
+      goto cleanup;                        \
+    }                                      \
+  } while (0)
+
+  SS_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+  SS_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+  for (int b = 0; b < NBUF; ++b) {
+    SS_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+    SS_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+    SS_CUDA(cudaEventCreateWithFlags(&ev_staged[b], cudaEventDisableTiming));
+  }
+  for (size_t i = 0; i < fields.size(); ++i) {
+    if (!fields[i].host) continue;
+    pinned[i] = is_pinned(fields[i].host);
+    const size_t bytes = (size_t)max_steps * S * fields[i].elem;
+    for (int b = 0; b < NBUF; ++b) {
+      SS_CUDA(cudaMallocAsync(&dev[b][i], bytes, s_copy));
+      if (!pinned[i]) SS_CUDA(cudaHostAlloc((void**)&stage[b][i], bytes, cudaHostAllocDefault));
+    }
+  }
+  SS_CUDA(cudaMallocAsync((void**)&out_dev, (size_t)n_units * n_bus * sizeof(float) + 16, s_copy));
+  SS_CUDA(cudaStreamSynchronize(s_copy));
+
+  {
+    int64_t it = 0;
+    for (int64_t u = 0; u < n_units; u += chunk_units, ++it) {
+      const int b = (int)(it % NBUF);
+      const int64_t e = u + chunk_units < n_units ? u + chunk_units : n_units;
+      const int64_t step0 = ustart(u), nsteps = ustart(e) - ustart(u);
+      // the ring slot is free once the kernel that read it has finished
+      if (it >= NBUF) SS_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+      for (size_t i = 0; i < fields.size(); ++i) {
+        if (!fields[i].host) continue;
+        const size_t off = (size_t)step0 * S * fields[i].elem;
+        const size_t bytes = (size_t)nsteps * S * fields[i].elem;
+        const char* src = fields[i].host + off;
+        if (!pinned[i]) {
+          if (it >= NBUF) SS_CUDA(cudaEventSynchronize(ev_staged[b]));  // staging slot drained
+          std::memcpy(stage[b][i], src, bytes);
+          src = stage[b][i];
+        }
+        SS_CUDA(cudaMemcpyAsync(dev[b][i], src, bytes, cudaMemcpyHostToDevice, s_copy));
+      }
+      SS_CUDA(cudaEventRecord(ev_staged[b], s_copy));
+      SS_CUDA(cudaEventRecord(ev_copied[b], s_copy));
+      SS_CUDA(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
+      rc = launch(dev[b], step0, e - u, out_dev + (size_t)u * n_bus, s_comp);
+      if (rc != ATL_OK) goto cleanup;
+      SS_CUDA(cudaEventRecord(ev_done[b], s_comp));
+    }
+  }
+  SS_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)n_units * n_bus * sizeof(float),
+                          cudaMemcpyDeviceToHost, s_comp));
+  SS_CUDA(cudaStreamSynchronize(s_comp));
+  SS_CUDA(cudaStreamSynchronize(s_copy));
+
+cleanup:
+  if (s_comp) cudaStreamSynchronize(s_comp);
+  if (s_copy) cudaStreamSynchronize(s_copy);
+  for (int b = 0; b < NBUF; ++b) {
+    for (size_t i = 0; i < fields.size(); ++i) {
+      if (dev[b][i]) cudaFreeAsync(dev[b][i], s_copy ? s_copy : 0);
+      if (stage[b][i]) cudaFreeHost(stage[b][i]);
+    }
+    if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
+    if (ev_done[b]) cudaEventDestroy(ev_done[b]);
+    if (ev_staged[b]) cudaEventDestroy(ev_staged[b]);
+  }
+  if (out_dev) cudaFreeAsync(out_dev, s_copy ? s_copy : 0);
+  if (s_copy) {
+    cudaStreamSynchronize(s_copy);
+    cudaStreamDestroy(s_copy);
+  }
+  if (s_comp) cudaStreamDestroy(s_comp);
+#undef SS_CUDA
+  return rc;
+}
+
+}  // namespace atl
+
+using namespace atl;
+
+namespace atl {
+int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const float* temp,
+                     const int32_t* d_days, int32_t base, const int64_t* day_start_host,
+                     int64_t n_days, float* out, cudaStream_t st);
+int heat_upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out, cudaStream_t st);
+}
+
+extern "C" {
+
+int atl_pv_reduce_host(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f,
+                       int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps) {
+  ATL_REQUIRE(op && plan && f, "NULL argument");
+  int32_t device, ny, nx, solar_src;
+  atl_pv_op_info(op, &device, &ny, &nx, &solar_src);
+  const size_t sol_elem = solar_src == ATL_SOLAR_STORED_F64 ? 8 : 4;
+  std::vector<SlabField> fields = {
+      {(const char*)f->influx_toa, 4},     {(const char*)f->influx_direct, 4},
+      {(const char*)f->influx_diffuse, 4}, {(const char*)f->influx, 4},
+      {(const char*)f->albedo, 4},         {(const char*)f->outflux, 4},
+      {(const char*)f->temperature, 4},    {(const char*)f->humidity, 4},
+      {(const char*)f->solar_altitude, sol_elem},
+      {(const char*)f->solar_azimuth, sol_elem}};
+  auto launch = [&](const std::vector<void*>& d, int64_t t_rel, int64_t n, float* out_dev,
+                    cudaStream_t st) {
+    AtlPvFields df;
+    df.influx_toa = (const float*)d[0];
+    df.influx_direct = (const float*)d[1];
+    df.influx_diffuse = (const float*)d[2];
+    df.influx = (const float*)d[3];
+    df.albedo = (const float*)d[4];
+    df.outflux = (const float*)d[5];
+    df.temperature = (const float*)d[6];
+    df.humidity = (const float*)d[7];
+    df.solar_altitude = d[8];
+    df.solar_azimuth = d[9];
+    return atl_pv_reduce(op, plan, &df, t0 + t_rel, n, out_dev, (void*)st);
+  };
+  AtlPlanInfo pi;
+  atl_plan_info(plan, &pi);
+  return stream_slabs(device, fields, (int64_t)ny * nx, nt, nullptr, chunk_steps, pi.n_bus,
+                      out_host, launch);
+}
+
+int atl_wind_reduce_host(const AtlWindOp* op, const AtlPlan* plan, const AtlWindFields* f,
+                         int64_t nt, float* out_host, int64_t chunk_steps) {
+  ATL_REQUIRE(op && plan && f, "NULL argument");
+  int32_t device, ny, nx;
+  atl_wind_op_info(op, &device, &ny, &nx);
+  std::vector<SlabField> fields = {{(const char*)f->wnd, 4}, {(const char*)f->aux, 4}};
+  auto launch = [&](const std::vector<void*>& d, int64_t, int64_t n, float* out_dev,
+                    cudaStream_t st) {
+    AtlWindFields df;
+    df.wnd = (const float*)d[0];
+    df.aux = (const float*)d[1];
+    return atl_wind_reduce(op, plan, &df, n, out_dev, (void*)st);
+  };
+  AtlPlanInfo pi;
+  atl_plan_info(plan, &pi);
+  return stream_slabs(device, fields, (int64_t)ny * nx, nt, nullptr, chunk_steps, pi.n_bus,
+                      out_host, launch);
+}
+
+int atl_heat_reduce_host(const AtlHeatOp* op, const AtlPlan* plan, const float* temperature,
+                         const int64_t* day_start, int64_t n_days, float* out_host,
+                         int64_t chunk_days) {
+  ATL_REQUIRE(op && plan && temperature && day_start, "NULL argument");
+  int32_t device, ny, nx;
+  atl_heat_op_info(op, &device, &ny, &nx);
+  std::vector<SlabField> fields = {{(const char*)temperature, 4}};
+  // one upload of the whole day table; slabs index into it
+  ATL_CUDA(cudaSetDevice(device));
+  int32_t* d_days = nullptr;
+  int rc0 = heat_upload_days(day_start, n_days, &d_days, 0);
+  if (rc0) return rc0;
+  int64_t cursor = 0;  // first day of the slab being launched (slabs are issued in order)
+  auto launch = [&](const std::vector<void*>& d, int64_t, int64_t n, float* out_dev,
+                    cudaStream_t st) {
+    int rc = heat_launch_core(0, op, plan, (const float*)d[0], d_days + cursor,
+                              (int32_t)day_start[cursor], day_start + cursor, n, out_dev, st);
+    cursor += n;
+    return rc;
+  };
+  AtlPlanInfo pi;
+  atl_plan_info(plan, &pi);
+  int rc = stream_slabs(device, fields, (int64_t)ny * nx, n_days, day_start, chunk_days,
+                        pi.n_bus, out_host, launch);
+  cudaFree(d_days);
+  return rc;
+}
+
+}  // extern "C"

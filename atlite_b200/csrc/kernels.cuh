@@ -1,0 +1,188 @@
+// kernels.cuh -- generic "per-cell physics -> {shape reduce | per-cell store |
+// per-cell time sum}" kernels, templated on a physics functor.
+//
+// A physics functor `Phys` provides
+//   struct Cell;   per-thread constants (geometry of the lane's 4 cells)
+//   struct Raw;    the raw field values of one time step (4 cells)
+//   static constexpr int kSmemFloats;        CTA-shared lookup tables
+//   __device__ void stage(float* smem) const;            (whole CTA, before use)
+//   __device__ void init(Cell&, const TileGeom&, const float* smem) const;
+//   __device__ void load(const Cell&, const TileGeom&, int t, Raw&) const;
+//   __device__ void compute(const Cell&, const TileGeom&, int t, const Raw&,
+//                           float (&v)[4], const float* smem) const;
+// `t` is relative to the slab the functor's field pointers address.
+//
+// Loop structure (all three kernels): a warp owns one 32x4 tile and walks a
+// block of `tb` consecutive time steps; the loads of step t+1 are issued
+// before the arithmetic of step t (register double buffer), so each thread
+// keeps 2 x (#fields x 4) independent 128-byte-coalesced loads in flight.
+#pragma once
+#include "common.cuh"
+
+namespace atl {
+
+template <class Phys>
+__global__ void __launch_bounds__(CTA_THREADS)
+    k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
+                   float* __restrict__ out, int nt, int tb) {
+  extern __shared__ float smem[];
+  phys.stage(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ai = blockIdx.x * WARPS_PER_CTA + warp;
+  if (ai >= plan.n_active) return;
+  const int tile = __ldg(plan.active_tiles + ai);
+  const TileGeom g = make_geom(tile, lane, gd);
+  const int s_beg = __ldg(plan.tile_slot_ptr + tile);
+  const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
+  const int t0 = blockIdx.y * tb;
+  const int t1 = min(nt, t0 + tb);
+
+  typename Phys::Cell c;
+  phys.init(c, g, smem);
+  typename Phys::Raw ra, rb;
+  float v[4];
+  phys.load(c, g, t0, ra);
+  for (int t = t0; t < t1; t += 2) {
+    const bool has_b = t + 1 < t1;
+    if (has_b) phys.load(c, g, t + 1, rb);
+    phys.compute(c, g, t, ra, v, smem);
+    reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
+    if (has_b) {
+      if (t + 2 < t1) phys.load(c, g, t + 2, ra);
+      phys.compute(c, g, t + 1, rb, v, smem);
+      reduce_slots(v, s_beg, s_end, plan, out + (size_t)(t + 1) * plan.n_bus, lane);
+    }
+  }
+}
+
+// mode 0: store per-cell values out[(t - t_begin), y, x]
+// mode 1: accumulate the (NaN-skipping) time sum into out[y, x]
+template <class Phys, int MODE>
+__global__ void __launch_bounds__(CTA_THREADS)
+    k_cells(const Phys phys, const GridDev gd, float* __restrict__ out, int t_begin,
+            int t_end, int tb) {
+  extern __shared__ float smem[];
+  phys.stage(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * WARPS_PER_CTA + warp;
+  if (tile >= gd.n_tx * gd.n_ty) return;
+  const TileGeom g = make_geom(tile, lane, gd);
+  const int t0 = t_begin + blockIdx.y * tb;
+  const int t1 = min(t_end, t0 + tb);
+
+  typename Phys::Cell c;
+  phys.init(c, g, smem);
+  typename Phys::Raw ra, rb;
+  float v[4];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  auto emit = [&](int t) {
+    if (MODE == 0) {
+      float* o = out + (int64_t)(t - t_begin) * gd.S + g.base;
+#pragma unroll
+      for (int r = 0; r < TILE_Y; ++r)
+        if ((g.valid >> r) & 1u) o[r * gd.nx] = v[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < TILE_Y; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
+    }
+  };
+  phys.load(c, g, t0, ra);
+  for (int t = t0; t < t1; t += 2) {
+    const bool has_b = t + 1 < t1;
+    if (has_b) phys.load(c, g, t + 1, rb);
+    phys.compute(c, g, t, ra, v, smem);
+    emit(t);
+    if (has_b) {
+      if (t + 2 < t1) phys.load(c, g, t + 2, ra);
+      phys.compute(c, g, t + 1, rb, v, smem);
+      emit(t + 1);
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int r = 0; r < TILE_Y; ++r)
+      if ((g.valid >> r) & 1u) atomicAdd(out + g.base + r * gd.nx, acc[r]);
+  }
+}
+
+// Generic CSR gather SpMM: out[t, row] = sum_k val[k] * dense[t, col[k]]
+// (aggregate.py:24-32 on an already materialised field).  One warp per
+// (row, t); used for plans that do not tile well and as second pass of the
+// two-pass fallback.
+__global__ void k_csr_spmm(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                           const float* __restrict__ val, const float* __restrict__ dense,
+                           int64_t S, float* __restrict__ out, int n_bus, int nt);
+
+inline int pick_tb(int n_cta_x, int64_t nt) {
+  // aim for >= ~8 waves of 148 SMs x 4 resident CTAs, but keep per-CTA
+  // prologue (geometry + slot setup) amortised over >= 8 steps
+  const int64_t want = 148LL * 4 * 8;
+  int64_t tb = (nt * n_cta_x + want - 1) / want;
+  if (tb < 8) tb = 8;
+  if (tb > 64) tb = 64;
+  tb += tb & 1;
+  if (tb > nt) tb = nt > 0 ? nt : 1;
+  return (int)tb;
+}
+
+template <class Phys>
+int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begin,
+                 int64_t t_end, bool timesum, cudaStream_t st) {
+  if (t_end <= t_begin) return ATL_OK;
+  const int n_tiles = gd.n_tx * gd.n_ty;
+  const int gx = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const int tb = pick_tb(gx, t_end - t_begin);
+  const int gy = (int)((t_end - t_begin + tb - 1) / tb);
+  dim3 grid(gx, gy);
+  const size_t smem = Phys::kSmemFloats * sizeof(float);
+  if (timesum)
+    k_cells<Phys, 1><<<grid, CTA_THREADS, smem, st>>>(phys, gd, out, (int)t_begin, (int)t_end, tb);
+  else
+    k_cells<Phys, 0><<<grid, CTA_THREADS, smem, st>>>(phys, gd, out, (int)t_begin, (int)t_end, tb);
+  ++g_launches;
+  ATL_CUDA(cudaGetLastError());
+  return ATL_OK;
+}
+
+int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* out,
+                    cudaStream_t st);
+
+template <class Phys>
+int launch_reduce(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt,
+                  cudaStream_t st) {
+  if (nt <= 0) return ATL_OK;
+  ATL_REQUIRE(nt < (1LL << 31), "slab too long");
+  if (plan->fused) {
+    ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * plan->n_bus * sizeof(float), st));
+    if (plan->n_active == 0) return ATL_OK;
+    const int gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int tb = pick_tb(gx, nt);
+    dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
+    k_fused_reduce<Phys><<<grid, CTA_THREADS, Phys::kSmemFloats * sizeof(float), st>>>(
+        phys, plan->grid, plan->dev(), out, (int)nt, tb);
+    ++g_launches;
+    ATL_CUDA(cudaGetLastError());
+    return ATL_OK;
+  }
+  // Two-pass fallback for matrices that do not tile (e.g. one bus per cell):
+  // materialise a block of per-cell values, then CSR-gather it.
+  const int64_t S = plan->grid.S;
+  int64_t blk = (256LL << 20) / (S * 4);  // <= 256 MiB scratch
+  if (blk < 1) blk = 1;
+  if (blk > nt) blk = nt;
+  float* scratch = nullptr;
+  ATL_CUDA(cudaMallocAsync((void**)&scratch, (size_t)blk * S * sizeof(float), st));
+  for (int64_t t = 0; t < nt; t += blk) {
+    const int64_t n = (nt - t < blk) ? nt - t : blk;
+    int rc = launch_cells(phys, plan->grid, scratch, t, t + n, false, st);
+    if (rc == ATL_OK) rc = launch_csr_spmm(plan, scratch, n, out + (size_t)t * plan->n_bus, st);
+    if (rc != ATL_OK) {
+      cudaFreeAsync(scratch, st);
+      return rc;
+    }
+  }
+  ATL_CUDA(cudaFreeAsync(scratch, st));
+  return ATL_OK;
+}
+
+}  // namespace atl

@@ -1,0 +1,277 @@
+// plan.cu -- error plumbing, aggregation-plan construction and the generic SpMM.
+//
+// The reference turns `matrix | shapes | layout` into ONE scipy CSR matrix
+// (convert.py:213-254) and multiplies every dense (time, spatial) block by its
+// transpose (aggregate.py:24-32).  Here the CSR is re-tiled once into
+// (tile, bus) "slots": for every 32x4-cell warp tile the distinct buses that
+// touch it, each with a dense 128-entry weight vector.  The fused kernels then
+// reduce the per-cell values of a tile into its slots with warp shuffles and
+// one atomicAdd per (slot, time step) -- per-cell values never reach HBM.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace atl {
+
+static thread_local std::string g_err;
+int64_t g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return ATL_ERR_CUDA;
+}
+
+__global__ void k_csr_spmm(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                           const float* __restrict__ val, const float* __restrict__ dense,
+                           int64_t S, float* __restrict__ out, int n_bus, int nt) {
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y * (blockDim.x >> 5) + warp;
+  if (t >= nt) return;
+  const int64_t b = indptr[row], e = indptr[row + 1];
+  const float* d = dense + (int64_t)t * S;
+  float acc = 0.f;
+  for (int64_t k = b + lane; k < e; k += 32) acc = fmaf(val[k], d[idx[k]], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[(size_t)t * n_bus + row] = acc;
+}
+
+int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* out,
+                    cudaStream_t st) {
+  if (nt <= 0 || plan->n_bus == 0) return ATL_OK;
+  const int wpb = 8;
+  for (int64_t t = 0; t < nt; t += 65535LL * wpb) {
+    const int64_t n = std::min<int64_t>(nt - t, 65535LL * wpb);
+    dim3 grid(plan->n_bus, (unsigned)((n + wpb - 1) / wpb));
+    k_csr_spmm<<<grid, 32 * wpb, 0, st>>>(plan->d_indptr, plan->d_indices, plan->d_vals,
+                                          dense + t * plan->grid.S, plan->grid.S,
+                                          out + (size_t)t * plan->n_bus, plan->n_bus, (int)n);
+    ++g_launches;
+    ATL_CUDA(cudaGetLastError());
+  }
+  return ATL_OK;
+}
+
+// Identity physics: the "field" already is the per-cell value (unknown
+// convert_func evaluated upstream) -> fused tile SpMM.
+struct IdentityPhys {
+  const float* f;
+  int64_t S;
+  int nx;
+  struct Cell {};
+  struct Raw {
+    float v[4];
+  };
+  static constexpr int kSmemFloats = 0;
+  __device__ void stage(float*) const {}
+  __device__ void init(Cell&, const TileGeom&, const float*) const {}
+  __device__ void load(const Cell&, const TileGeom& g, int t, Raw& r) const {
+    load4(f, S, nx, g, t, r.v);
+  }
+  __device__ void compute(const Cell&, const TileGeom&, int, const Raw& r, float (&v)[4],
+                          const float*) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = r.v[i];
+  }
+};
+
+}  // namespace atl
+
+using namespace atl;
+
+extern "C" {
+
+int atl_abi_version(void) { return ATL_ABI_VERSION; }
+const char* atl_last_error(void) { return g_err.c_str(); }
+int64_t atl_launch_count(void) { return g_launches; }
+
+int atl_device_count(int* count_out) {
+  ATL_REQUIRE(count_out, "count_out is NULL");
+  *count_out = 0;
+  ATL_CUDA(cudaGetDeviceCount(count_out));
+  return ATL_OK;
+}
+
+int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
+                    const int64_t* indptr, const int32_t* indices, const double* data,
+                    AtlPlan** plan_out) {
+  ATL_REQUIRE(plan_out, "plan_out is NULL");
+  *plan_out = nullptr;
+  ATL_REQUIRE(ny > 0 && nx > 0 && n_bus >= 0, "bad plan shape");
+  ATL_REQUIRE((int64_t)ny * nx < (1LL << 31), "grid too large (ny*nx must fit int32)");
+  ATL_REQUIRE(indptr && (n_bus == 0 || indptr[n_bus] == 0 || (indices && data)),
+              "CSR arrays missing");
+  const GridDev gd = make_grid(ny, nx);
+  const int64_t nnz_in = n_bus ? indptr[n_bus] : 0;
+  const int64_t n_tiles = (int64_t)gd.n_tx * gd.n_ty;
+
+  // (tile, bus) key of every stored entry
+  struct Ent {
+    int64_t key;
+    int32_t local;  // lane * 4 + row-in-tile
+    float w;
+  };
+  std::vector<Ent> ents;
+  ents.reserve((size_t)nnz_in);
+  for (int32_t r = 0; r < n_bus; ++r) {
+    ATL_REQUIRE(indptr[r + 1] >= indptr[r], "indptr not monotone");
+    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+      const int32_t c = indices[k];
+      ATL_REQUIRE(c >= 0 && c < gd.S, "column index out of range");
+      const int iy = c / nx, ix = c - iy * nx;
+      const int64_t tile = (int64_t)(iy / TILE_Y) * gd.n_tx + ix / TILE_X;
+      Ent e;
+      e.key = tile * (int64_t)n_bus + r;
+      e.local = (ix % TILE_X) * TILE_Y + (iy % TILE_Y);
+      e.w = (float)data[k];
+      ents.push_back(e);
+    }
+  }
+  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.key < b.key; });
+
+  std::vector<int32_t> tile_slot_ptr((size_t)n_tiles + 1, 0);
+  std::vector<int32_t> slot_row;
+  int64_t n_slots = 0;
+  {
+    int64_t prev = -1;
+    for (const Ent& e : ents)
+      if (e.key != prev) {
+        prev = e.key;
+        ++n_slots;
+      }
+  }
+  ATL_REQUIRE(n_slots < (1LL << 31) / 1, "too many (tile,bus) slots");
+  // A matrix "tiles well" when the padded slot work is within a small factor
+  // of nnz; otherwise (e.g. one bus per cell) use the two-pass CSR path.
+  int64_t n_active = 0;
+  {
+    int64_t prev_tile = -1;
+    for (const Ent& e : ents) {
+      const int64_t tile = e.key / std::max<int64_t>(n_bus, 1);
+      if (tile != prev_tile) {
+        prev_tile = tile;
+        ++n_active;
+      }
+    }
+  }
+  const double spt = n_active ? (double)n_slots / (double)n_active : 0.0;
+  const bool fused = spt <= 24.0 && (double)n_slots * TILE_CELLS * 4.0 <= 4.0e9;
+
+  AtlPlan* p = new AtlPlan();
+  p->device = device;
+  p->grid = gd;
+  p->n_bus = n_bus;
+  p->nnz = nnz_in;
+  p->n_tiles = (int32_t)n_tiles;
+  p->n_active = (int32_t)n_active;
+  p->n_slots = n_slots;
+  p->fused = fused;
+
+  auto fail = [&](int rc) {
+    atl_plan_destroy(p);
+    return rc;
+  };
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(cuda_fail(ce, "cudaSetDevice"));
+
+#define PLAN_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t _e = (call);                              \
+    if (_e != cudaSuccess) return fail(cuda_fail(_e, #call)); \
+  } while (0)
+
+  if (fused) {
+    slot_row.resize((size_t)n_slots);
+    std::vector<float> w((size_t)n_slots * TILE_CELLS, 0.f);
+    std::vector<int32_t> active;
+    active.reserve((size_t)n_active);
+    int64_t s = -1, prev = -1, prev_tile = -1;
+    for (const Ent& e : ents) {
+      if (e.key != prev) {
+        prev = e.key;
+        ++s;
+        const int64_t tile = e.key / n_bus;
+        slot_row[(size_t)s] = (int32_t)(e.key - tile * n_bus);
+        tile_slot_ptr[(size_t)tile + 1]++;
+        if (tile != prev_tile) {
+          prev_tile = tile;
+          active.push_back((int32_t)tile);
+        }
+      }
+      w[(size_t)s * TILE_CELLS + e.local] += e.w;  // duplicates sum (csr_matrix semantics)
+    }
+    for (int64_t t = 0; t < n_tiles; ++t) tile_slot_ptr[(size_t)t + 1] += tile_slot_ptr[(size_t)t];
+    PLAN_CUDA(cudaMalloc((void**)&p->d_tile_slot_ptr, tile_slot_ptr.size() * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_tile_slot_ptr, tile_slot_ptr.data(), tile_slot_ptr.size() * 4,
+                         cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_row, std::max<size_t>(slot_row.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_slot_row, slot_row.data(), slot_row.size() * 4,
+                         cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, std::max<size_t>(w.size(), 4) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_slot_w4, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(active.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_active, active.data(), active.size() * 4,
+                         cudaMemcpyHostToDevice));
+  }
+  {
+    // CSR copy (float weights) for the gather SpMM
+    std::vector<float> vals((size_t)nnz_in);
+    for (int64_t k = 0; k < nnz_in; ++k) vals[(size_t)k] = (float)data[k];
+    PLAN_CUDA(cudaMalloc((void**)&p->d_indptr, ((size_t)n_bus + 1) * 8));
+    PLAN_CUDA(cudaMemcpy(p->d_indptr, indptr, ((size_t)n_bus + 1) * 8, cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_indices, std::max<size_t>((size_t)nnz_in, 1) * 4));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_vals, std::max<size_t>((size_t)nnz_in, 1) * 4));
+    if (nnz_in) {
+      PLAN_CUDA(cudaMemcpy(p->d_indices, indices, (size_t)nnz_in * 4, cudaMemcpyHostToDevice));
+      PLAN_CUDA(cudaMemcpy(p->d_vals, vals.data(), (size_t)nnz_in * 4, cudaMemcpyHostToDevice));
+    }
+  }
+#undef PLAN_CUDA
+  *plan_out = p;
+  return ATL_OK;
+}
+
+int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info) {
+  ATL_REQUIRE(plan && info, "NULL argument");
+  info->ny = plan->grid.ny;
+  info->nx = plan->grid.nx;
+  info->n_bus = plan->n_bus;
+  info->nnz = plan->nnz;
+  info->n_tiles = plan->n_tiles;
+  info->n_active_tiles = plan->n_active;
+  info->n_slots = plan->n_slots;
+  info->slots_per_active_tile = plan->n_active ? (double)plan->n_slots / plan->n_active : 0.0;
+  info->fused = plan->fused ? 1 : 0;
+  return ATL_OK;
+}
+
+void atl_plan_destroy(AtlPlan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_tile_slot_ptr);
+  cudaFree(p->d_slot_row);
+  cudaFree(p->d_slot_w4);
+  cudaFree(p->d_active);
+  cudaFree(p->d_indptr);
+  cudaFree(p->d_indices);
+  cudaFree(p->d_vals);
+  delete p;
+}
+
+int atl_spmm(const AtlPlan* plan, const float* dense_dev, int64_t nt, float* out_dev,
+             void* stream) {
+  ATL_REQUIRE(plan && dense_dev && out_dev, "NULL argument");
+  ATL_CUDA(cudaSetDevice(plan->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!plan->fused) return launch_csr_spmm(plan, dense_dev, nt, out_dev, st);
+  IdentityPhys ph;
+  ph.f = dense_dev;
+  ph.S = plan->grid.S;
+  ph.nx = plan->grid.nx;
+  return launch_reduce(ph, plan, out_dev, nt, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// pv.cu -- fused PV conversion: SolarPosition -> SurfaceOrientation ->
+// TiltedIrradiation -> SolarPanelModel -> shape reduce  (convert.py:840-854).
+//
+// Algorithmic traffic (ERA5 branch, solar position computed in-kernel):
+// 5 float32 fields = 20 B per cell-timestep.
+//
+// Solar geometry is SEPARABLE (pv/solar_position.py:86-114): everything except
+// cos/sin of the hour angle h = H0(t) + lon(x) depends on time only.  The host
+// evaluates the almanac in float64 once per time step and ships
+//     tt[t] = { sin dec, cos dec, cos H0, sin H0 }
+// with H0 = radians(lmst without lon) - ra; per column xt[x] = {cos lon, sin lon};
+// per row yt[y] = {sin lat, cos lat, cos slope, sin slope, cos saz, sin saz,
+// sin^3(slope/2)}.  Per cell the kernel then needs NO transcendental for the
+// geometry:
+//     cos h = cH0 coslon - sH0 sinlon,  sin h = sH0 coslon + cH0 sinlon
+//     sinalt            = sd sl + cd cl cos h                   (:103-105)
+//     X = cosalt cos az = sd cl - cd sl cos h                   (:109-113)
+//     Y = cosalt sin az = -cd sin h                             (:114, sign of h)
+// and every orientation / tracking formula of pv/orientation.py:114-176 is a
+// polynomial/sqrt expression in (sinalt, cosalt, X, Y) (derivations inline).
+#include <cmath>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace atl {
+
+enum {  // panel coefficient slots (float, device)
+  PC_C_AMB = 0, PC_C_IRR, PC_R_TMOD, PC_INV_R_IRR, PC_K1, PC_K2, PC_K3, PC_K4, PC_K5, PC_K6,
+  PC_INV_EFF,
+  // bofinger
+  PC_A = 0, PC_B, PC_C, PC_D, PC_FRACTION, PC_TSTD, PC_DEN, PC_SCALE, PC_THRESHOLD
+};
+
+// FAST = the ERA5 default configuration compiled to constants: fixed panel
+// (tracking None), solar position computed in-kernel, influx_direct +
+// influx_diffuse + albedo variables.  FAST=false keeps every switch at run
+// time (stored solar position, Reindl split, outflux albedo, tracking modes).
+template <bool FAST>
+struct PvPhys {
+  const float *toa, *dir, *dif, *influx, *alb, *outflux, *temp, *hum;
+  const void *salt, *saz;
+  const float4* tt;  // per time step (absolute index t_off + t)
+  const float2* xt;  // per column
+  const float* yt;   // per row, 8 floats
+  int64_t S;
+  int nx;
+  int t_off;
+  int tracking_, trigon, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model;
+  float sin_thr;
+  float pc[12];
+
+  __device__ __forceinline__ int tracking() const { return FAST ? ATL_TRACK_NONE : tracking_; }
+  __device__ __forceinline__ int irr_branch() const {
+    return FAST ? ATL_IRR_DIRECT_DIFFUSE : irr_branch_;
+  }
+  __device__ __forceinline__ int albedo_src() const { return FAST ? ATL_ALBEDO_VAR : albedo_src_; }
+  __device__ __forceinline__ int solar_src() const { return FAST ? ATL_SOLAR_COMPUTED : solar_src_; }
+
+  struct Cell {
+    float clon, slon;
+    float sl[4], cl[4], cs[4], ss[4], cph[4], sph[4], hd3[4];
+  };
+  struct Raw {
+    float toa[4], a[4], b[4], alb[4], temp[4], hum[4], salt[4], saz[4];
+  };
+  static constexpr int kSmemFloats = 0;
+  __device__ void stage(float*) const {}
+
+  __device__ void init(Cell& c, const TileGeom& g, const float*) const {
+    const float2 xl = g.x < nx ? __ldg(xt + g.x) : make_float2(1.f, 0.f);
+    c.clon = xl.x;
+    c.slon = xl.y;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if ((g.valid >> r) & 1u) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(yt) + 2 * (g.y0 + r));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(yt) + 2 * (g.y0 + r) + 1);
+        c.sl[r] = a.x; c.cl[r] = a.y; c.cs[r] = a.z; c.ss[r] = a.w;
+        c.cph[r] = b.x; c.sph[r] = b.y; c.hd3[r] = b.z;
+      } else {
+        c.sl[r] = 0.f; c.cl[r] = 1.f; c.cs[r] = 1.f; c.ss[r] = 0.f;
+        c.cph[r] = 1.f; c.sph[r] = 0.f; c.hd3[r] = 0.f;
+      }
+    }
+  }
+
+  __device__ void load(const Cell&, const TileGeom& g, int t, Raw& r) const {
+    load4(toa, S, nx, g, t, r.toa);
+    if (irr_branch() == ATL_IRR_DIRECT_DIFFUSE) {
+      load4(dir, S, nx, g, t, r.a);
+      load4(dif, S, nx, g, t, r.b);
+    } else {
+      load4(influx, S, nx, g, t, r.a);
+      if (clearsky == ATL_CLEARSKY_ENHANCED) load4(hum, S, nx, g, t, r.hum);
+    }
+    load4(albedo_src() == ATL_ALBEDO_VAR ? alb : outflux, S, nx, g, t, r.alb);
+    load4(temp, S, nx, g, t, r.temp);
+    if (solar_src() == ATL_SOLAR_STORED_F32) {
+      load4((const float*)salt, S, nx, g, t, r.salt);
+      load4((const float*)saz, S, nx, g, t, r.saz);
+    } else if (solar_src() == ATL_SOLAR_STORED_F64) {
+      load4((const double*)salt, S, nx, g, t, r.salt);
+      load4((const double*)saz, S, nx, g, t, r.saz);
+    }
+  }
+
+  // pv/solar_panel_model.py:12-44 (huld), 47-74 (bofinger)
+  __device__ __forceinline__ float panel(float G, float T) const {
+    if (panel_model == ATL_PANEL_HULD) {
+      const float T_ = fmaf(pc[PC_C_AMB], T, fmaf(pc[PC_C_IRR], G, -pc[PC_R_TMOD]));
+      const float G_ = G * pc[PC_INV_R_IRR];
+      const float lg = __logf(G_);  // G_ <= 0 -> -inf/NaN -> eff NaN/-inf -> 0 below
+      const float p1 = fmaf(fmaf(pc[PC_K2], lg, pc[PC_K1]), lg, 1.f);
+      const float p2 = fmaf(fmaf(pc[PC_K5], lg, pc[PC_K4]), lg, pc[PC_K3]);
+      float eff = fmaf(T_, fmaf(pc[PC_K6], T_, p2), p1);
+      eff = (G_ > 0.f) ? fmaxf(eff, 0.f) : 0.f;  // .where(G_>0) .. fillna(0).clip(min=0)
+      return G_ * eff * pc[PC_INV_EFF];
+    } else {
+      const float eta_ref = fmaf(pc[PC_B], G, fmaf(pc[PC_C], __logf(G), pc[PC_A]));
+      float eta = eta_ref * fmaf(pc[PC_D], fmaf(pc[PC_FRACTION], G, T - pc[PC_TSTD]), 1.f) /
+                  fmaf(pc[PC_DEN] * eta_ref, G, 1.f);
+      eta = (G != 0.f && eta == eta) ? eta : 0.f;  // log(where(G != 0)) -> NaN -> fillna(0)
+      const float power = G * eta * pc[PC_SCALE];
+      return (G >= pc[PC_THRESHOLD]) ? power : 0.f;
+    }
+  }
+
+  __device__ void compute(const Cell& c, const TileGeom& g, int t, const Raw& r, float (&v)[4],
+                          const float*) const {
+    float sd = 0.f, cd = 0.f, ch = 0.f, sh = 0.f;
+    if (solar_src() == ATL_SOLAR_COMPUTED) {
+      const float4 q = __ldg(tt + t_off + t);
+      sd = q.x;
+      cd = q.y;
+      ch = q.z * c.clon - q.w * c.slon;
+      sh = q.w * c.clon + q.z * c.slon;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // ---- solar position (pv/solar_position.py:103-114)
+      float sinalt, cosalt, X, Y;
+      if (solar_src() == ATL_SOLAR_COMPUTED) {
+        sinalt = fminf(fmaxf(fmaf(cd * c.cl[i], ch, sd * c.sl[i]), -1.f), 1.f);
+        X = fmaf(-(cd * c.sl[i]), ch, sd * c.cl[i]);
+        Y = -cd * sh;
+        cosalt = sqrtf(fmaxf(fmaf(-sinalt, sinalt, 1.f), 0.f));
+      } else {
+        float saz_s, saz_c;
+        sincosf(r.salt[i], &sinalt, &cosalt);
+        sincosf(r.saz[i], &saz_s, &saz_c);
+        X = cosalt * saz_c;
+        Y = cosalt * saz_s;
+      }
+      // ---- surface orientation (pv/orientation.py:114-188)
+      float cosinc, cslope;  // cos(incidence), cos(surface slope)
+      const int trk = tracking();
+      if (trk == ATL_TRACK_NONE) {
+        // sin b cos a cos(phi - az) + cos b sin a, with cos a cos az = X, cos a sin az = Y
+        cosinc = fmaf(c.ss[i], fmaf(c.cph[i], X, c.sph[i] * Y), c.cs[i] * sinalt);
+        cslope = c.cs[i];
+      } else if (trk == ATL_TRACK_VERTICAL) {
+        cosinc = fmaf(c.ss[i], cosalt, c.cs[i] * sinalt);
+        cslope = c.cs[i];
+      } else if (trk == ATL_TRACK_DUAL) {
+        cosinc = 1.f;
+        cslope = (trigon == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[i];  // irradiation.py:216-219
+      } else {
+        // q = cos a sin(az - phi), p = cos a cos(az - phi)
+        const float q = fmaf(Y, c.cph[i], -X * c.sph[i]);
+        if (trk == ATL_TRACK_HORIZONTAL) {
+          // rotation = atan(q / sinalt); slope = |rotation|; the panel azimuth is
+          // phi + sign(rotation) pi/2, so cosinc = sign(sinalt) sqrt(sinalt^2 + q^2)
+          const float D = sqrtf(fmaf(sinalt, sinalt, q * q));
+          cosinc = sinalt > 0.f ? D : 0.f;
+          cslope = __fdividef(fabsf(sinalt), D);
+        } else {  // tilted_horizontal: rotation = atan2(q, den) after the +-pi fix-ups
+          const float p = fmaf(X, c.cph[i], Y * c.sph[i]);
+          const float den = fmaf(p, c.ss[i], sinalt * c.cs[i]);
+          const float E = sqrtf(fmaf(q, q, den * den));
+          cosinc = E;  // cos(rot) den + sin(rot) q
+          cslope = __fdividef(fabsf(den) * c.cs[i], E);
+        }
+      }
+      cosinc = fmaxf(cosinc, 0.f);  // :188
+
+      // ---- irradiation split (pv/irradiation.py:198-208, 13-73)
+      const float toa_ = r.toa[i];
+      float direct, diffuse;
+      if (irr_branch() == ATL_IRR_DIRECT_DIFFUSE) {
+        direct = fminf(fmaxf(r.a[i], 0.f), toa_);
+        diffuse = fminf(fmaxf(r.b[i], 0.f), toa_ - direct);
+      } else {
+        const float inf_ = fminf(fmaxf(r.a[i], 0.f), toa_);
+        const float k = inf_ / toa_;  // 0/0 -> NaN -> fraction 0
+        float fr = 0.f;
+        if (clearsky == ATL_CLEARSKY_SIMPLE) {
+          if (k > 0.f && k <= 0.3f)
+            fr = fminf(1.f, 1.020f - 0.254f * k + 0.0123f * sinalt);
+          else if (k > 0.3f && k < 0.78f)
+            fr = fminf(0.97f, fmaxf(0.1f, 1.400f - 1.749f * k + 0.177f * sinalt));
+          else if (k >= 0.78f)
+            fr = fmaxf(0.1f, 0.486f * k - 0.182f * sinalt);
+        } else {
+          const float T = r.temp[i], rh = r.hum[i];
+          if (k > 0.f && k <= 0.3f)
+            fr = fminf(1.f, 1.000f - 0.232f * k + 0.0239f * sinalt - 0.000682f * T + 0.0195f * rh);
+          else if (k > 0.3f && k < 0.78f)
+            fr = fminf(0.97f, fmaxf(0.1f, 1.329f - 1.716f * k + 0.267f * sinalt - 0.00357f * T +
+                                              0.106f * rh));
+          else if (k >= 0.78f)
+            fr = fmaxf(0.1f, 0.426f * k - 0.256f * sinalt + 0.00349f * T + 0.0734f * rh);
+        }
+        diffuse = inf_ * fr;
+        direct = inf_ - diffuse;
+      }
+      const float influx_ = direct + diffuse;
+      float albedo;
+      if (albedo_src() == ATL_ALBEDO_VAR) {
+        albedo = r.alb[i];
+      } else {  // (outflux / influx.where(influx != 0)).fillna(0).clip(max=1)  :132
+        const float a = r.alb[i] / influx_;
+        albedo = (influx_ != 0.f && a == a) ? fminf(a, 1.f) : 0.f;
+      }
+
+      // ---- tilted irradiation (pv/irradiation.py:214-236, 76-125, 142-145)
+      const float Rb = __fdividef(cosinc, sinalt);
+      float total;
+      if (trigon == ATL_TRIGON_SIMPLE) {
+        total = fmaf(Rb, direct,
+                     fmaf(fmaf(0.5f, cslope, 0.5f), diffuse,
+                          albedo * influx_ * fmaf(-0.5f, cslope, 0.5f)));
+      } else {
+        float hd3 = c.hd3[i];
+        if (trk == ATL_TRACK_HORIZONTAL || trk == ATL_TRACK_TILTED_HORIZONTAL) {
+          const float s2 = sqrtf(fmaxf(fmaf(-0.5f, cslope, 0.5f), 0.f));  // sin(slope/2)
+          hd3 = s2 * s2 * s2;
+        }
+        const float f = influx_ > 0.f ? sqrtf(__fdividef(direct, influx_)) : 0.f;
+        const float A = direct / toa_;
+        float dt = fmaf(A, Rb, (1.f - A) * fmaf(0.5f, cslope, 0.5f) * fmaf(f, hd3, 1.f)) * diffuse;
+        dt = fmaxf(dt, 0.f);  // clip(min=0).fillna(0): fmaxf drops NaN
+        total = fmaf(Rb, direct, dt) + influx_ * albedo * fmaf(-0.5f, cslope, 0.5f);
+      }
+      // altitude / darkness mask  :251-252
+      const bool masked = (sinalt < sin_thr) || (influx_ <= 0.01f);
+      const float G = masked ? 0.f : total;
+      const float pw = panel(G, r.temp[i]);
+      v[i] = ((g.valid >> i) & 1u) ? pw : 0.f;
+    }
+  }
+};
+
+}  // namespace atl
+
+using namespace atl;
+
+struct AtlPvOp {
+  int device;
+  GridDev grid;
+  int64_t nt;
+  int tracking, trigon, clearsky, irr_branch, albedo_src, solar_src, panel_model;
+  float sin_thr;
+  float pc[12];
+  float4* d_tt = nullptr;
+  float2* d_xt = nullptr;
+  float* d_yt = nullptr;
+  bool fast;
+};
+
+template <bool FAST>
+static PvPhys<FAST> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t0) {
+  PvPhys<FAST> p;
+  p.toa = f->influx_toa;
+  p.dir = f->influx_direct;
+  p.dif = f->influx_diffuse;
+  p.influx = f->influx;
+  p.alb = f->albedo;
+  p.outflux = f->outflux;
+  p.temp = f->temperature;
+  p.hum = f->humidity;
+  p.salt = f->solar_altitude;
+  p.saz = f->solar_azimuth;
+  p.tt = op->d_tt;
+  p.xt = op->d_xt;
+  p.yt = op->d_yt;
+  p.S = op->grid.S;
+  p.nx = op->grid.nx;
+  p.t_off = (int)t0;
+  p.tracking_ = op->tracking;
+  p.trigon = op->trigon;
+  p.clearsky = op->clearsky;
+  p.irr_branch_ = op->irr_branch;
+  p.albedo_src_ = op->albedo_src;
+  p.solar_src_ = op->solar_src;
+  p.panel_model = op->panel_model;
+  p.sin_thr = op->sin_thr;
+  for (int i = 0; i < 12; ++i) p.pc[i] = op->pc[i];
+  return p;
+}
+
+static int check(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt) {
+  ATL_REQUIRE(op && f, "NULL argument");
+  ATL_REQUIRE(t0 >= 0 && nt >= 0 && t0 + nt <= op->nt, "slab outside the operator's time axis");
+  ATL_REQUIRE(f->influx_toa && f->temperature, "influx_toa / temperature field missing");
+  if (op->irr_branch == ATL_IRR_DIRECT_DIFFUSE)
+    ATL_REQUIRE(f->influx_direct && f->influx_diffuse,
+                "Need either influx or influx_direct and influx_diffuse in the dataset.");
+  else {
+    ATL_REQUIRE(f->influx, "influx field missing");
+    if (op->clearsky == ATL_CLEARSKY_ENHANCED) ATL_REQUIRE(f->humidity, "humidity field missing");
+  }
+  if (op->albedo_src == ATL_ALBEDO_VAR)
+    ATL_REQUIRE(f->albedo, "Need either albedo or outflux as a variable in the dataset.");
+  else
+    ATL_REQUIRE(f->outflux, "outflux field missing");
+  if (op->solar_src != ATL_SOLAR_COMPUTED)
+    ATL_REQUIRE(f->solar_altitude && f->solar_azimuth, "stored solar position fields missing");
+  return ATL_OK;
+}
+
+extern "C" {
+
+int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
+  ATL_REQUIRE(cfg && op_out, "NULL argument");
+  *op_out = nullptr;
+  ATL_REQUIRE(cfg->ny > 0 && cfg->nx > 0 && cfg->nt >= 0, "bad shape");
+  ATL_REQUIRE(cfg->lon_deg && cfg->lat_deg && cfg->slope_rad && cfg->azimuth_rad,
+              "coordinate / orientation tables missing");
+  ATL_REQUIRE(cfg->solar_src != ATL_SOLAR_COMPUTED || cfg->time_ns || cfg->nt == 0,
+              "time axis missing");
+  ATL_REQUIRE(cfg->tracking >= 0 && cfg->tracking <= ATL_TRACK_DUAL, "bad tracking mode");
+  ATL_REQUIRE(cfg->trigon_model >= 0 && cfg->trigon_model <= 1, "bad trigon model");
+  ATL_REQUIRE(cfg->clearsky_model >= 0 && cfg->clearsky_model <= 1,
+              "`clearsky model` must be chosen from 'simple' and 'enhanced'");
+  ATL_REQUIRE(cfg->irr_branch >= 0 && cfg->irr_branch <= 1, "bad irradiation branch");
+  ATL_REQUIRE(cfg->albedo_src >= 0 && cfg->albedo_src <= 1, "bad albedo source");
+  ATL_REQUIRE(cfg->solar_src >= 0 && cfg->solar_src <= 2, "bad solar source");
+  ATL_REQUIRE(cfg->panel_model >= 0 && cfg->panel_model <= 1, "Unknown panel model");
+
+  const double PI = 3.14159265358979323846;
+  const double D2R = PI / 180.0;
+  AtlPvOp* op = new AtlPvOp();
+  op->device = device;
+  op->grid = make_grid(cfg->ny, cfg->nx);
+  op->nt = cfg->nt;
+  op->tracking = cfg->tracking;
+  op->trigon = cfg->trigon_model;
+  op->clearsky = cfg->clearsky_model;
+  op->irr_branch = cfg->irr_branch;
+  op->albedo_src = cfg->albedo_src;
+  op->solar_src = cfg->solar_src;
+  op->panel_model = cfg->panel_model;
+  op->sin_thr = (float)std::sin(cfg->altitude_threshold_deg * D2R);
+  op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
+             cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR;
+  const double* P = cfg->panel;
+  for (int i = 0; i < 12; ++i) op->pc[i] = 0.f;
+  if (cfg->panel_model == ATL_PANEL_HULD) {
+    op->pc[PC_C_AMB] = (float)P[0];
+    op->pc[PC_C_IRR] = (float)P[1];
+    op->pc[PC_R_TMOD] = (float)P[2];
+    op->pc[PC_INV_R_IRR] = (float)(1.0 / P[3]);
+    for (int k = 0; k < 6; ++k) op->pc[PC_K1 + k] = (float)P[4 + k];
+    op->pc[PC_INV_EFF] = (float)P[10];
+  } else {
+    // A, B, C, D, NOCT, Tamb, Intc, Tstd, ta, threshold, inverter_efficiency
+    const double A = P[0], B = P[1], C = P[2], D = P[3], NOCT = P[4], Tamb = P[5], Intc = P[6],
+                 Tstd = P[7], ta = P[8], thr = P[9], inv = P[10];
+    const double fraction = (NOCT - Tamb) / Intc;
+    const double capacity = (A + B * 1000.0 + C * std::log(1000.0)) * 1e3;
+    op->pc[PC_A] = (float)A;
+    op->pc[PC_B] = (float)B;
+    op->pc[PC_C] = (float)C;
+    op->pc[PC_D] = (float)D;
+    op->pc[PC_FRACTION] = (float)fraction;
+    op->pc[PC_TSTD] = (float)Tstd;
+    op->pc[PC_DEN] = (float)(D * fraction / ta);
+    op->pc[PC_SCALE] = (float)(inv / capacity);
+    op->pc[PC_THRESHOLD] = (float)thr;
+  }
+
+  // ---- per-time-step almanac (pv/solar_position.py:71-97), float64 on host
+  std::vector<float4> tt((size_t)std::max<int64_t>(cfg->nt, 1));
+  if (cfg->time_ns) {
+    for (int64_t i = 0; i < cfg->nt; ++i) {
+      const int64_t ns = cfg->time_ns[i] + cfg->time_shift_ns;
+      const int64_t DAY = 86400LL * 1000000000LL;
+      int64_t day = ns / DAY, rem = ns % DAY;
+      if (rem < 0) {
+        rem += DAY;
+        day -= 1;
+      }
+      const int64_t hour = rem / 3600000000000LL;
+      const int64_t minute = (rem / 60000000000LL) % 60;
+      const int64_t second = (rem / 1000000000LL) % 60;
+      const int64_t micro = (rem / 1000LL) % 1000000;
+      const int64_t nano = rem % 1000;
+      // pandas DatetimeIndex.to_julian_date: integer day count + 0.5, then + day fraction
+      const double jd = ((double)day + 2440587.5) +
+                        ((double)hour + (double)minute / 60.0 + (double)second / 3600.0 +
+                         (double)micro / 3600.0 / 1e6 + (double)nano / 3600.0 / 1e9) /
+                            24.0;
+      const double n = jd - 2451545.0;                                   // :74
+      const double L = 280.460 + 0.9856474 * n;                          // :86
+      const double gg = (357.528 + 0.9856003 * n) * D2R;                 // :87
+      const double l = (L + 1.915 * std::sin(gg) + 0.020 * std::sin(2 * gg)) * D2R;  // :88
+      const double ep = (23.439 - 4e-7 * n) * D2R;                       // :89
+      const double ra = std::atan2(std::cos(ep) * std::sin(l), std::cos(l));  // :91
+      const double lmst0 =
+          (6.697375 + ((double)hour + (double)minute / 60.0) + 0.0657098242 * n) * 15.0;  // :92
+      const double H0 = lmst0 * D2R - ra;                                // :95 (without lon)
+      const double dec = std::asin(std::sin(ep) * std::sin(l));          // :97
+      tt[(size_t)i] = make_float4((float)std::sin(dec), (float)std::cos(dec), (float)std::cos(H0),
+                                  (float)std::sin(H0));
+    }
+  }
+  std::vector<float2> xt((size_t)cfg->nx);
+  for (int i = 0; i < cfg->nx; ++i) {
+    const double lon = cfg->lon_deg[i] * D2R;
+    xt[(size_t)i] = make_float2((float)std::cos(lon), (float)std::sin(lon));
+  }
+  std::vector<float> yt((size_t)cfg->ny * 8);
+  for (int j = 0; j < cfg->ny; ++j) {
+    const double lat = cfg->lat_deg[j] * D2R, sl = cfg->slope_rad[j], az = cfg->azimuth_rad[j];
+    float* o = &yt[(size_t)j * 8];
+    o[0] = (float)std::sin(lat);
+    o[1] = (float)std::cos(lat);
+    o[2] = (float)std::cos(sl);
+    o[3] = (float)std::sin(sl);
+    o[4] = (float)std::cos(az);
+    o[5] = (float)std::sin(az);
+    o[6] = (float)std::pow(std::sin(sl / 2.0), 3);
+    o[7] = 0.f;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_tt, tt.size() * sizeof(float4));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(op->d_tt, tt.data(), tt.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_xt, xt.size() * sizeof(float2));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(op->d_xt, xt.data(), xt.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_yt, yt.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(op->d_yt, yt.data(), yt.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    atl_pv_destroy(op);
+    return cuda_fail(e, "atl_pv_create");
+  }
+  *op_out = op;
+  return ATL_OK;
+}
+
+void atl_pv_destroy(AtlPvOp* op) {
+  if (!op) return;
+  cudaSetDevice(op->device);
+  cudaFree(op->d_tt);
+  cudaFree(op->d_xt);
+  cudaFree(op->d_yt);
+  delete op;
+}
+
+int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
+                   int32_t* solar_src) {
+  ATL_REQUIRE(op, "NULL argument");
+  if (device) *device = op->device;
+  if (ny) *ny = op->grid.ny;
+  if (nx) *nx = op->grid.nx;
+  if (solar_src) *solar_src = op->solar_src;
+  return ATL_OK;
+}
+
+int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f, int64_t t0,
+                  int64_t nt, float* out_dev, void* stream) {
+  int rc = check(op, f, t0, nt);
+  if (rc) return rc;
+  ATL_REQUIRE(plan && out_dev, "NULL argument");
+  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
+              "plan / operator grid mismatch");
+  ATL_CUDA(cudaSetDevice(op->device));
+  if (op->fast)
+    return launch_reduce(make_phys<true>(op, f, t0), plan, out_dev, nt, (cudaStream_t)stream);
+  return launch_reduce(make_phys<false>(op, f, t0), plan, out_dev, nt, (cudaStream_t)stream);
+}
+
+int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
+                 float* out_dev, void* stream) {
+  int rc = check(op, f, t0, nt);
+  if (rc) return rc;
+  ATL_REQUIRE(out_dev, "NULL argument");
+  ATL_CUDA(cudaSetDevice(op->device));
+  if (op->fast)
+    return launch_cells(make_phys<true>(op, f, t0), op->grid, out_dev, 0, nt, false,
+                        (cudaStream_t)stream);
+  return launch_cells(make_phys<false>(op, f, t0), op->grid, out_dev, 0, nt, false,
+                      (cudaStream_t)stream);
+}
+
+int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
+                   float* out_dev, void* stream) {
+  int rc = check(op, f, t0, nt);
+  if (rc) return rc;
+  ATL_REQUIRE(out_dev, "NULL argument");
+  ATL_CUDA(cudaSetDevice(op->device));
+  if (op->fast)
+    return launch_cells(make_phys<true>(op, f, t0), op->grid, out_dev, 0, nt, true,
+                        (cudaStream_t)stream);
+  return launch_cells(make_phys<false>(op, f, t0), op->grid, out_dev, 0, nt, true,
+                      (cudaStream_t)stream);
+}
+
+}  // extern "C"

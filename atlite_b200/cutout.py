@@ -1,0 +1,143 @@
+"""``Cutout``: the container the conversion methods are bound to.
+
+The reference's ``Cutout`` (cutout.py:61-689) also creates/downloads/prepares
+NetCDF cutouts and does GIS work; none of that is on the hot path.  This class
+keeps what ``convert_and_aggregate`` consumes -- ``.data`` (variables as
+``(time, y, x)`` arrays with ``x, y, time, lon, lat`` coordinates), ``.grid``
+(cells in y-major / x-minor order, cutout.py:355-376) -- binds the same
+conversion methods (cutout.py:653-689), and adds device residency:
+``to_device()`` uploads the fields once so repeated pv / wind / heat_demand
+calls read them straight from HBM.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from . import convert as _convert
+from .labelled import HAVE_XARRAY, DataArray, Dataset, make_dataarray
+
+if HAVE_XARRAY:  # pragma: no cover
+    import xarray as xr
+
+
+class Cutout:
+    def __init__(self, path=None, data=None, time_shard=None, **kwargs):
+        if data is None:
+            if path is None:
+                raise ValueError("Cutout needs `data=` (or a NetCDF `path` when xarray is installed)")
+            if not HAVE_XARRAY:
+                raise ImportError(
+                    "opening a NetCDF cutout needs xarray; pass `data=` "
+                    "(atlite_b200.Dataset of NumPy arrays) instead"
+                )
+            chunks = kwargs.pop("chunks", {"time": 100})
+            data = xr.open_dataset(str(path), chunks=chunks)
+        elif isinstance(data, dict):
+            data = Dataset(
+                {k: v for k, v in data.items() if k not in ("time", "x", "y", "lon", "lat")},
+                coords={k: data[k] for k in ("time", "x", "y", "lon", "lat") if k in data},
+            )
+        for c in ("x", "y", "time"):
+            if c not in data.coords:
+                raise ValueError(f"cutout data lacks coordinate {c!r}")
+        if isinstance(data, Dataset):
+            if "lon" not in data.coords:
+                data.coords["lon"] = data.coords["x"]
+            if "lat" not in data.coords:
+                data.coords["lat"] = data.coords["y"]
+        self.path = path
+        self.data = data
+        # set by atlite_b200.dist.TimeShard: this process holds one contiguous
+        # time shard of the cutout and results are gathered across ranks
+        self.time_shard = time_shard
+
+    # ---- geometry (cutout.py:300-376)
+    @property
+    def coords(self):
+        return self.data.coords
+
+    @property
+    def shape(self):
+        return len(self.coords["y"]), len(self.coords["x"])
+
+    @property
+    def dx(self):
+        x = np.asarray(self.coords["x"])
+        return float(np.round(x[1] - x[0], 8)) if len(x) > 1 else 0.0
+
+    @property
+    def dy(self):
+        y = np.asarray(self.coords["y"])
+        return float(np.round(y[1] - y[0], 8)) if len(y) > 1 else 0.0
+
+    @property
+    def extent(self):
+        x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
+        return np.array([x.min() - self.dx / 2, x.max() + self.dx / 2,
+                         y.min() - self.dy / 2, y.max() + self.dy / 2])
+
+    @property
+    def grid(self):
+        """Cell centres in y-major, x-minor order: flat index s = iy*nx + ix."""
+        x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
+        xs, ys = np.meshgrid(x, y)
+        return pd.DataFrame({"x": xs.ravel(), "y": ys.ravel()})
+
+    def uniform_layout(self):
+        ny, nx = self.shape
+        return make_dataarray(
+            np.ones((ny, nx)), ("y", "x"),
+            {"y": np.asarray(self.coords["y"]), "x": np.asarray(self.coords["x"])},
+        )
+
+    def indicatormatrix(self, shapes, shapes_crs=4326):
+        """Cell x shape overlap matrix (gis.py:104-145).  GIS preprocessing is
+        outside the hot path: delegate to atlite when it
+        and its GIS stack are importable, otherwise ask for ``matrix=``."""
+        try:
+            from atlite.gis import compute_indicatormatrix  # type: ignore
+            from shapely.geometry import box  # type: ignore
+        except Exception as e:  # noqa: BLE001
+            raise NotImplementedError(
+                "building an indicator matrix from shapes needs shapely/atlite; "
+                "pass a precomputed `matrix=` (n_bus x n_cells, cutout.grid order)"
+            ) from e
+        g = self.grid
+        dx, dy = self.dx, self.dy
+        cells = [box(x - dx / 2, y - dy / 2, x + dx / 2, y + dy / 2) for x, y in zip(g.x, g.y)]
+        return compute_indicatormatrix(cells, shapes, 4326, shapes_crs)
+
+    # ---- device residency
+    def to_device(self, device=None, variables=None):
+        """Return a Cutout whose (time, y, x) variables live in GPU memory as
+        float32 torch tensors (solar position variables keep float64)."""
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        ds = self.data
+        names = list(ds.data_vars) if variables is None else list(variables)
+        out = Dataset(coords={k: np.asarray(getattr(v, "values", v)) for k, v in dict(ds.coords).items()
+                              if k in ("time", "x", "y", "lon", "lat")},
+                      attrs=dict(getattr(ds, "attrs", {})))
+        for n in names:
+            arr = _convert._raw(ds, n)
+            if not _convert.engine._is_torch(arr):
+                a = np.asarray(arr)
+                if not (n.startswith("solar_") and a.dtype == np.float64):
+                    a = np.ascontiguousarray(a, dtype=np.float32)
+                arr = torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+            dims = ("time", "y", "x")[-arr.ndim:]
+            out[n] = (dims, arr.contiguous())
+        return Cutout(data=out, time_shard=self.time_shard)
+
+    def __repr__(self):
+        ny, nx = self.shape
+        return f"<atlite_b200.Cutout {nx} x {ny} x {len(self.coords['time'])}>"
+
+    # ---- conversion and aggregation (cutout.py:653-689)
+    convert_and_aggregate = _convert.convert_and_aggregate
+    heat_demand = _convert.heat_demand
+    wind = _convert.wind
+    pv = _convert.pv

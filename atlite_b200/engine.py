@@ -1,0 +1,376 @@
+"""Handle wrappers over the C ABI: aggregation plans and the pv / wind / heat
+operators.  Arrays may be NumPy (host) or torch CUDA tensors (device-resident
+cutout); host arrays go through the library's streaming entry points
+(``atl_*_reduce_host``), device tensors through the kernel entry points.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import zlib
+from collections import OrderedDict
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+from . import _lib
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def current_device():
+    try:
+        torch = _torch()
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:  # noqa: BLE001
+        pass
+    return 0
+
+
+def _stream_ptr():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_cuda and x.is_contiguous()
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("device pointer requested for a non-torch array")
+
+
+def _hptr(x):
+    if x is None:
+        return None
+    assert isinstance(x, np.ndarray) and x.flags["C_CONTIGUOUS"]
+    return C.c_void_p(x.ctypes.data)
+
+
+def host_f32(a):
+    """C-contiguous float32 view/copy of a host array."""
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def time_ns(time):
+    """datetime-like sequence -> contiguous int64 nanoseconds since the epoch (UTC)."""
+    idx = pd.DatetimeIndex(np.asarray(time))
+    return np.ascontiguousarray(idx.as_unit("ns").asi8, dtype=np.int64)
+
+
+class Plan:
+    """Device-side aggregation plan built from an (n_bus, S) CSR matrix."""
+
+    def __init__(self, matrix, ny, nx, device=None):
+        lib = _lib.load()
+        m = sp.csr_matrix(matrix)
+        m.sum_duplicates()
+        if m.shape[1] != ny * nx:
+            raise ValueError(
+                f"matrix has {m.shape[1]} columns but the cutout grid has {ny}x{nx}={ny * nx} cells"
+            )
+        self.shape = m.shape
+        self.device = current_device() if device is None else device
+        self._indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        self._indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        self._data = np.ascontiguousarray(m.data, dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(
+            lib.atl_plan_create(
+                self.device, ny, nx, m.shape[0],
+                _lib.ptr(self._indptr), _lib.ptr(self._indices), _lib.ptr(self._data),
+                C.byref(h),
+            )
+        )
+        self.handle = h
+        info = _lib.PlanInfo()
+        _lib.check(lib.atl_plan_info(h, C.byref(info)))
+        self.info = {f[0]: getattr(info, f[0]) for f in _lib.PlanInfo._fields_}
+        self.n_bus = m.shape[0]
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                _lib.load().atl_plan_destroy(h)
+            except Exception:  # noqa: BLE001
+                pass
+            self.handle = None
+
+    def spmm(self, dense):
+        """(nt, ny, nx) | (nt, S) per-cell values (host or device) -> (nt, n_bus) float32."""
+        torch = _torch()
+        if not _is_torch(dense):
+            dense = torch.from_numpy(host_f32(dense)).to(f"cuda:{self.device}")
+        dense = dense.contiguous().to(torch.float32)
+        nt = dense.shape[0]
+        out = torch.empty((nt, self.n_bus), dtype=torch.float32, device=dense.device)
+        _lib.check(_lib.load().atl_spmm(self.handle, _dptr(dense), nt, _dptr(out), _stream_ptr()))
+        return out
+
+
+_PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
+
+
+def get_plan(matrix, ny, nx, device=None):
+    """Plans are cached (LRU, 4 entries): the typical workflow evaluates many
+    technologies against the same shapes."""
+    m = sp.csr_matrix(matrix)
+    device = current_device() if device is None else device
+    key = (
+        device, ny, nx, m.shape, m.nnz,
+        zlib.crc32(np.ascontiguousarray(m.indptr).view(np.uint8)),
+        zlib.crc32(np.ascontiguousarray(m.indices).view(np.uint8)),
+        zlib.crc32(np.ascontiguousarray(m.data).view(np.uint8)),
+    )
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = Plan(m, ny, nx, device)
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > 4:
+            _PLAN_CACHE.popitem(last=False)
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return plan
+
+
+class _Op:
+    _destroy = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                getattr(_lib.load(), self._destroy)(h)
+            except Exception:  # noqa: BLE001
+                pass
+            self.handle = None
+
+    @staticmethod
+    def _all_device(arrs):
+        kinds = {_is_torch(a) for a in arrs if a is not None}
+        if len(kinds) > 1:
+            raise ValueError("mixing host (NumPy) and device (torch) fields in one call")
+        return kinds.pop() if kinds else False
+
+    def _out(self, shape, like):
+        torch = _torch()
+        return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+class PvOp(_Op):
+    """convert_pv (convert.py:840-854) operator; see include/atlite_b200.h."""
+
+    _destroy = "atl_pv_destroy"
+    FIELD_NAMES = tuple(n for n, _ in _lib.PvFields._fields_)
+
+    def __init__(self, *, ny, nx, time, lon, lat, slope, azimuth, tracking, trigon_model,
+                 clearsky_model, irr_branch, albedo_src, solar_src, panel, time_shift="0h",
+                 altitude_threshold=1.0, device=None):
+        lib = _lib.load()
+        self.device = current_device() if device is None else device
+        self.ny, self.nx = ny, nx
+        self._time = time_ns(time)
+        self.nt = len(self._time)
+        self._lon, self._lat = _lib.as_f64(lon), _lib.as_f64(lat)
+        self._slope = np.ascontiguousarray(np.broadcast_to(np.asarray(slope, dtype=np.float64), (ny,)))
+        self._az = np.ascontiguousarray(np.broadcast_to(np.asarray(azimuth, dtype=np.float64), (ny,)))
+        cfg = _lib.PvConfig()
+        cfg.ny, cfg.nx, cfg.nt = ny, nx, self.nt
+        cfg.time_ns = _lib.ptr(self._time).value
+        cfg.time_shift_ns = int(pd.to_timedelta(time_shift).value)
+        cfg.lon_deg, cfg.lat_deg = _lib.ptr(self._lon).value, _lib.ptr(self._lat).value
+        cfg.slope_rad, cfg.azimuth_rad = _lib.ptr(self._slope).value, _lib.ptr(self._az).value
+        cfg.tracking = _lib.TRACKING[tracking]
+        cfg.trigon_model = trigon_model
+        cfg.clearsky_model = clearsky_model
+        cfg.irr_branch, cfg.albedo_src, cfg.solar_src = irr_branch, albedo_src, solar_src
+        model = panel.get("model", "huld")
+        if model not in _lib.PANEL:
+            raise AssertionError(f"Unknown panel model: {model}")
+        cfg.panel_model = _lib.PANEL[model]
+        cfg.altitude_threshold_deg = altitude_threshold
+        if model == "huld":
+            vals = [panel["c_temp_amb"], panel["c_temp_irrad"], panel["r_tmod"], panel["r_irradiance"]]
+            vals += [panel[f"k_{i}"] for i in range(1, 7)]
+            vals += [panel.get("inverter_efficiency", 1.0)]
+        else:
+            vals = [panel[k] for k in ("A", "B", "C", "D", "NOCT", "Tamb", "Intc", "Tstd", "ta", "threshold")]
+            vals += [panel.get("inverter_efficiency", 1.0)]
+        for i, v in enumerate(vals):
+            cfg.panel[i] = float(v)
+        h = C.c_void_p()
+        _lib.check(lib.atl_pv_create(self.device, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    def _fields(self, fields, host):
+        f = _lib.PvFields()
+        keep = []
+        for n in self.FIELD_NAMES:
+            a = fields.get(n)
+            if a is None:
+                setattr(f, n, None)
+                continue
+            if host:
+                if n.startswith("solar_") and np.asarray(a).dtype == np.float64:
+                    a = np.ascontiguousarray(a)
+                else:
+                    a = host_f32(a)
+                keep.append(a)
+                setattr(f, n, a.ctypes.data)
+            else:
+                a = a.contiguous()
+                keep.append(a)
+                setattr(f, n, a.data_ptr())
+        return f, keep
+
+    def reduce(self, plan, fields, t0=0, nt=None, chunk_steps=0):
+        """(nt, n_bus) float32: torch CUDA tensor for device fields, ndarray for host fields."""
+        lib = _lib.load()
+        dev = self._all_device(fields.values())
+        first = next(a for a in fields.values() if a is not None)
+        nt = first.shape[0] if nt is None else nt
+        f, keep = self._fields(fields, host=not dev)
+        if dev:
+            out = self._out((nt, plan.n_bus), first)
+            _lib.check(lib.atl_pv_reduce(self.handle, plan.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+            return out
+        out = np.empty((nt, plan.n_bus), dtype=np.float32)
+        _lib.check(lib.atl_pv_reduce_host(self.handle, plan.handle, C.byref(f), t0, nt, _hptr(out), chunk_steps))
+        return out
+
+    def cells(self, fields, t0=0, timesum=False):
+        """Per-cell values (nt, ny, nx) or their time sum (ny, nx); device fields only."""
+        lib = _lib.load()
+        first = next(a for a in fields.values() if a is not None)
+        nt = first.shape[0]
+        f, keep = self._fields(fields, host=False)
+        torch = _torch()
+        if timesum:
+            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=first.device)
+            _lib.check(lib.atl_pv_timesum(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+        else:
+            out = self._out((nt, self.ny, self.nx), first)
+            _lib.check(lib.atl_pv_cells(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+        return out
+
+
+class WindOp(_Op):
+    """convert_wind (convert.py:634-662) operator."""
+
+    _destroy = "atl_wind_destroy"
+
+    def __init__(self, *, ny, nx, V, POW_norm, method, from_height, to_height, device=None):
+        lib = _lib.load()
+        self.device = current_device() if device is None else device
+        self.ny, self.nx = ny, nx
+        self._V, self._P = _lib.as_f64(V), _lib.as_f64(POW_norm)
+        cfg = _lib.WindConfig()
+        cfg.ny, cfg.nx, cfg.method = ny, nx, method
+        cfg.from_height, cfg.to_height = float(from_height), float(to_height)
+        cfg.n_knots = len(self._V)
+        cfg.V, cfg.POW_norm = _lib.ptr(self._V).value, _lib.ptr(self._P).value
+        h = C.c_void_p()
+        _lib.check(lib.atl_wind_create(self.device, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    def _fields(self, wnd, aux, host):
+        f = _lib.WindFields()
+        keep = []
+        for n, a in (("wnd", wnd), ("aux", aux)):
+            if a is None:
+                setattr(f, n, None)
+            elif host:
+                a = host_f32(a)
+                keep.append(a)
+                setattr(f, n, a.ctypes.data)
+            else:
+                a = a.contiguous()
+                keep.append(a)
+                setattr(f, n, a.data_ptr())
+        return f, keep
+
+    def reduce(self, plan, wnd, aux=None, chunk_steps=0):
+        lib = _lib.load()
+        dev = self._all_device([wnd, aux])
+        nt = wnd.shape[0]
+        f, keep = self._fields(wnd, aux, host=not dev)
+        if dev:
+            out = self._out((nt, plan.n_bus), wnd)
+            _lib.check(lib.atl_wind_reduce(self.handle, plan.handle, C.byref(f), nt, _dptr(out), _stream_ptr()))
+            return out
+        out = np.empty((nt, plan.n_bus), dtype=np.float32)
+        _lib.check(lib.atl_wind_reduce_host(self.handle, plan.handle, C.byref(f), nt, _hptr(out), chunk_steps))
+        return out
+
+    def cells(self, wnd, aux=None, timesum=False):
+        lib = _lib.load()
+        nt = wnd.shape[0]
+        f, keep = self._fields(wnd, aux, host=False)
+        torch = _torch()
+        if timesum:
+            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=wnd.device)
+            _lib.check(lib.atl_wind_timesum(self.handle, C.byref(f), nt, _dptr(out), _stream_ptr()))
+        else:
+            out = self._out((nt, self.ny, self.nx), wnd)
+            _lib.check(lib.atl_wind_cells(self.handle, C.byref(f), nt, _dptr(out), _stream_ptr()))
+        return out
+
+
+class HeatOp(_Op):
+    """convert_heat_demand (convert.py:405-418) operator."""
+
+    _destroy = "atl_heat_destroy"
+
+    def __init__(self, *, ny, nx, threshold, a, constant, device=None):
+        lib = _lib.load()
+        self.device = current_device() if device is None else device
+        self.ny, self.nx = ny, nx
+        cfg = _lib.HeatConfig()
+        cfg.ny, cfg.nx = ny, nx
+        cfg.threshold_c, cfg.a, cfg.constant = float(threshold), float(a), float(constant)
+        h = C.c_void_p()
+        _lib.check(lib.atl_heat_create(self.device, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    def reduce(self, plan, temperature, day_start, chunk_days=0):
+        lib = _lib.load()
+        ds = np.ascontiguousarray(day_start, dtype=np.int64)
+        nd = len(ds) - 1
+        if _is_torch(temperature):
+            t = temperature.contiguous()
+            out = self._out((nd, plan.n_bus), t)
+            _lib.check(lib.atl_heat_reduce(self.handle, plan.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
+            return out
+        t = host_f32(temperature)
+        out = np.empty((nd, plan.n_bus), dtype=np.float32)
+        _lib.check(lib.atl_heat_reduce_host(self.handle, plan.handle, _hptr(t), _lib.ptr(ds), nd, _hptr(out), chunk_days))
+        return out
+
+    def cells(self, temperature, day_start, timesum=False):
+        lib = _lib.load()
+        ds = np.ascontiguousarray(day_start, dtype=np.int64)
+        nd = len(ds) - 1
+        t = temperature.contiguous()
+        torch = _torch()
+        if timesum:
+            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=t.device)
+            _lib.check(lib.atl_heat_timesum(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
+        else:
+            out = self._out((nd, self.ny, self.nx), t)
+            _lib.check(lib.atl_heat_cells(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
+        return out

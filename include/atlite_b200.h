@@ -1,0 +1,227 @@
+/*
+ * atlite_b200.h -- C ABI of libatlite_b200.so
+ *
+ * B200-native (sm_100a) replacement for the conversion-and-aggregation hot
+ * path of PyPSA/atlite.  Plain C: pointers, sizes, opaque handles; no torch
+ * or C++ types cross this boundary.  The reference is pure Python, so the
+ * "FFI a maintainer would bind" is a ctypes stub; the
+ * entry points below are cut exactly where the reference hands work to
+ * NumPy/dask/scipy:
+ *
+ *   reference (paths relative to /root/reference/atlite/)      entry point
+ *   ---------------------------------------------------------  ------------------------
+ *   aggregate.py:16-35  aggregate_matrix (dense x CSR^T)        atl_plan_create + *_reduce, atl_spmm
+ *   convert.py:840-854  convert_pv  (+ pv/*.py)                 atl_pv_create, atl_pv_reduce/cells/timesum
+ *   convert.py:634-662  convert_wind (+ wind.py:24-128)         atl_wind_create, atl_wind_*
+ *   convert.py:405-418  convert_heat_demand                     atl_heat_create, atl_heat_*
+ *   convert.py:200-211  no-matrix branch (_aggregate_time)      *_cells, *_timesum
+ *   convert.py:257-271  reduce + time aggregation               *_reduce (+ host finalisation in Python)
+ *
+ * Conventions
+ *   - All weather fields are C-contiguous (time, y, x) float32 slabs, x fastest
+ *     (the cutout's NetCDF layout).  A "slab" covers time
+ *     steps [t0, t0+nt) of the operator's time axis and its pointers address
+ *     the slab's first step.
+ *   - Pointers named *_dev are device pointers on the operator's device, those
+ *     named *_host are host pointers.  Small tables (coordinates, time axis,
+ *     power curve) are always host pointers and are copied at create time.
+ *   - The aggregated output is (nt, n_bus) float32, time-major -- the dim
+ *     order of the reference's dask branch (aggregate.py:24-32) -- and is
+ *     OVERWRITTEN (zero-filled, then accumulated) by each *_reduce call.
+ *   - Every function returns ATL_OK (0) or a negative error code;
+ *     atl_last_error() returns a thread-local message.  Nothing here falls
+ *     back to a CPU implementation: without a CUDA device every compute entry
+ *     point fails with ATL_ERR_CUDA.
+ *   - stream: a cudaStream_t passed as void* (NULL = default stream).  Calls
+ *     are asynchronous w.r.t. the host unless stated otherwise.
+ */
+#ifndef ATLITE_B200_H
+#define ATLITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATL_OK 0
+#define ATL_ERR_INVALID (-1) /* bad argument / unsupported combination */
+#define ATL_ERR_CUDA (-2)    /* CUDA runtime error (see atl_last_error) */
+#define ATL_ERR_NOMEM (-3)
+
+#define ATL_ABI_VERSION 1
+
+int atl_abi_version(void);
+const char* atl_last_error(void);
+int atl_device_count(int* count_out);
+
+/* ------------------------------------------------------------------ */
+/* Aggregation plan: the (n_bus x S) CSR indicator/layout matrix       */
+/* (convert.py:213-254) pre-tiled for the fused reduce kernels.        */
+/* ------------------------------------------------------------------ */
+typedef struct AtlPlan AtlPlan;
+
+typedef struct {
+  int32_t ny, nx, n_bus;
+  int64_t nnz;            /* stored entries after merging duplicates   */
+  int32_t n_tiles;        /* 32x4-cell warp tiles covering the grid     */
+  int32_t n_active_tiles; /* tiles touched by at least one entry        */
+  int64_t n_slots;        /* distinct (tile, bus) pairs                 */
+  double slots_per_active_tile;
+  int32_t fused;          /* 1: fused tile path, 0: two-pass CSR fallback */
+} AtlPlanInfo;
+
+/* indptr/indices/data: host CSR arrays (scipy layout), column index
+ * s = iy*nx + ix (cutout.grid order, cutout.py:355-376). */
+int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
+                    const int64_t* indptr_host, const int32_t* indices_host,
+                    const double* data_host, AtlPlan** plan_out);
+int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info_out);
+void atl_plan_destroy(AtlPlan* plan);
+
+/* Generic (time, S) dense  x  CSR^T  ->  (time, n_bus)  (aggregate.py:24-32):
+ * the path for unknown convert_func results. */
+int atl_spmm(const AtlPlan* plan, const float* dense_dev, int64_t nt,
+             float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* PV: SolarPosition -> SurfaceOrientation -> TiltedIrradiation ->     */
+/* SolarPanelModel (convert.py:840-854)                                */
+/* ------------------------------------------------------------------ */
+enum { ATL_TRACK_NONE = 0, ATL_TRACK_HORIZONTAL = 1, ATL_TRACK_TILTED_HORIZONTAL = 2,
+       ATL_TRACK_VERTICAL = 3, ATL_TRACK_DUAL = 4 };       /* pv/orientation.py:114-176 */
+enum { ATL_TRIGON_SIMPLE = 0, ATL_TRIGON_HAY_DAVIES = 1 };  /* pv/irradiation.py:214-236 */
+enum { ATL_CLEARSKY_SIMPLE = 0, ATL_CLEARSKY_ENHANCED = 1 };/* pv/irradiation.py:33-65  */
+enum { ATL_IRR_DIRECT_DIFFUSE = 0, ATL_IRR_INFLUX = 1 };    /* pv/irradiation.py:202-208 */
+enum { ATL_ALBEDO_VAR = 0, ATL_ALBEDO_OUTFLUX = 1 };        /* pv/irradiation.py:128-139 */
+enum { ATL_SOLAR_COMPUTED = 0, ATL_SOLAR_STORED_F32 = 1, ATL_SOLAR_STORED_F64 = 2 }; /* pv/solar_position.py:54-60 vs 69-116 */
+enum { ATL_PANEL_HULD = 0, ATL_PANEL_BOFINGER = 1 };        /* pv/solar_panel_model.py:12-74 */
+
+typedef struct {
+  int32_t ny, nx;
+  int64_t nt;                 /* length of the time axis                        */
+  const int64_t* time_ns;     /* host, nt: datetime64[ns] UTC                   */
+  int64_t time_shift_ns;      /* SolarPosition(time_shift=...), default 0       */
+  const double* lon_deg;      /* host, nx   (ds["lon"])                          */
+  const double* lat_deg;      /* host, ny   (ds["lat"])                          */
+  const double* slope_rad;    /* host, ny   orientation(lon,lat,sp)["slope"]     */
+  const double* azimuth_rad;  /* host, ny   orientation(...)["azimuth"]          */
+  int32_t tracking, trigon_model, clearsky_model, irr_branch, albedo_src,
+      solar_src, panel_model;
+  double altitude_threshold_deg; /* pv/irradiation.py:155, default 1.0         */
+  /* Huld: c_temp_amb, c_temp_irrad, r_tmod, r_irradiance, k_1..k_6, inverter_efficiency
+   * Bofinger: A, B, C, D, NOCT, Tamb, Intc, Tstd, ta, threshold, inverter_efficiency */
+  double panel[16];
+} AtlPvConfig;
+
+typedef struct { /* device pointers to (nt_slab, ny, nx) slabs; unused = NULL */
+  const float* influx_toa;
+  const float* influx_direct;
+  const float* influx_diffuse;
+  const float* influx;
+  const float* albedo;
+  const float* outflux;
+  const float* temperature;
+  const float* humidity;
+  const void* solar_altitude; /* float or double per solar_src */
+  const void* solar_azimuth;
+} AtlPvFields;
+
+typedef struct AtlPvOp AtlPvOp;
+int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out);
+void atl_pv_destroy(AtlPvOp* op);
+/* fused convert + aggregate of slab [t0, t0+nt): out_dev (nt, n_bus) */
+int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f,
+                  int64_t t0, int64_t nt, float* out_dev, void* stream);
+/* per-cell result (aggregate_time=None, no matrix): out_dev (nt, ny, nx) */
+int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
+                 float* out_dev, void* stream);
+/* per-cell time sum, ACCUMULATED into out_dev (ny, nx) (caller zero-fills) */
+int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
+                   float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Wind: extrapolate_wind_speed + np.interp power curve                */
+/* (wind.py:24-128, convert.py:634-662)                                */
+/* ------------------------------------------------------------------ */
+enum { ATL_WIND_NONE = 0 /* wnd{hub}m present, wind.py:75-78 */,
+       ATL_WIND_LOG = 1 /* wind.py:91-102 */, ATL_WIND_POWER = 2 /* wind.py:103-112 */ };
+
+typedef struct {
+  int32_t ny, nx;
+  int32_t method;
+  double from_height, to_height;
+  int32_t n_knots;         /* <= 255 */
+  const double* V;         /* host, n_knots, non-decreasing (resource.py:346-355) */
+  const double* POW_norm;  /* host, n_knots: POW / P  (convert.py:649)            */
+} AtlWindConfig;
+
+typedef struct {
+  const float* wnd; /* wnd{from}m, (nt, ny, nx)                           */
+  const float* aux; /* roughness (LOG) or wnd_shear_exp (POWER) or NULL   */
+} AtlWindFields;
+
+typedef struct AtlWindOp AtlWindOp;
+int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out);
+void atl_wind_destroy(AtlWindOp* op);
+int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindFields* f,
+                    int64_t nt, float* out_dev, void* stream);
+int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt,
+                   float* out_dev, void* stream);
+int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt,
+                     float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Heat demand: daily mean temperature -> degree days                  */
+/* (convert.py:405-418)                                                */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int32_t ny, nx;
+  double threshold_c, a, constant; /* convert.py:413-418 (threshold in deg C) */
+} AtlHeatConfig;
+
+typedef struct AtlHeatOp AtlHeatOp;
+int atl_heat_create(int device, const AtlHeatConfig* cfg, AtlHeatOp** op_out);
+void atl_heat_destroy(AtlHeatOp* op);
+/* day_start_host: n_days+1 offsets into the slab's time steps (calendar-day
+ * bins of time+hour_shift, convert.py:408-412); out_dev (n_days, n_bus). */
+int atl_heat_reduce(const AtlHeatOp* op, const AtlPlan* plan, const float* temperature_dev,
+                    const int64_t* day_start_host, int64_t n_days, float* out_dev,
+                    void* stream);
+int atl_heat_cells(const AtlHeatOp* op, const float* temperature_dev,
+                   const int64_t* day_start_host, int64_t n_days, float* out_dev,
+                   void* stream);
+int atl_heat_timesum(const AtlHeatOp* op, const float* temperature_dev,
+                     const int64_t* day_start_host, int64_t n_days, float* out_dev,
+                     void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Host-buffer entry points: the call the reference-facing Python API  */
+/* makes when the cutout lives in host memory (NumPy / NetCDF).  The   */
+/* library streams time slabs through a pinned ring (H2D overlapped    */
+/* with the kernels) and returns the (nt, n_bus) result in host memory.*/
+/* Synchronous.  chunk_steps <= 0 picks a default.                     */
+/* ------------------------------------------------------------------ */
+int atl_pv_reduce_host(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f_host,
+                       int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps);
+int atl_wind_reduce_host(const AtlWindOp* op, const AtlPlan* plan,
+                         const AtlWindFields* f_host, int64_t nt, float* out_host,
+                         int64_t chunk_steps);
+int atl_heat_reduce_host(const AtlHeatOp* op, const AtlPlan* plan,
+                         const float* temperature_host, const int64_t* day_start_host,
+                         int64_t n_days, float* out_host, int64_t chunk_days);
+
+/* Introspection of operator handles (device, grid). */
+int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
+                   int32_t* solar_src);
+int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
+int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
+
+/* Number of kernel launches issued by this library since load (bench.py's
+ * "gpu_launches" evidence). */
+int64_t atl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLITE_B200_H */
