@@ -47,7 +47,7 @@ struct PvPhys {
   int nx;
   int t_off;
   int tracking_, trigon, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model;
-  float sin_thr;
+  float sin_thr, alt_thr;
   float pc[12];
 
   __device__ __forceinline__ int tracking() const { return FAST ? ATL_TRACK_NONE : tracking_; }
@@ -243,7 +243,11 @@ struct PvPhys {
         total = fmaf(Rb, direct, dt) + influx_ * albedo * fmaf(-0.5f, cslope, 0.5f);
       }
       // altitude / darkness mask  :251-252
-      const bool masked = (sinalt < sin_thr) || (influx_ <= 0.01f);
+      // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
+      // stored mode compares the stored altitude itself, as the reference does
+      const bool low = (solar_src() == ATL_SOLAR_COMPUTED) ? (sinalt < sin_thr)
+                                                           : (r.salt[i] < alt_thr);
+      const bool masked = low || (influx_ <= 0.01f);
       const float G = masked ? 0.f : total;
       const float pw = panel(G, r.temp[i]);
       v[i] = ((g.valid >> i) & 1u) ? pw : 0.f;
@@ -260,7 +264,7 @@ struct AtlPvOp {
   GridDev grid;
   int64_t nt;
   int tracking, trigon, clearsky, irr_branch, albedo_src, solar_src, panel_model;
-  float sin_thr;
+  float sin_thr, alt_thr;
   float pc[12];
   float4* d_tt = nullptr;
   float2* d_xt = nullptr;
@@ -295,6 +299,7 @@ static PvPhys<FAST> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t
   p.solar_src_ = op->solar_src;
   p.panel_model = op->panel_model;
   p.sin_thr = op->sin_thr;
+  p.alt_thr = op->alt_thr;
   for (int i = 0; i < 12; ++i) p.pc[i] = op->pc[i];
   return p;
 }
@@ -352,6 +357,7 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   op->solar_src = cfg->solar_src;
   op->panel_model = cfg->panel_model;
   op->sin_thr = (float)std::sin(cfg->altitude_threshold_deg * D2R);
+  op->alt_thr = (float)(cfg->altitude_threshold_deg * D2R);
   op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
              cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR;
   const double* P = cfg->panel;

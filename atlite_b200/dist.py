@@ -48,8 +48,9 @@ class TimeShard:
             return t if t.is_cuda else t.cuda()
         return t.cpu()
 
-    def gather_time(self, local, labels):
-        """Concatenate per-rank (nt_r, ...) results along time, in rank order."""
+    def gather_time(self, local, labels=None):
+        """Concatenate per-rank (nt_r, ...) results along time, in rank order.
+        ``labels=None`` skips the (host-side, pickled) gather of the time labels."""
         import torch
         import torch.distributed as dist
 
@@ -69,6 +70,8 @@ class TimeShard:
             parts = [torch.empty_like(pad) for _ in range(self.world)]
             dist.all_gather(parts, pad, group=self.group)
             out = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+        if labels is None:
+            return out, None
         all_labels = [None] * self.world
         dist.all_gather_object(all_labels, np.asarray(pd.Index(labels).values), group=self.group)
         lab = np.concatenate(all_labels)

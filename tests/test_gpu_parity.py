@@ -1,0 +1,391 @@
+"""GPU parity tests: the CUDA path (through the C ABI / public API) against the
+float64 oracle on the same seeded synthetic inputs.
+
+Tolerance (stated once, see conftest.assert_parity): fp32 kernels vs float64
+oracle, |gpu - oracle| <= 1e-4 * |oracle| + 1e-6 * capacity_bus.
+"""
+
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+from conftest import assert_parity, oracle_ds
+
+import atlite_oracle as O
+import atlite_b200 as ab
+from atlite_b200 import _lib, engine, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+warnings.filterwarnings("ignore", category=DeprecationWarning)
+
+
+def cap_of(m):
+    return np.asarray(sp.csr_matrix(m).sum(-1)).flatten()
+
+
+def bt(res):
+    """public API result (bus, time) -> oracle layout (time, bus)"""
+    assert res.dims[1] == "time"
+    return np.asarray(res.values).T
+
+
+@pytest.fixture(scope="module")
+def ds_full():
+    # 70 x 45 cells (neither a multiple of 32 nor of 4), 3 days, both hemispheres
+    return syn.make_dataset(70, 45, 72, x0=-10.0, y0=-20.0, dx=0.5, dy=1.0,
+                            extra=("wnd_shear_exp", "humidity"))
+
+
+@pytest.fixture(scope="module")
+def shapes(ds_full):
+    return syn.make_shapes(70, 45, 23)
+
+
+# ------------------------------------------------------------------ wind
+
+
+@pytest.mark.parametrize("turbine", ["Vestas_V112_3MW", "Enercon_E126_7500kW", "NREL_ReferenceTurbine_5MW_offshore"])
+@pytest.mark.parametrize("method", ["logarithmic", "power"])
+def test_wind_reduce(ds_full, shapes, turbine, method):
+    c = ab.Cutout(data=ds_full)
+    res = c.wind(turbine, matrix=shapes, interpolation_method=method, aggregate_time=None)
+    t = ab.get_windturbineconfig(turbine)
+    want = O.convert_and_aggregate(oracle_ds(ds_full), O.convert_wind, matrix=shapes,
+                                   aggregate_time=None, turbine=t, interpolation_method=method)
+    assert_parity(bt(res), want, cap_of(shapes), what=f"wind {turbine} {method}")
+    assert res.attrs["units"] == "MW"
+
+
+def test_wind_smooth_and_fast_lane(ds_full, shapes):
+    c = ab.Cutout(data=ds_full)
+    t = O.windturbine_smooth(ab.get_windturbineconfig("Vestas_V112_3MW"))
+    res = c.wind("Vestas_V112_3MW", smooth=True, matrix=shapes, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds_full), O.convert_wind, matrix=shapes,
+                                   aggregate_time=None, turbine=t)
+    assert_parity(bt(res), want, cap_of(shapes), what="wind smooth")
+    # hub height == available height: wind.py:75-78
+    t100 = dict(ab.get_windturbineconfig("Vestas_V112_3MW"), hub_height=100)
+    res = c.wind(t100, matrix=shapes, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds_full), O.convert_wind, matrix=shapes,
+                                   aggregate_time=None, turbine=t100)
+    assert_parity(bt(res), want, cap_of(shapes), what="wind fast lane")
+
+
+def test_wind_interp_edges():
+    """np.interp semantics at and around the knots: duplicate cut-out knot, values
+    below the first / above the last knot, NaN, zero/negative roughness."""
+    nx, ny, nt = 33, 5, 2
+    ds = syn.make_dataset(nx, ny, nt, kinds=("wind",))
+    t = dict(ab.get_windturbineconfig("Vestas_V112_3MW"), hub_height=100)  # no extrapolation
+    w = ds.raw("wnd100m")
+    specials = np.array([0.0, 2.0, np.nextafter(np.float32(2.0), np.float32(3)), 3.0, 12.999999, 13.0, 24.999998,
+                         25.0, np.nextafter(np.float32(25.0), np.float32(26)), 30.0, 1e6, -1.0, 1e-30],
+                        dtype=np.float32)
+    w[0, 0, : len(specials)] = specials
+    c = ab.Cutout(data=ds).to_device()
+    got = np.asarray(c.wind(t, aggregate_time=None).values)
+    want = O.convert_wind(oracle_ds(ds), t)
+    assert_parity(got, want, what="interp edges")
+    assert got[0, 0, 7] == 0.0 and got[0, 0, 6] == 1.0  # exactly at / just below cut-out
+    # NaN propagates to exactly the buses that contain the cell
+    w[1, 2, 3] = np.nan
+    r = ds.raw("roughness")
+    r[1, 1, 1] = 0.0
+    r[1, 1, 2] = -1.0
+    m = sp.csr_matrix(np.kron(np.eye(ny), np.ones((1, nx))))  # one bus per row of cells
+    t80 = ab.get_windturbineconfig("Vestas_V112_3MW")
+    got = bt(ab.Cutout(data=ds).wind(t80, matrix=m, aggregate_time=None))
+    want = O.convert_and_aggregate(oracle_ds(ds), O.convert_wind, matrix=m, aggregate_time=None, turbine=t80)
+    assert np.isnan(want[1, 2]) and np.isnan(want[1, 1]) and not np.isnan(want[1, 0])
+    assert_parity(got, want, cap_of(m), what="NaN routing")
+
+
+# ------------------------------------------------------------------ pv
+
+
+PV_CASES = [
+    dict(panel="CSi", orientation="latitude_optimal"),
+    dict(panel="CdTe", orientation={"slope": 0.0, "azimuth": 0.0}),
+    dict(panel="KANENA", orientation="latitude_optimal"),
+    dict(panel="CSi", orientation="latitude", trigon_model="other"),
+    dict(panel="CSi", orientation={"slope": 35.0, "azimuth": 160.0}, trigon_model="other"),
+    dict(panel="CSi", orientation={"slope": 0.0, "azimuth": 180.0}, tracking="horizontal"),
+    dict(panel="CSi", orientation={"slope": 30.0, "azimuth": 170.0}, tracking="tilted_horizontal"),
+    dict(panel="CSi", orientation={"slope": 30.0, "azimuth": 180.0}, tracking="vertical"),
+    dict(panel="CdTe", orientation={"slope": 30.0, "azimuth": 180.0}, tracking="dual"),
+    dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="horizontal", trigon_model="other"),
+    dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="tilted_horizontal", trigon_model="other"),
+    dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="dual", trigon_model="other"),
+]
+
+
+def _oracle_pv(ds, matrix, case, **kw):
+    case = dict(case)
+    panel = ab.get_solarpanelconfig(case.pop("panel"))
+    orientation = O.get_orientation(case.pop("orientation"))
+    return O.convert_and_aggregate(oracle_ds(ds) if not isinstance(ds, dict) else ds, O.convert_pv,
+                                   matrix=matrix, aggregate_time=None, panel=panel,
+                                   orientation=orientation, **case, **kw)
+
+
+@pytest.mark.parametrize("case", PV_CASES, ids=lambda c: "-".join(str(v) for v in c.values())[:60])
+def test_pv_reduce(ds_full, shapes, case):
+    c = ab.Cutout(data=ds_full)
+    res = c.pv(matrix=shapes, aggregate_time=None, **case)
+    want = _oracle_pv(ds_full, shapes, case)
+    assert_parity(bt(res), want, cap_of(shapes), what=f"pv {case}")
+    assert want.sum() > 0
+
+
+def test_pv_night_is_exactly_zero_and_capacity(ds_full, shapes):
+    c = ab.Cutout(data=ds_full)
+    lay = syn.make_layout(70, 45)
+    layout = ab.DataArray(lay, {"y": ds_full.coords["y"], "x": ds_full.coords["x"]}, ("y", "x"))
+    res, cap = c.pv("CdTe", {"slope": 0.0, "azimuth": 0.0}, matrix=shapes, layout=layout,
+                    return_capacity=True, aggregate_time=None)
+    want, wcap = O.convert_and_aggregate(
+        oracle_ds(ds_full), O.convert_pv, matrix=shapes, layout=lay, return_capacity=True,
+        aggregate_time=None, panel=ab.get_solarpanelconfig("CdTe"),
+        orientation=O.get_orientation({"slope": 0.0, "azimuth": 0.0}))
+    assert_parity(bt(res), want, wcap, what="pv layout")
+    np.testing.assert_allclose(cap.values, wcap, rtol=1e-12)
+    assert (bt(res)[want == 0] == 0).all(), "oracle-zero entries (night) must be exactly zero"
+    assert (want == 0).any()
+    assert cap.attrs["units"] == "MW"
+
+
+@pytest.mark.parametrize("variant", ["influx_simple", "influx_enhanced", "outflux", "stored_f32", "stored_f64"])
+def test_pv_input_variants(variant):
+    extra = {"influx_simple": ("influx",), "influx_enhanced": ("influx", "humidity"),
+             "outflux": ("outflux",), "stored_f32": (), "stored_f64": ()}[variant]
+    ds = syn.make_dataset(40, 21, 48, x0=5.0, y0=35.0, kinds=("pv",), extra=extra)
+    kw = {}
+    if variant.startswith("stored"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sp_ = O.solar_position(oracle_ds(ds))
+        dt = np.float32 if variant.endswith("f32") else np.float64
+        ds["solar_altitude"] = sp_["altitude"].astype(dt)
+        ds["solar_azimuth"] = sp_["azimuth"].astype(dt)
+    if variant == "influx_simple":
+        kw["clearsky_model"] = "simple"
+    m = syn.make_shapes(40, 21, 9)
+    case = dict(panel="CSi", orientation="latitude_optimal")
+    res = ab.Cutout(data=ds).pv(matrix=m, aggregate_time=None, **case, **kw)
+    # pv() passes clearsky_model=None by default (auto: enhanced iff humidity present)
+    want = _oracle_pv(ds, m, case, clearsky_model=kw.get("clearsky_model"))
+    assert_parity(bt(res), want, cap_of(m), what=variant)
+    assert want.sum() > 0
+
+
+def test_pv_missing_variables_raise():
+    ds = syn.make_dataset(8, 6, 4, kinds=("pv",))
+    d = {k: ds.raw(k) for k in ds.keys() if k != "albedo"}
+    d.update(time=ds.coords["time"], x=ds.coords["x"], y=ds.coords["y"])
+    with pytest.raises(AssertionError, match="albedo or outflux"):
+        ab.Cutout(data=d).pv("CSi", "latitude_optimal", aggregate_time="sum")
+    d.pop("influx_direct")
+    with pytest.raises(AssertionError, match="influx_direct and influx_diffuse"):
+        ab.Cutout(data=d).pv("CSi", "latitude_optimal", aggregate_time="sum")
+
+
+# ------------------------------------------------------------------ heat demand
+
+
+@pytest.mark.parametrize("hour_shift", [0.0, 4.0, -5.0])
+def test_heat_demand(ds_full, shapes, hour_shift):
+    c = ab.Cutout(data=ds_full)
+    res = c.heat_demand(threshold=17.0, a=1.3, constant=0.2, hour_shift=hour_shift,
+                        matrix=shapes, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds_full), O.convert_heat_demand, matrix=shapes,
+                                   aggregate_time=None, threshold=17.0, a=1.3, constant=0.2,
+                                   hour_shift=hour_shift)
+    assert_parity(bt(res), want, cap_of(shapes) * 50.0, what=f"heat {hour_shift}")
+    labels, _ = O.day_bins(ds_full.coords["time"], hour_shift)
+    assert list(pd.DatetimeIndex(res.coords["time"])) == list(labels)
+
+
+# ------------------------------------------------------------------ orchestration semantics
+
+
+def test_no_matrix_modes(ds_full):
+    c = ab.Cutout(data=ds_full)
+    od = oracle_ds(ds_full)
+    t = ab.get_windturbineconfig("Vestas_V112_3MW")
+    cube = c.wind("Vestas_V112_3MW", aggregate_time=None)
+    assert cube.dims == ("time", "y", "x")
+    want = O.convert_wind(od, t)
+    assert_parity(cube.values, want, what="wind cells")
+    assert_parity(c.wind("Vestas_V112_3MW", aggregate_time="mean").values, want.mean(0), what="wind mean")
+    assert_parity(c.wind("Vestas_V112_3MW", aggregate_time="sum").values, want.sum(0), 72.0, what="wind sum")
+    with pytest.warns(FutureWarning, match="legacy"):
+        leg = c.pv("CSi", "latitude_optimal")
+    pvw = O.convert_pv(od, ab.get_solarpanelconfig("CSi"), O.get_orientation("latitude_optimal"))
+    assert leg.dims == ("y", "x")
+    assert_parity(leg.values, pvw.sum(0), 72.0, what="pv legacy sum")
+    hd = c.heat_demand(aggregate_time=None)
+    hw, labels = O.convert_heat_demand(od, 15.0, 1.0, 0.0, 0.0)
+    assert_parity(hd.values, hw, 50.0, what="heat cells")
+    assert_parity(c.heat_demand(aggregate_time="sum").values, hw.sum(0), 150.0, what="heat sum")
+
+
+def test_per_unit_and_time_aggregation(ds_full, shapes):
+    c = ab.Cutout(data=ds_full)
+    od = oracle_ds(ds_full)
+    t = ab.get_windturbineconfig("Vestas_V112_3MW")
+    for agg in ("mean", "sum", None):
+        res = c.wind("Vestas_V112_3MW", matrix=shapes, per_unit=True, aggregate_time=agg)
+        want = O.convert_and_aggregate(od, O.convert_wind, matrix=shapes, per_unit=True,
+                                       aggregate_time=agg, turbine=t)
+        got = bt(res) if agg is None else res.values
+        assert_parity(got, want, 72.0 if agg == "sum" else 1.0, what=f"per_unit {agg}")
+        assert res.attrs["units"] == "p.u."
+    # empty bus -> capacity 0 -> per-unit 0 (convert.py:264-266)
+    m = sp.vstack([shapes, sp.csr_matrix((1, shapes.shape[1]))]).tocsr()
+    res = c.wind("Vestas_V112_3MW", matrix=m, per_unit=True, aggregate_time=None)
+    assert (bt(res)[:, -1] == 0).all()
+    with pytest.warns(FutureWarning, match="legacy"):
+        leg = c.wind("Vestas_V112_3MW", matrix=shapes)
+    assert "time" in leg.dims
+    idx = pd.Index([f"bus{i}" for i in range(23)], name="bus")
+    res = c.wind("Vestas_V112_3MW", matrix=shapes, index=idx, aggregate_time="mean")
+    assert res.dims == ("bus",) and list(res.coords["bus"]) == list(idx)
+    with pytest.raises(ValueError, match="single dimension|pandas index"):
+        c.wind("Vestas_V112_3MW", matrix=shapes, index=[1, 2, 3], aggregate_time=None)
+
+
+def test_reference_aggregate_time_suite_on_gpu():
+    """test/test_aggregate_time.py ported: MockCutout + identity_convert, layout path."""
+    rng = np.random.RandomState(42)
+    times = pd.date_range("2020-01-01", periods=24, freq="h")
+    var = rng.rand(24, 3, 4)
+    ds = ab.Dataset({"var": var}, coords=dict(time=times, y=[50.0, 51.0, 52.0], x=[5.0, 6.0, 7.0, 8.0]))
+    cutout = ab.Cutout(data=ds)
+
+    def identity_convert(d, **kwargs):
+        return d["var"]
+
+    layout = ab.DataArray(np.ones((3, 4)), {"y": ds.coords["y"], "x": ds.coords["x"]}, ("y", "x"))
+    ts = ab.convert_and_aggregate(cutout, identity_convert, layout=layout, aggregate_time=None)
+    assert "time" in ts.dims
+    np.testing.assert_allclose(ts.values[0], var.reshape(24, -1).sum(1), rtol=1e-6)
+    mean = ab.convert_and_aggregate(cutout, identity_convert, layout=layout, aggregate_time="mean")
+    assert "time" not in mean.dims
+    np.testing.assert_allclose(mean.values, ts.mean("time").values, rtol=1e-6)
+    tot = ab.convert_and_aggregate(cutout, identity_convert, layout=layout, aggregate_time="sum")
+    np.testing.assert_allclose(tot.values, ts.sum("time").values, rtol=1e-6)
+    with pytest.warns(FutureWarning, match="aggregate_time='legacy'"):
+        r = ab.convert_and_aggregate(cutout, identity_convert, layout=layout)
+    assert "time" in r.dims
+    lay2 = layout * 2.0
+    pu = ab.convert_and_aggregate(cutout, identity_convert, layout=lay2, per_unit=True, aggregate_time="mean")
+    pu_ts = ab.convert_and_aggregate(cutout, identity_convert, layout=lay2, per_unit=True, aggregate_time=None)
+    np.testing.assert_allclose(pu.values, pu_ts.mean("time").values, rtol=1e-6)
+    np.testing.assert_allclose(pu_ts.values[0], var.reshape(24, -1).mean(1), rtol=1e-6)
+    with pytest.warns(FutureWarning, match="capacity_factor_timeseries is deprecated"):
+        r = ab.convert_and_aggregate(cutout, identity_convert, layout=layout, capacity_factor_timeseries=True)
+    assert "time" in r.dims
+
+
+# ------------------------------------------------------------------ plans / matrices / paths
+
+
+def test_plan_edge_cases(ds_full):
+    c = ab.Cutout(data=ds_full)
+    od = oracle_ds(ds_full)
+    t = ab.get_windturbineconfig("Vestas_V112_3MW")
+    S = 70 * 45
+    rng = np.random.default_rng(0)
+    mats = {
+        "one_bus_all_cells": sp.csr_matrix(np.ones((1, S))),
+        "identity_one_bus_per_cell": sp.identity(S, format="csr"),  # two-pass fallback
+        "random_sparse": sp.random(11, S, density=0.02, random_state=3, format="csr"),
+        "dense_rows": sp.csr_matrix(rng.uniform(0, 1, size=(5, S))),
+        "empty": sp.csr_matrix((4, S)),
+        "duplicates": sp.csr_matrix((np.ones(6), ([0, 0, 1, 1, 1, 2], [5, 5, 7, 7, 7, S - 1])), shape=(3, S)),
+        "negative_and_zero_weights": sp.csr_matrix(
+            (np.array([-1.5, 0.0, 2.0]), ([0, 0, 1], [0, 1, 2])), shape=(2, S)),
+    }
+    infos = {}
+    for name, m in mats.items():
+        res = c.wind("Vestas_V112_3MW", matrix=m, aggregate_time=None)
+        want = O.convert_and_aggregate(od, O.convert_wind, matrix=m, aggregate_time=None, turbine=t)
+        cap = np.asarray(abs(sp.csr_matrix(m)).sum(-1)).flatten()
+        assert_parity(bt(res), want, cap, what=name)
+        infos[name] = engine.get_plan(m, 45, 70).info
+    assert infos["identity_one_bus_per_cell"]["fused"] == 0
+    assert infos["one_bus_all_cells"]["fused"] == 1
+    assert infos["empty"]["n_active_tiles"] == 0
+    with pytest.raises(ValueError, match="columns"):
+        c.wind("Vestas_V112_3MW", matrix=np.ones((2, 10)), aggregate_time=None)
+
+
+def test_generic_convert_func_uses_gpu_spmm(ds_full, shapes):
+    c = ab.Cutout(data=ds_full)
+
+    def convert_custom(ds, scale):
+        return ds["temperature"] * scale
+
+    n0 = _lib.launch_count()
+    res = c.convert_and_aggregate(convert_custom, matrix=shapes, aggregate_time=None, scale=0.5)
+    assert _lib.launch_count() > n0
+    want = (shapes @ (0.5 * ds_full.raw("temperature").astype(np.float64)).reshape(72, -1).T).T
+    assert_parity(bt(res), want, cap_of(shapes) * 300, what="generic spmm")
+
+
+def test_device_resident_matches_host_streaming(ds_full, shapes):
+    """Same result through atl_*_reduce (device tensors) and atl_*_reduce_host
+    (pinned/pageable host streaming with small slabs)."""
+    host = ab.Cutout(data=ds_full)
+    dev = host.to_device()
+    a = host.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values
+    b = dev.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-6)
+    plan = engine.get_plan(shapes, 45, 70)
+    spec_fields = {k: ds_full.raw(k) for k in ("influx_toa", "influx_direct", "influx_diffuse", "albedo", "temperature")}
+    from atlite_b200.convert import _PvSpec
+
+    spec = _PvSpec(ds_full, ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
+    whole = spec.op.reduce(plan, spec_fields)
+    chunked = spec.op.reduce(plan, spec_fields, chunk_steps=7)  # ragged slabs through the ring
+    np.testing.assert_allclose(whole, chunked, rtol=2e-5, atol=1e-6)
+    hh = host.heat_demand(matrix=shapes, aggregate_time=None, hour_shift=3.0).values
+    hd = dev.heat_demand(matrix=shapes, aggregate_time=None, hour_shift=3.0).values
+    np.testing.assert_allclose(hh, hd, rtol=2e-5, atol=1e-4)
+
+
+def test_time_slab_offsets(ds_full, shapes):
+    """A slab [t0, t0+nt) of the operator's time axis equals the same rows of the whole."""
+    from atlite_b200.convert import _PvSpec
+
+    dev = ab.Cutout(data=ds_full).to_device()
+    spec = _PvSpec(dev.data, ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
+    plan = engine.get_plan(shapes, 45, 70)
+    whole = spec.op.reduce(plan, spec.fields).cpu().numpy()
+    part = spec.op.reduce(plan, {k: v[30:61] for k, v in spec.fields.items()}, t0=30, nt=31).cpu().numpy()
+    np.testing.assert_allclose(part, whole[30:61], rtol=2e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ size-independent properties
+
+
+def test_properties_at_scale():
+    """Bigger than the oracle is comfortable with: check structure instead.
+    (a) linearity in the weights; (b) a partition of the grid sums to the
+    all-cells bus; (c) per-cell cube reduced on the host == fused result."""
+    nx, ny, nt = 256, 160, 240
+    ds = syn.make_dataset(nx, ny, nt, kinds=("pv",))
+    c = ab.Cutout(data=ds).to_device()
+    m = syn.make_shapes(nx, ny, 150)
+    kw = dict(panel="CSi", orientation="latitude_optimal", aggregate_time=None)
+    r1 = bt(c.pv(matrix=m, **kw))
+    r3 = bt(c.pv(matrix=m * 3.0, **kw))
+    np.testing.assert_allclose(r3, 3.0 * r1, rtol=1e-5, atol=1e-5)
+    allc = bt(c.pv(matrix=sp.csr_matrix(np.ones((1, nx * ny))), **kw))[:, 0]
+    np.testing.assert_allclose(r1.sum(1), allc, rtol=5e-5, atol=1e-3)  # border weights sum to 1 per cell
+    cube = c.pv("CSi", "latitude_optimal", aggregate_time=None).values.reshape(nt, -1).astype(np.float64)
+    np.testing.assert_allclose(r1, (m @ cube.T).T, rtol=5e-5, atol=1e-4)
+    assert (cube >= 0).all() and not np.isnan(cube).any() and cube.max() < 1.2
