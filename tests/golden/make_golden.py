@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""Generate the golden vectors that pin the oracle:  run the REFERENCE'S OWN
+source (atlite/convert.py, aggregate.py, wind.py, pv/*.py, resource.py) from
+/root/reference on small seeded synthetic cutouts and store inputs + outputs.
+
+The reference cannot be imported as a package in the build container
+(xarray / dask / geopandas are not installed and there is no network), so its
+hot-path modules are loaded from their files under the container stand-ins of
+``xr_shim.py``; every formula that executes is the reference's own line.
+
+    python tests/golden/make_golden.py        # needs /root/reference; writes tests/golden/*.npz
+
+The outputs are committed; tests/test_oracle_vs_reference.py (CPU) checks the
+oracle against them, so nothing reads /root/reference at test time.
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import xr_shim  # noqa: E402
+
+from atlite_b200 import synthetic as syn  # noqa: E402  (input generator only)
+
+warnings.simplefilter("ignore")
+conv = xr_shim.install()
+import atlite.resource as ref_resource  # noqa: E402  (the reference's module, loaded by the shim)
+from atlite.pv.orientation import get_orientation as ref_get_orientation  # noqa: E402
+from atlite.pv.solar_position import SolarPosition as RefSolarPosition  # noqa: E402
+
+
+class MockCutout:  # reference test/test_aggregate_time.py:13-18
+    def __init__(self, data):
+        self.data = data
+        grid = np.array([(x, y) for y in np.asarray(data.coords["y"].values) for x in np.asarray(data.coords["x"].values)])
+        self.grid = pd.DataFrame(grid, columns=["x", "y"])
+
+
+MockCutout.convert_and_aggregate = conv.convert_and_aggregate  # bound as in cutout.py:659
+
+
+def ref_dataset(fields, time, x, y):
+    return xr_shim.Dataset({k: (("time", "y", "x"), v) for k, v in fields.items()},
+                           coords=dict(time=time, x=x, y=y, lon=x, lat=y), attrs={"module": "era5"})
+
+
+def values_tb(res):
+    """Values in the oracle's layout, transposed BY DIM NAME: (time, bus) (the reference's
+    NumPy branch returns (bus, time), aggregate.py:34-35) and (time, y, x) (the reference's
+    per-cell PV cube comes out as (y, time, x): xarray orders dims by first appearance and
+    sin(slope[y]) leads the product in pv/orientation.py:115)."""
+    if res.ndim == 2 and "time" in res.dims:
+        other = [d for d in res.dims if d != "time"][0]
+        return np.asarray(res.transpose("time", other).values)
+    if res.ndim == 3:
+        return np.asarray(res.transpose("time", "y", "x").values)
+    return np.asarray(res.values)
+
+
+def main():
+    nx, ny, nt, nbus = 14, 9, 54, 5
+    base = syn.make_dataset(nx, ny, nt, x0=-8.0, y0=-30.0, dx=1.5, dy=7.5, start="2013-03-09 05:00",
+                            extra=("wnd_shear_exp", "humidity"))
+    x, y, time = base.coords["x"], base.coords["y"], base.coords["time"]
+    F = {k: np.asarray(base.raw(k)) for k in base.keys()}
+    m = syn.make_shapes(nx, ny, nbus)
+    lay = syn.make_layout(nx, ny)
+    out = {"x": x, "y": y, "time_ns": pd.DatetimeIndex(time).as_unit("ns").asi8,
+           "matrix_data": m.data, "matrix_indices": m.indices, "matrix_indptr": m.indptr,
+           "matrix_shape": np.array(m.shape), "layout": lay}
+    for k, v in F.items():
+        out["in_" + k] = v
+    cases = []
+
+    def run(name, func, ds, **kw):
+        res = func(MockCutout(ds), **kw)
+        if isinstance(res, tuple):
+            out[f"out_{name}"] = values_tb(res[0])
+            out[f"out_{name}__capacity"] = np.asarray(res[1].values)
+        else:
+            out[f"out_{name}"] = values_tb(res)
+        r0 = res[0] if isinstance(res, tuple) else res
+        out[f"dims_{name}"] = np.array(list(r0.dims))
+        cases.append(name)
+
+    pv_names = ["influx_toa", "influx_direct", "influx_diffuse", "albedo", "temperature"]
+    ds_pv = ref_dataset({k: F[k] for k in pv_names}, time, x, y)
+    ds_wind = ref_dataset({k: F[k] for k in ("wnd100m", "roughness", "wnd_shear_exp")}, time, x, y)
+    ds_t = ref_dataset({"temperature": F["temperature"]}, time, x, y)
+
+    # ---- wind (convert.py:634-744, wind.py:24-128, resource.py)
+    for turb in ("Vestas_V112_3MW", "Enercon_E126_7500kW"):
+        for method in ("logarithmic", "power"):
+            run(f"wind|{turb}|{method}", conv.wind, ds_wind, turbine=turb, matrix=m,
+                interpolation_method=method, aggregate_time=None)
+    run("wind|Vestas_V112_3MW|smooth", conv.wind, ds_wind, turbine="Vestas_V112_3MW", smooth=True,
+        matrix=m, aggregate_time=None)
+    t100 = dict(ref_resource.get_windturbineconfig("Vestas_V112_3MW"), hub_height=100)
+    run("wind|hub100|fastlane", conv.wind, ds_wind, turbine=t100, matrix=m, aggregate_time=None)
+    run("wind|cells", conv.wind, ds_wind, turbine="Vestas_V112_3MW", aggregate_time=None)
+    run("wind|cells_mean", conv.wind, ds_wind, turbine="Vestas_V112_3MW", aggregate_time="mean")
+    xl = xr_shim.DataArray(lay, {"y": y, "x": x}, ("y", "x"))
+    run("wind|layout_capacity", conv.wind, ds_wind, turbine="Vestas_V112_3MW", matrix=m, layout=xl,
+        return_capacity=True, aggregate_time=None)
+    run("wind|per_unit_mean", conv.wind, ds_wind, turbine="Vestas_V112_3MW", matrix=m, per_unit=True,
+        aggregate_time="mean")
+    run("wind|layout_only_sum", conv.wind, ds_wind, turbine="Vestas_V112_3MW", layout=xl, aggregate_time="sum")
+    sm = ref_resource.windturbine_smooth(ref_resource.get_windturbineconfig("Vestas_V112_3MW"))
+    out["smooth_V"], out["smooth_POW"] = sm["V"], sm["POW"]
+
+    # ---- pv (convert.py:840-936, pv/*.py)
+    pv_cases = {
+        "CSi|latitude_optimal|None|simple": dict(panel="CSi", orientation="latitude_optimal"),
+        "CdTe|flat|None|simple": dict(panel="CdTe", orientation={"slope": 0.0, "azimuth": 0.0}),
+        "KANENA|latitude_optimal|None|simple": dict(panel="KANENA", orientation="latitude_optimal"),
+        "CSi|latitude|None|other": dict(panel="CSi", orientation="latitude", trigon_model="other"),
+        "CSi|s35a160|None|other": dict(panel="CSi", orientation={"slope": 35.0, "azimuth": 160.0}, trigon_model="other"),
+        "CSi|s0a180|horizontal|simple": dict(panel="CSi", orientation={"slope": 0.0, "azimuth": 180.0}, tracking="horizontal"),
+        "CSi|s30a170|tilted_horizontal|simple": dict(panel="CSi", orientation={"slope": 30.0, "azimuth": 170.0}, tracking="tilted_horizontal"),
+        "CSi|s30a180|vertical|simple": dict(panel="CSi", orientation={"slope": 30.0, "azimuth": 180.0}, tracking="vertical"),
+        "CdTe|s30a180|dual|simple": dict(panel="CdTe", orientation={"slope": 30.0, "azimuth": 180.0}, tracking="dual"),
+        "CSi|s25a200|horizontal|other": dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="horizontal", trigon_model="other"),
+        "CSi|s25a200|tilted_horizontal|other": dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="tilted_horizontal", trigon_model="other"),
+        "CSi|s25a200|dual|other": dict(panel="CSi", orientation={"slope": 25.0, "azimuth": 200.0}, tracking="dual", trigon_model="other"),
+    }
+    for name, kw in pv_cases.items():
+        run(f"pv|{name}", conv.pv, ds_pv, matrix=m, aggregate_time=None, **kw)
+    run("pv|cells", conv.pv, ds_pv, panel="CSi", orientation="latitude_optimal", aggregate_time=None)
+    # input variants: total influx + Reindl split, outflux albedo, stored solar position
+    infl = F["influx_direct"] + F["influx_diffuse"]
+    ds_inf = ref_dataset({"influx_toa": F["influx_toa"], "influx": infl, "albedo": F["albedo"],
+                          "temperature": F["temperature"]}, time, x, y)
+    run("pv|influx_simple", conv.pv, ds_inf, panel="CSi", orientation="latitude_optimal", matrix=m,
+        aggregate_time=None)
+    ds_enh = ref_dataset({"influx_toa": F["influx_toa"], "influx": infl, "albedo": F["albedo"],
+                          "temperature": F["temperature"], "humidity": F["humidity"]}, time, x, y)
+    run("pv|influx_enhanced", conv.pv, ds_enh, panel="CSi", orientation="latitude_optimal", matrix=m,
+        aggregate_time=None)
+    outflux = infl * F["albedo"]
+    out["in_outflux"] = outflux
+    ds_out = ref_dataset({"influx_toa": F["influx_toa"], "influx_direct": F["influx_direct"],
+                          "influx_diffuse": F["influx_diffuse"], "outflux": outflux,
+                          "temperature": F["temperature"]}, time, x, y)
+    run("pv|outflux", conv.pv, ds_out, panel="CSi", orientation="latitude_optimal", matrix=m,
+        aggregate_time=None)
+    sp_ = RefSolarPosition(ds_pv)
+    out["solar_altitude"], out["solar_azimuth"] = sp_["altitude"].values, sp_["azimuth"].values
+    ds_st = ref_dataset({**{k: F[k] for k in pv_names}, "solar_altitude": sp_["altitude"].values,
+                         "solar_azimuth": sp_["azimuth"].values}, time, x, y)
+    run("pv|stored_solar", conv.pv, ds_st, panel="CSi", orientation="latitude_optimal", matrix=m,
+        aggregate_time=None)
+
+    # ---- heat demand (convert.py:405-471)
+    for hs in (0.0, 4.0, -5.0):
+        run(f"heat|{hs}", conv.heat_demand, ds_t, threshold=17.0, a=1.3, constant=0.2, hour_shift=hs,
+            matrix=m, aggregate_time=None)
+    run("heat|cells", conv.heat_demand, ds_t, aggregate_time=None)
+
+    out["cases"] = np.array(cases)
+    path = os.path.join(HERE, "reference_outputs.npz")
+    np.savez_compressed(path, **out)
+    print(f"{len(cases)} cases -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
+if __name__ == "__main__":
+    main()
