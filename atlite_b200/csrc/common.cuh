@@ -60,26 +60,58 @@ inline GridDev make_grid(int ny, int nx) {
 struct PlanDev {
   const int32_t* tile_slot_ptr;  // [n_tiles + 1]
   const int32_t* slot_row;       // [n_slots] bus index of each (tile, bus) slot
-  const float4* slot_w4;         // [n_slots * 32] weights: lane l -> rows 0..3 of column l
+  const float4* slot_w4;         // [n_slots * 32] weights: lane l -> its 4 cells (layout per `vec`)
   const int32_t* active_tiles;   // [n_active]
   int32_t n_active;
   int32_t n_bus;
 };
 
-struct TileGeom {
-  int x;           // column handled by this lane
-  int y0;          // first row of the tile
-  int base;        // y0 * nx + x  (flat cell offset of row 0)
-  unsigned valid;  // bit r set: cell (y0 + r, x) lies inside the grid
+// Two lane layouts over the same 32 x 4 tile:
+//  * SCALAR (any nx): lane l owns column 32*tx + l and rows 4*ty .. 4*ty+3; four
+//    scalar loads per field, each a coalesced 128-byte row segment.
+//  * VEC (nx % 4 == 0, 16-byte aligned fields): lane l owns row 4*ty + l/8 and the
+//    four consecutive columns 32*tx + 4*(l%8) ..+3: ONE 16-byte load per field
+//    (a warp still touches four full 128-byte lines), a quarter of the address
+//    arithmetic.
+// Cell i of a lane is (cell_y(i), cell_x(i)); `valid` has bit i set if it lies in
+// the grid.  Load offsets are CLAMPED into the grid so loads never need a
+// predicate; out-of-grid lanes read a border cell whose value is discarded.
+template <bool VEC>
+struct TileGeomT;
+
+template <>
+struct TileGeomT<false> {
+  int x, y0;
+  unsigned valid;
+  int off[4];
+  __host__ __device__ int cell_x(int) const { return x; }
+  __host__ __device__ int cell_y(int i) const { return y0 + i; }
+};
+template <>
+struct TileGeomT<true> {
+  int x0, y;
+  unsigned valid;
+  int off;  // flat offset of the first of the 4 cells (multiple of 4)
+  __host__ __device__ int cell_x(int i) const { return x0 + i; }
+  __host__ __device__ int cell_y(int) const { return y; }
 };
 
+// position of cell (iy, ix) inside its tile's 128-entry weight vector
+__host__ __device__ inline int tile_local_index(bool vec, int iy, int ix) {
+  const int lx = ix % TILE_X, ly = iy % TILE_Y;
+  return vec ? ((ly * 8 + lx / 4) * 4 + (lx & 3)) : (lx * 4 + ly);
+}
+
 #ifdef __CUDACC__
-__device__ __forceinline__ TileGeom make_geom(int tile, int lane, const GridDev& gd) {
-  TileGeom g;
+template <bool VEC>
+__device__ __forceinline__ TileGeomT<VEC> make_geom(int tile, int lane, const GridDev& gd);
+
+template <>
+__device__ __forceinline__ TileGeomT<false> make_geom<false>(int tile, int lane, const GridDev& gd) {
+  TileGeomT<false> g;
   const int tx = tile % gd.n_tx, ty = tile / gd.n_tx;
   g.x = tx * TILE_X + lane;
   g.y0 = ty * TILE_Y;
-  g.base = g.y0 * gd.nx + g.x;
   unsigned v = 0;
   if (g.x < gd.nx) {
 #pragma unroll
@@ -87,6 +119,19 @@ __device__ __forceinline__ TileGeom make_geom(int tile, int lane, const GridDev&
       if (g.y0 + r < gd.ny) v |= 1u << r;
   }
   g.valid = v;
+  const int xc = min(g.x, gd.nx - 1);
+#pragma unroll
+  for (int r = 0; r < TILE_Y; ++r) g.off[r] = min(g.y0 + r, gd.ny - 1) * gd.nx + xc;
+  return g;
+}
+template <>
+__device__ __forceinline__ TileGeomT<true> make_geom<true>(int tile, int lane, const GridDev& gd) {
+  TileGeomT<true> g;
+  const int tx = tile % gd.n_tx, ty = tile / gd.n_tx;
+  g.x0 = tx * TILE_X + 4 * (lane & 7);
+  g.y = ty * TILE_Y + (lane >> 3);
+  g.valid = (g.x0 < gd.nx && g.y < gd.ny) ? 0xFu : 0u;  // nx % 4 == 0: all 4 or none
+  g.off = min(g.y, gd.ny - 1) * gd.nx + min(g.x0, gd.nx - 4);
   return g;
 }
 
@@ -100,58 +145,111 @@ __device__ __forceinline__ float warp_sum(float p) {
 // weight / table lines stay resident.
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
-// Load the 4 rows of one field for this lane at time step t (slab-relative).
-__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t S, int nx,
-                                      const TileGeom& g, int t, float (&o)[4]) {
-  const float* p = f + (int64_t)t * S + g.base;
-#pragma unroll
-  for (int r = 0; r < TILE_Y; ++r) o[r] = (g.valid >> r) & 1u ? ld_stream(p + r * nx) : 0.f;
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p));
+  return v;
 }
-__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t S, int nx,
-                                      const TileGeom& g, int t, float (&o)[4]) {
-  const double* p = f + (int64_t)t * S + g.base;
+
+// Load the lane's 4 cells of one field at time step t (slab-relative): one
+// warp-uniform slab pointer + 32-bit per-lane offsets.
+__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t S,
+                                      const TileGeomT<false>& g, int t, float (&o)[4]) {
+  const float* p = f + (int64_t)t * S;
+#pragma unroll
+  for (int r = 0; r < TILE_Y; ++r) o[r] = ld_stream(p + g.off[r]);
+}
+__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t S,
+                                      const TileGeomT<true>& g, int t, float (&o)[4]) {
+  const float4 v = ld_stream4(f + (int64_t)t * S + g.off);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t S,
+                                      const TileGeomT<false>& g, int t, float (&o)[4]) {
+  const double* p = f + (int64_t)t * S;
+#pragma unroll
+  for (int r = 0; r < TILE_Y; ++r) o[r] = (float)ld_stream(p + g.off[r]);
+}
+__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t S,
+                                      const TileGeomT<true>& g, int t, float (&o)[4]) {
+  const double* p = f + (int64_t)t * S + g.off;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r] = (float)ld_stream(p + r);
+}
+
+// Store the lane's 4 per-cell values into a (y, x) plane.
+__device__ __forceinline__ void store4(float* __restrict__ plane, const GridDev& gd,
+                                       const TileGeomT<false>& g, const float (&v)[4]) {
 #pragma unroll
   for (int r = 0; r < TILE_Y; ++r)
-    o[r] = (g.valid >> r) & 1u ? (float)ld_stream(p + r * nx) : 0.f;
+    if ((g.valid >> r) & 1u) plane[(g.y0 + r) * gd.nx + g.x] = v[r];
+}
+__device__ __forceinline__ void store4(float* __restrict__ plane, const GridDev& gd,
+                                       const TileGeomT<true>& g, const float (&v)[4]) {
+  if (g.valid) *reinterpret_cast<float4*>(plane + g.y * gd.nx + g.x0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void atomic_add4(float* __restrict__ plane, const GridDev& gd,
+                                            const TileGeomT<false>& g, const float (&v)[4]) {
+#pragma unroll
+  for (int r = 0; r < TILE_Y; ++r)
+    if ((g.valid >> r) & 1u) atomicAdd(plane + (g.y0 + r) * gd.nx + g.x, v[r]);
+}
+__device__ __forceinline__ void atomic_add4(float* __restrict__ plane, const GridDev& gd,
+                                            const TileGeomT<true>& g, const float (&v)[4]) {
+  if (g.valid) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) atomicAdd(plane + g.y * gd.nx + g.x0 + r, v[r]);
+  }
+}
+
+// Exact path for tiles holding a NaN/Inf: zero weights must not touch the value
+// (a sparse matrix never multiplies entries it does not store: aggregate.py:25 /
+// scipy CSR product).  Kept out of line: it is cold.
+static __device__ __noinline__ void reduce_slots_exact(float v0, float v1, float v2, float v3, int s_beg,
+                                               int s_end, const PlanDev& plan,
+                                               float* __restrict__ out_row, int lane) {
+#pragma unroll 1
+  for (int s = s_beg; s < s_end; ++s) {
+    const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
+    float p = 0.f;
+    if (w.x != 0.f) p += w.x * v0;
+    if (w.y != 0.f) p += w.y * v1;
+    if (w.z != 0.f) p += w.z * v2;
+    if (w.w != 0.f) p += w.w * v3;
+    p = warp_sum(p);
+    if (lane == 0) atomicAdd(out_row + __ldg(plan.slot_row + s), p);
+  }
 }
 
 // Reduce the 4 per-cell values of every lane into the tile's (tile, bus) slots
 // and add the warp totals to out_row[bus].  Weight lines are L1-resident after
-// the first time step.  A NaN/Inf anywhere in the warp takes the exact path in
-// which zero weights do not touch the value (a sparse matrix never multiplies
-// entries it does not store: aggregate.py:25 / scipy CSR product).
+// the first time step.
 __device__ __forceinline__ void reduce_slots(const float (&v)[4], int s_beg, int s_end,
                                              const PlanDev& plan, float* __restrict__ out_row,
                                              int lane) {
   const float chk = (v[0] + v[1]) + (v[2] + v[3]);
   const bool bad = !(fabsf(chk) <= 3.0e38f);
-  if (!__any_sync(0xffffffffu, bad)) {
-    for (int s = s_beg; s < s_end; ++s) {
-      const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
-      float p = fmaf(w.x, v[0], fmaf(w.y, v[1], fmaf(w.z, v[2], w.w * v[3])));
-      p = warp_sum(p);
-      if (lane == 0) atomicAdd(out_row + __ldg(plan.slot_row + s), p);
-    }
-  } else {
-    for (int s = s_beg; s < s_end; ++s) {
-      const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
-      float p = 0.f;
-      if (w.x != 0.f) p += w.x * v[0];
-      if (w.y != 0.f) p += w.y * v[1];
-      if (w.z != 0.f) p += w.z * v[2];
-      if (w.w != 0.f) p += w.w * v[3];
-      p = warp_sum(p);
-      if (lane == 0) atomicAdd(out_row + __ldg(plan.slot_row + s), p);
-    }
+  if (__any_sync(0xffffffffu, bad)) {
+    reduce_slots_exact(v[0], v[1], v[2], v[3], s_beg, s_end, plan, out_row, lane);
+    return;
+  }
+#pragma unroll 1
+  for (int s = s_beg; s < s_end; ++s) {
+    const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
+    float p = fmaf(w.x, v[0], fmaf(w.y, v[1], fmaf(w.z, v[2], w.w * v[3])));
+    p = warp_sum(p);
+    if (lane == 0) atomicAdd(out_row + __ldg(plan.slot_row + s), p);
   }
 }
 #endif  // __CUDACC__
@@ -167,6 +265,7 @@ struct AtlPlan {
   int32_t n_tiles, n_active;
   int64_t n_slots;
   bool fused;
+  bool vec;  // weight layout / kernels: VEC lane layout (nx % 4 == 0)
   // device arrays
   int32_t* d_tile_slot_ptr = nullptr;
   int32_t* d_slot_row = nullptr;

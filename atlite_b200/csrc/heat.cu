@@ -21,7 +21,8 @@ struct HeatParams {
 constexpr int HEAT_UNROLL = 6;
 
 // daily mean + degree-day formula for the lane's 4 cells of day d
-__device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeom& g, int d,
+template <bool VEC>
+__device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<VEC>& g, int d,
                                          float (&v)[4]) {
   const int s0 = __ldg(hp.day_start + d) - hp.base, s1 = __ldg(hp.day_start + d + 1) - hp.base;
   float sum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
@@ -30,7 +31,7 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeom& g
 #pragma unroll
     for (int u = 0; u < HEAT_UNROLL; ++u) {
       if (s + u < s1) {
-        load4(hp.temp, hp.S, hp.nx, g, s + u, x[u]);
+        load4(hp.temp, hp.S, g, s + u, x[u]);
       } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) x[u][r] = __int_as_float(0x7fc00000);  // NaN: skipped
@@ -57,7 +58,7 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeom& g
 
 // MODE 0: fused reduce -> out (n_days, n_bus); 1: cells -> out (n_days, ny, nx);
 // MODE 2: per-cell sum over days accumulated into out (ny, nx)
-template <int MODE>
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(CTA_THREADS)
     k_heat(const HeatParams hp, const GridDev gd, const PlanDev plan, float* __restrict__ out,
            int n_days, int db) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
     if (ai >= gd.n_tx * gd.n_ty) return;
     tile = ai;
   }
-  const TileGeom g = make_geom(tile, lane, gd);
+  const TileGeomT<VEC> g = make_geom<VEC>(tile, lane, gd);
   const int d0 = blockIdx.y * db, d1 = min(n_days, d0 + db);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float v[4];
@@ -82,20 +83,13 @@ __global__ void __launch_bounds__(CTA_THREADS)
     if (MODE == 0) {
       reduce_slots(v, s_beg, s_end, plan, out + (size_t)d * plan.n_bus, lane);
     } else if (MODE == 1) {
-      float* o = out + (int64_t)d * gd.S + g.base;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if ((g.valid >> r) & 1u) o[r * gd.nx] = v[r];
+      store4(out + (int64_t)d * gd.S, gd, g, v);
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
     }
   }
-  if (MODE == 2) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if ((g.valid >> r) & 1u) atomicAdd(out + g.base + r * gd.nx, acc[r]);
-  }
+  if (MODE == 2) atomic_add4(out, gd, g, acc);
 }
 
 // Phys adaptor used only by the two-pass fallback (never on the fused path).
@@ -180,12 +174,29 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   int db = (int)((n_days * gx + 148LL * 4 * 8 - 1) / (148LL * 4 * 8));
   db = db < 1 ? 1 : (db > 8 ? 8 : db);
   dim3 grid(gx, (unsigned)((n_days + db - 1) / db));
-  if (mode == 0)
-    k_heat<0><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
-  else if (mode == 1)
-    k_heat<1><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
-  else
-    k_heat<2><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+  // lane layout: the plan's for the fused reduce, else by grid width / alignment
+  const bool al = aligned16(temp) && (mode != 1 || aligned16(out));
+  bool vec = op->grid.nx % 4 == 0 && al;
+  if (mode == 0) {
+    vec = plan->vec;
+    ATL_REQUIRE(!vec || al,
+                "field pointers must be 16-byte aligned (nx % 4 == 0 uses 128-bit loads)");
+  }
+  if (vec) {
+    if (mode == 0)
+      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+    else if (mode == 1)
+      k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+    else
+      k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+  } else {
+    if (mode == 0)
+      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+    else if (mode == 1)
+      k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+    else
+      k_heat<2, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+  }
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   return ATL_OK;

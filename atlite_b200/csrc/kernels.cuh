@@ -2,27 +2,31 @@
 // per-cell time sum}" kernels, templated on a physics functor.
 //
 // A physics functor `Phys` provides
+//   static constexpr bool kVec;   lane layout (see common.cuh: TileGeomT<VEC>)
 //   struct Cell;   per-thread constants (geometry of the lane's 4 cells)
 //   struct Raw;    the raw field values of one time step (4 cells)
 //   static constexpr int kSmemFloats;        CTA-shared lookup tables
 //   __device__ void stage(float* smem) const;            (whole CTA, before use)
-//   __device__ void init(Cell&, const TileGeom&, const float* smem) const;
-//   __device__ void load(const Cell&, const TileGeom&, int t, Raw&) const;
-//   __device__ void compute(const Cell&, const TileGeom&, int t, const Raw&,
+//   __device__ void init(Cell&, const Geom&, const float* smem) const;
+//   __device__ void load(const Cell&, const Geom&, int t, Raw&) const;
+//   __device__ void compute(const Cell&, const Geom&, int t, const Raw&,
 //                           float (&v)[4], const float* smem) const;
 // `t` is relative to the slab the functor's field pointers address.
 //
-// Loop structure (all three kernels): a warp owns one 32x4 tile and walks a
-// block of `tb` consecutive time steps; the loads of step t+1 are issued
-// before the arithmetic of step t (register double buffer), so each thread
-// keeps 2 x (#fields x 4) independent 128-byte-coalesced loads in flight.
+// Loop structure: a warp owns one 32x4 tile and walks a block of `tb`
+// consecutive time steps.  Memory latency is hidden by occupancy (PREFETCH=0:
+// few registers, many resident warps) or additionally by a register double
+// buffer (PREFETCH=1: the loads of step t+1 are issued before the arithmetic
+// of step t).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace atl {
 
-template <class Phys>
-__global__ void __launch_bounds__(CTA_THREADS)
+template <class Phys, int PREFETCH, int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
     k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
                    float* __restrict__ out, int nt, int tb) {
   extern __shared__ float smem[];
@@ -31,7 +35,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
   const int ai = blockIdx.x * WARPS_PER_CTA + warp;
   if (ai >= plan.n_active) return;
   const int tile = __ldg(plan.active_tiles + ai);
-  const TileGeom g = make_geom(tile, lane, gd);
+  const auto g = make_geom<Phys::kVec>(tile, lane, gd);
   const int s_beg = __ldg(plan.tile_slot_ptr + tile);
   const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
   const int t0 = blockIdx.y * tb;
@@ -39,26 +43,37 @@ __global__ void __launch_bounds__(CTA_THREADS)
 
   typename Phys::Cell c;
   phys.init(c, g, smem);
-  typename Phys::Raw ra, rb;
   float v[4];
-  phys.load(c, g, t0, ra);
-  for (int t = t0; t < t1; t += 2) {
-    const bool has_b = t + 1 < t1;
-    if (has_b) phys.load(c, g, t + 1, rb);
-    phys.compute(c, g, t, ra, v, smem);
-    reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
-    if (has_b) {
-      if (t + 2 < t1) phys.load(c, g, t + 2, ra);
-      phys.compute(c, g, t + 1, rb, v, smem);
-      reduce_slots(v, s_beg, s_end, plan, out + (size_t)(t + 1) * plan.n_bus, lane);
+  if (PREFETCH) {
+    typename Phys::Raw ra, rb;
+    phys.load(c, g, t0, ra);
+#pragma unroll 1
+    for (int t = t0; t < t1; t += 2) {
+      const bool has_b = t + 1 < t1;
+      if (has_b) phys.load(c, g, t + 1, rb);
+      phys.compute(c, g, t, ra, v, smem);
+      reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
+      if (has_b) {
+        if (t + 2 < t1) phys.load(c, g, t + 2, ra);
+        phys.compute(c, g, t + 1, rb, v, smem);
+        reduce_slots(v, s_beg, s_end, plan, out + (size_t)(t + 1) * plan.n_bus, lane);
+      }
+    }
+  } else {
+    typename Phys::Raw ra;
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+      phys.load(c, g, t, ra);
+      phys.compute(c, g, t, ra, v, smem);
+      reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
     }
   }
 }
 
-// mode 0: store per-cell values out[(t - t_begin), y, x]
-// mode 1: accumulate the (NaN-skipping) time sum into out[y, x]
+// MODE 0: store per-cell values out[(t - t_begin), y, x]
+// MODE 1: accumulate the (NaN-skipping) time sum into out[y, x]
 template <class Phys, int MODE>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 4)
     k_cells(const Phys phys, const GridDev gd, float* __restrict__ out, int t_begin,
             int t_end, int tb) {
   extern __shared__ float smem[];
@@ -66,43 +81,27 @@ __global__ void __launch_bounds__(CTA_THREADS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x * WARPS_PER_CTA + warp;
   if (tile >= gd.n_tx * gd.n_ty) return;
-  const TileGeom g = make_geom(tile, lane, gd);
+  const auto g = make_geom<Phys::kVec>(tile, lane, gd);
   const int t0 = t_begin + blockIdx.y * tb;
   const int t1 = min(t_end, t0 + tb);
 
   typename Phys::Cell c;
   phys.init(c, g, smem);
-  typename Phys::Raw ra, rb;
+  typename Phys::Raw ra;
   float v[4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  auto emit = [&](int t) {
+#pragma unroll 1
+  for (int t = t0; t < t1; ++t) {
+    phys.load(c, g, t, ra);
+    phys.compute(c, g, t, ra, v, smem);
     if (MODE == 0) {
-      float* o = out + (int64_t)(t - t_begin) * gd.S + g.base;
-#pragma unroll
-      for (int r = 0; r < TILE_Y; ++r)
-        if ((g.valid >> r) & 1u) o[r * gd.nx] = v[r];
+      store4(out + (int64_t)(t - t_begin) * gd.S, gd, g, v);
     } else {
 #pragma unroll
-      for (int r = 0; r < TILE_Y; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
-    }
-  };
-  phys.load(c, g, t0, ra);
-  for (int t = t0; t < t1; t += 2) {
-    const bool has_b = t + 1 < t1;
-    if (has_b) phys.load(c, g, t + 1, rb);
-    phys.compute(c, g, t, ra, v, smem);
-    emit(t);
-    if (has_b) {
-      if (t + 2 < t1) phys.load(c, g, t + 2, ra);
-      phys.compute(c, g, t + 1, rb, v, smem);
-      emit(t + 1);
+      for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
     }
   }
-  if (MODE == 1) {
-#pragma unroll
-    for (int r = 0; r < TILE_Y; ++r)
-      if ((g.valid >> r) & 1u) atomicAdd(out + g.base + r * gd.nx, acc[r]);
-  }
+  if (MODE == 1) atomic_add4(out, gd, g, acc);
 }
 
 // Generic CSR gather SpMM: out[t, row] = sum_k val[k] * dense[t, col[k]]
@@ -113,10 +112,17 @@ __global__ void k_csr_spmm(const int64_t* __restrict__ indptr, const int32_t* __
                            const float* __restrict__ val, const float* __restrict__ dense,
                            int64_t S, float* __restrict__ out, int n_bus, int nt);
 
+// Run-time tuning knobs (environment: ATL_VARIANT, ATL_TB), for experiments.
+struct Tuning {
+  int variant = 0;
+  int tb = 0;
+};
+const Tuning& tuning();
+
 inline int pick_tb(int n_cta_x, int64_t nt) {
-  // aim for >= ~8 waves of 148 SMs x 4 resident CTAs, but keep per-CTA
+  // aim for >= ~8 waves of 148 SMs x 6 resident CTAs, but keep the per-CTA
   // prologue (geometry + slot setup) amortised over >= 8 steps
-  const int64_t want = 148LL * 4 * 8;
+  const int64_t want = 148LL * 6 * 8;
   int64_t tb = (nt * n_cta_x + want - 1) / want;
   if (tb < 8) tb = 8;
   if (tb > 64) tb = 64;
@@ -124,6 +130,8 @@ inline int pick_tb(int n_cta_x, int64_t nt) {
   if (tb > nt) tb = nt > 0 ? nt : 1;
   return (int)tb;
 }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <class Phys>
 int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begin,
@@ -147,25 +155,41 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
 int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* out,
                     cudaStream_t st);
 
+// Fused path of one slab.  `Phys` must use the plan's lane layout.
 template <class Phys>
-int launch_reduce(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt,
-                  cudaStream_t st) {
-  if (nt <= 0) return ATL_OK;
-  ATL_REQUIRE(nt < (1LL << 31), "slab too long");
-  if (plan->fused) {
-    ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * plan->n_bus * sizeof(float), st));
-    if (plan->n_active == 0) return ATL_OK;
-    const int gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int tb = pick_tb(gx, nt);
-    dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
-    k_fused_reduce<Phys><<<grid, CTA_THREADS, Phys::kSmemFloats * sizeof(float), st>>>(
-        phys, plan->grid, plan->dev(), out, (int)nt, tb);
-    ++g_launches;
-    ATL_CUDA(cudaGetLastError());
-    return ATL_OK;
+int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, cudaStream_t st) {
+  ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * plan->n_bus * sizeof(float), st));
+  if (plan->n_active == 0) return ATL_OK;
+  const int gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const int tb = tuning().tb > 0 ? tuning().tb : pick_tb(gx, nt);
+  dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
+  const size_t smem = Phys::kSmemFloats * sizeof(float);
+  const GridDev gd = plan->grid;
+  const PlanDev pd = plan->dev();
+  switch (tuning().variant) {
+    case 1:
+      k_fused_reduce<Phys, 1, 4><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
+      break;
+    case 2:
+      k_fused_reduce<Phys, 0, 8><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
+      break;
+    case 3:
+      k_fused_reduce<Phys, 1, 6><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
+      break;
+    default:
+      k_fused_reduce<Phys, 0, 6><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
+      break;
   }
-  // Two-pass fallback for matrices that do not tile (e.g. one bus per cell):
-  // materialise a block of per-cell values, then CSR-gather it.
+  ++g_launches;
+  ATL_CUDA(cudaGetLastError());
+  return ATL_OK;
+}
+
+// Two-pass fallback for matrices that do not tile (e.g. one bus per cell):
+// materialise a block of per-cell values, then CSR-gather it.
+template <class Phys>
+int launch_two_pass(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt,
+                    cudaStream_t st) {
   const int64_t S = plan->grid.S;
   int64_t blk = (256LL << 20) / (S * 4);  // <= 256 MiB scratch
   if (blk < 1) blk = 1;
@@ -183,6 +207,34 @@ int launch_reduce(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt,
   }
   ATL_CUDA(cudaFreeAsync(scratch, st));
   return ATL_OK;
+}
+
+// Dispatch on the lane layout.  `make(vec_tag)` builds the functor for a layout:
+// make(std::true_type{}) -> Phys<VEC>, make(std::false_type{}) -> Phys<SCALAR>.
+// `ptrs_aligned`: every field pointer is 16-byte aligned (needed for VEC).
+template <class Make>
+int dispatch_reduce(Make make, const AtlPlan* plan, bool ptrs_aligned, float* out, int64_t nt,
+                    cudaStream_t st) {
+  if (nt <= 0) return ATL_OK;
+  ATL_REQUIRE(nt < (1LL << 31), "slab too long");
+  if (plan->fused) {
+    if (plan->vec) {
+      ATL_REQUIRE(ptrs_aligned,
+                  "field pointers must be 16-byte aligned (nx % 4 == 0 uses 128-bit loads)");
+      return launch_fused(make(std::true_type{}), plan, out, nt, st);
+    }
+    return launch_fused(make(std::false_type{}), plan, out, nt, st);
+  }
+  if (plan->vec && ptrs_aligned) return launch_two_pass(make(std::true_type{}), plan, out, nt, st);
+  return launch_two_pass(make(std::false_type{}), plan, out, nt, st);
+}
+
+template <class Make>
+int dispatch_cells(Make make, const GridDev& gd, bool ptrs_aligned, float* out, int64_t nt,
+                   bool timesum, cudaStream_t st) {
+  if (gd.nx % 4 == 0 && ptrs_aligned && (timesum || aligned16(out)))
+    return launch_cells(make(std::true_type{}), gd, out, 0, nt, timesum, st);
+  return launch_cells(make(std::false_type{}), gd, out, 0, nt, timesum, st);
 }
 
 }  // namespace atl

@@ -8,6 +8,7 @@
 // reduce the per-cell values of a tile into its slots with warp shuffles and
 // one atomicAdd per (slot, time step) -- per-cell values never reach HBM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -17,6 +18,16 @@ namespace atl {
 
 static thread_local std::string g_err;
 int64_t g_launches = 0;
+
+const Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning x;
+    if (const char* v = getenv("ATL_VARIANT")) x.variant = atoi(v);
+    if (const char* v = getenv("ATL_TB")) x.tb = atoi(v);
+    return x;
+  }();
+  return t;
+}
 
 void set_error(const std::string& msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -57,24 +68,24 @@ int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* 
 
 // Identity physics: the "field" already is the per-cell value (unknown
 // convert_func evaluated upstream) -> fused tile SpMM.
+template <bool VEC>
 struct IdentityPhys {
+  static constexpr bool kVec = VEC;
+  using Geom = TileGeomT<VEC>;
   const float* f;
   int64_t S;
-  int nx;
   struct Cell {};
   struct Raw {
     float v[4];
   };
   static constexpr int kSmemFloats = 0;
   __device__ void stage(float*) const {}
-  __device__ void init(Cell&, const TileGeom&, const float*) const {}
-  __device__ void load(const Cell&, const TileGeom& g, int t, Raw& r) const {
-    load4(f, S, nx, g, t, r.v);
-  }
-  __device__ void compute(const Cell&, const TileGeom&, int, const Raw& r, float (&v)[4],
+  __device__ void init(Cell&, const Geom&, const float*) const {}
+  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const { load4(f, S, g, t, r.v); }
+  __device__ void compute(const Cell&, const Geom& g, int, const Raw& r, float (&v)[4],
                           const float*) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = r.v[i];
+    for (int i = 0; i < 4; ++i) v[i] = ((g.valid >> i) & 1u) ? r.v[i] : 0.f;
   }
 };
 
@@ -105,6 +116,7 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
   ATL_REQUIRE(indptr && (n_bus == 0 || indptr[n_bus] == 0 || (indices && data)),
               "CSR arrays missing");
   const GridDev gd = make_grid(ny, nx);
+  const bool vec = (nx % 4 == 0);  // lane layout of the weight vectors / kernels
   const int64_t nnz_in = n_bus ? indptr[n_bus] : 0;
   const int64_t n_tiles = (int64_t)gd.n_tx * gd.n_ty;
 
@@ -125,7 +137,7 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
       const int64_t tile = (int64_t)(iy / TILE_Y) * gd.n_tx + ix / TILE_X;
       Ent e;
       e.key = tile * (int64_t)n_bus + r;
-      e.local = (ix % TILE_X) * TILE_Y + (iy % TILE_Y);
+      e.local = tile_local_index(vec, iy, ix);
       e.w = (float)data[k];
       ents.push_back(e);
     }
@@ -169,6 +181,7 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
   p->n_active = (int32_t)n_active;
   p->n_slots = n_slots;
   p->fused = fused;
+  p->vec = vec;
 
   auto fail = [&](int rc) {
     atl_plan_destroy(p);
@@ -267,11 +280,13 @@ int atl_spmm(const AtlPlan* plan, const float* dense_dev, int64_t nt, float* out
   ATL_CUDA(cudaSetDevice(plan->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (!plan->fused) return launch_csr_spmm(plan, dense_dev, nt, out_dev, st);
-  IdentityPhys ph;
-  ph.f = dense_dev;
-  ph.S = plan->grid.S;
-  ph.nx = plan->grid.nx;
-  return launch_reduce(ph, plan, out_dev, nt, st);
+  auto make = [&](auto vec) {
+    IdentityPhys<decltype(vec)::value> ph;
+    ph.f = dense_dev;
+    ph.S = plan->grid.S;
+    return ph;
+  };
+  return dispatch_reduce(make, plan, aligned16(dense_dev), out_dev, nt, st);
 }
 
 }  // extern "C"

@@ -36,15 +36,22 @@ enum {  // panel coefficient slots (float, device)
 // (tracking None), solar position computed in-kernel, influx_direct +
 // influx_diffuse + albedo variables.  FAST=false keeps every switch at run
 // time (stored solar position, Reindl split, outflux albedo, tracking modes).
-template <bool FAST>
+template <bool FAST, bool VEC>
 struct PvPhys {
+  static constexpr bool kVec = VEC;
+  using Geom = TileGeomT<VEC>;
+  // cell i of a lane -> index into the per-column / per-row constant arrays: the
+  // SCALAR layout has 1 column x 4 rows per lane, the VEC layout 4 columns x 1 row
+  static constexpr int NXC = VEC ? 4 : 1, NYC = VEC ? 1 : 4;
+  static __device__ __forceinline__ int ix(int i) { return VEC ? i : 0; }
+  static __device__ __forceinline__ int iy(int i) { return VEC ? 0 : i; }
   const float *toa, *dir, *dif, *influx, *alb, *outflux, *temp, *hum;
   const void *salt, *saz;
   const float4* tt;  // per time step (absolute index t_off + t)
   const float2* xt;  // per column
   const float* yt;   // per row, 8 floats
   int64_t S;
-  int nx;
+  int nx, ny;
   int t_off;
   int tracking_, trigon, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model;
   float sin_thr, alt_thr;
@@ -58,8 +65,8 @@ struct PvPhys {
   __device__ __forceinline__ int solar_src() const { return FAST ? ATL_SOLAR_COMPUTED : solar_src_; }
 
   struct Cell {
-    float clon, slon;
-    float sl[4], cl[4], cs[4], ss[4], cph[4], sph[4], hd3[4];
+    float clon[NXC], slon[NXC];
+    float sl[NYC], cl[NYC], cs[NYC], u[NYC], v[NYC], ss[NYC], cph[NYC], sph[NYC], hd3[NYC];
   };
   struct Raw {
     float toa[4], a[4], b[4], alb[4], temp[4], hum[4], salt[4], saz[4];
@@ -67,41 +74,42 @@ struct PvPhys {
   static constexpr int kSmemFloats = 0;
   __device__ void stage(float*) const {}
 
-  __device__ void init(Cell& c, const TileGeom& g, const float*) const {
-    const float2 xl = g.x < nx ? __ldg(xt + g.x) : make_float2(1.f, 0.f);
-    c.clon = xl.x;
-    c.slon = xl.y;
+  __device__ void init(Cell& c, const Geom& g, const float*) const {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if ((g.valid >> r) & 1u) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(yt) + 2 * (g.y0 + r));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(yt) + 2 * (g.y0 + r) + 1);
-        c.sl[r] = a.x; c.cl[r] = a.y; c.cs[r] = a.z; c.ss[r] = a.w;
-        c.cph[r] = b.x; c.sph[r] = b.y; c.hd3[r] = b.z;
-      } else {
-        c.sl[r] = 0.f; c.cl[r] = 1.f; c.cs[r] = 1.f; c.ss[r] = 0.f;
-        c.cph[r] = 1.f; c.sph[r] = 0.f; c.hd3[r] = 0.f;
-      }
+    for (int a = 0; a < NXC; ++a) {
+      const float2 xl = __ldg(xt + min(g.cell_x(VEC ? a : 0), nx - 1));
+      c.clon[a] = xl.x;
+      c.slon[a] = xl.y;
+    }
+#pragma unroll
+    for (int b = 0; b < NYC; ++b) {
+      const int y = min(g.cell_y(VEC ? 0 : b), ny - 1);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(yt) + 2 * y);
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(yt) + 2 * y + 1);
+      c.sl[b] = p0.x; c.cl[b] = p0.y; c.cs[b] = p0.z; c.ss[b] = p0.w;
+      c.cph[b] = p1.x; c.sph[b] = p1.y; c.hd3[b] = p1.z;
+      c.u[b] = p0.w * p1.x;  // sin(slope) cos(azimuth)
+      c.v[b] = p0.w * p1.y;  // sin(slope) sin(azimuth)
     }
   }
 
-  __device__ void load(const Cell&, const TileGeom& g, int t, Raw& r) const {
-    load4(toa, S, nx, g, t, r.toa);
+  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const {
+    load4(toa, S, g, t, r.toa);
     if (irr_branch() == ATL_IRR_DIRECT_DIFFUSE) {
-      load4(dir, S, nx, g, t, r.a);
-      load4(dif, S, nx, g, t, r.b);
+      load4(dir, S, g, t, r.a);
+      load4(dif, S, g, t, r.b);
     } else {
-      load4(influx, S, nx, g, t, r.a);
-      if (clearsky == ATL_CLEARSKY_ENHANCED) load4(hum, S, nx, g, t, r.hum);
+      load4(influx, S, g, t, r.a);
+      if (clearsky == ATL_CLEARSKY_ENHANCED) load4(hum, S, g, t, r.hum);
     }
-    load4(albedo_src() == ATL_ALBEDO_VAR ? alb : outflux, S, nx, g, t, r.alb);
-    load4(temp, S, nx, g, t, r.temp);
+    load4(albedo_src() == ATL_ALBEDO_VAR ? alb : outflux, S, g, t, r.alb);
+    load4(temp, S, g, t, r.temp);
     if (solar_src() == ATL_SOLAR_STORED_F32) {
-      load4((const float*)salt, S, nx, g, t, r.salt);
-      load4((const float*)saz, S, nx, g, t, r.saz);
+      load4((const float*)salt, S, g, t, r.salt);
+      load4((const float*)saz, S, g, t, r.saz);
     } else if (solar_src() == ATL_SOLAR_STORED_F64) {
-      load4((const double*)salt, S, nx, g, t, r.salt);
-      load4((const double*)saz, S, nx, g, t, r.saz);
+      load4((const double*)salt, S, g, t, r.salt);
+      load4((const double*)saz, S, g, t, r.saz);
     }
   }
 
@@ -126,24 +134,28 @@ struct PvPhys {
     }
   }
 
-  __device__ void compute(const Cell& c, const TileGeom& g, int t, const Raw& r, float (&v)[4],
+  __device__ void compute(const Cell& c, const Geom& g, int t, const Raw& r, float (&v)[4],
                           const float*) const {
-    float sd = 0.f, cd = 0.f, ch = 0.f, sh = 0.f;
+    float sd = 0.f, cd = 0.f, ch[NXC], sh[NXC];
     if (solar_src() == ATL_SOLAR_COMPUTED) {
       const float4 q = __ldg(tt + t_off + t);
       sd = q.x;
       cd = q.y;
-      ch = q.z * c.clon - q.w * c.slon;
-      sh = q.w * c.clon + q.z * c.slon;
+#pragma unroll
+      for (int a = 0; a < NXC; ++a) {
+        ch[a] = q.z * c.clon[a] - q.w * c.slon[a];
+        sh[a] = q.w * c.clon[a] + q.z * c.slon[a];
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      const int a = ix(i), b = iy(i);
       // ---- solar position (pv/solar_position.py:103-114)
       float sinalt, cosalt, X, Y;
       if (solar_src() == ATL_SOLAR_COMPUTED) {
-        sinalt = fminf(fmaxf(fmaf(cd * c.cl[i], ch, sd * c.sl[i]), -1.f), 1.f);
-        X = fmaf(-(cd * c.sl[i]), ch, sd * c.cl[i]);
-        Y = -cd * sh;
+        sinalt = fminf(fmaxf(fmaf(cd * c.cl[b], ch[a], sd * c.sl[b]), -1.f), 1.f);
+        X = fmaf(-(cd * c.sl[b]), ch[a], sd * c.cl[b]);
+        Y = -cd * sh[a];
         cosalt = sqrtf(fmaxf(fmaf(-sinalt, sinalt, 1.f), 0.f));
       } else {
         float saz_s, saz_c;
@@ -157,17 +169,17 @@ struct PvPhys {
       const int trk = tracking();
       if (trk == ATL_TRACK_NONE) {
         // sin b cos a cos(phi - az) + cos b sin a, with cos a cos az = X, cos a sin az = Y
-        cosinc = fmaf(c.ss[i], fmaf(c.cph[i], X, c.sph[i] * Y), c.cs[i] * sinalt);
-        cslope = c.cs[i];
+        cosinc = fmaf(c.u[b], X, fmaf(c.v[b], Y, c.cs[b] * sinalt));
+        cslope = c.cs[b];
       } else if (trk == ATL_TRACK_VERTICAL) {
-        cosinc = fmaf(c.ss[i], cosalt, c.cs[i] * sinalt);
-        cslope = c.cs[i];
+        cosinc = fmaf(c.ss[b], cosalt, c.cs[b] * sinalt);
+        cslope = c.cs[b];
       } else if (trk == ATL_TRACK_DUAL) {
         cosinc = 1.f;
-        cslope = (trigon == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[i];  // irradiation.py:216-219
+        cslope = (trigon == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[b];  // irradiation.py:216-219
       } else {
         // q = cos a sin(az - phi), p = cos a cos(az - phi)
-        const float q = fmaf(Y, c.cph[i], -X * c.sph[i]);
+        const float q = fmaf(Y, c.cph[b], -X * c.sph[b]);
         if (trk == ATL_TRACK_HORIZONTAL) {
           // rotation = atan(q / sinalt); slope = |rotation|; the panel azimuth is
           // phi + sign(rotation) pi/2, so cosinc = sign(sinalt) sqrt(sinalt^2 + q^2)
@@ -175,11 +187,11 @@ struct PvPhys {
           cosinc = sinalt > 0.f ? D : 0.f;
           cslope = __fdividef(fabsf(sinalt), D);
         } else {  // tilted_horizontal: rotation = atan2(q, den) after the +-pi fix-ups
-          const float p = fmaf(X, c.cph[i], Y * c.sph[i]);
-          const float den = fmaf(p, c.ss[i], sinalt * c.cs[i]);
+          const float p = fmaf(X, c.cph[b], Y * c.sph[b]);
+          const float den = fmaf(p, c.ss[b], sinalt * c.cs[b]);
           const float E = sqrtf(fmaf(q, q, den * den));
           cosinc = E;  // cos(rot) den + sin(rot) q
-          cslope = __fdividef(fabsf(den) * c.cs[i], E);
+          cslope = __fdividef(fabsf(den) * c.cs[b], E);
         }
       }
       cosinc = fmaxf(cosinc, 0.f);  // :188
@@ -231,7 +243,7 @@ struct PvPhys {
                      fmaf(fmaf(0.5f, cslope, 0.5f), diffuse,
                           albedo * influx_ * fmaf(-0.5f, cslope, 0.5f)));
       } else {
-        float hd3 = c.hd3[i];
+        float hd3 = c.hd3[b];
         if (trk == ATL_TRACK_HORIZONTAL || trk == ATL_TRACK_TILTED_HORIZONTAL) {
           const float s2 = sqrtf(fmaxf(fmaf(-0.5f, cslope, 0.5f), 0.f));  // sin(slope/2)
           hd3 = s2 * s2 * s2;
@@ -272,9 +284,9 @@ struct AtlPvOp {
   bool fast;
 };
 
-template <bool FAST>
-static PvPhys<FAST> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t0) {
-  PvPhys<FAST> p;
+template <bool FAST, bool VEC>
+static PvPhys<FAST, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t0) {
+  PvPhys<FAST, VEC> p;
   p.toa = f->influx_toa;
   p.dir = f->influx_direct;
   p.dif = f->influx_diffuse;
@@ -290,6 +302,7 @@ static PvPhys<FAST> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t
   p.yt = op->d_yt;
   p.S = op->grid.S;
   p.nx = op->grid.nx;
+  p.ny = op->grid.ny;
   p.t_off = (int)t0;
   p.tracking_ = op->tracking;
   p.trigon = op->trigon;
@@ -302,6 +315,15 @@ static PvPhys<FAST> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t
   p.alt_thr = op->alt_thr;
   for (int i = 0; i < 12; ++i) p.pc[i] = op->pc[i];
   return p;
+}
+
+static bool fields_aligned(const AtlPvFields* f) {
+  const void* ps[] = {f->influx_toa, f->influx_direct, f->influx_diffuse, f->influx, f->albedo,
+                      f->outflux,    f->temperature,   f->humidity,       f->solar_altitude,
+                      f->solar_azimuth};
+  for (const void* q : ps)
+    if (!aligned16(q)) return false;
+  return true;
 }
 
 static int check(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt) {
@@ -484,9 +506,13 @@ int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f, 
   ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
               "plan / operator grid mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
-  if (op->fast)
-    return launch_reduce(make_phys<true>(op, f, t0), plan, out_dev, nt, (cudaStream_t)stream);
-  return launch_reduce(make_phys<false>(op, f, t0), plan, out_dev, nt, (cudaStream_t)stream);
+  const bool al = fields_aligned(f);
+  if (op->fast) {
+    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
+    return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);
+  }
+  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
+  return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);
 }
 
 int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
@@ -495,11 +521,13 @@ int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  if (op->fast)
-    return launch_cells(make_phys<true>(op, f, t0), op->grid, out_dev, 0, nt, false,
-                        (cudaStream_t)stream);
-  return launch_cells(make_phys<false>(op, f, t0), op->grid, out_dev, 0, nt, false,
-                      (cudaStream_t)stream);
+  const bool al = fields_aligned(f);
+  if (op->fast) {
+    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
+    return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);
+  }
+  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
+  return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);
 }
 
 int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
@@ -508,11 +536,13 @@ int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t 
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  if (op->fast)
-    return launch_cells(make_phys<true>(op, f, t0), op->grid, out_dev, 0, nt, true,
-                        (cudaStream_t)stream);
-  return launch_cells(make_phys<false>(op, f, t0), op->grid, out_dev, 0, nt, true,
-                      (cudaStream_t)stream);
+  const bool al = fields_aligned(f);
+  if (op->fast) {
+    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
+    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);
+  }
+  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
+  return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

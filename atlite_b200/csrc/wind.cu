@@ -19,12 +19,14 @@ namespace atl {
 //   slope (f[j+1]-f[j]) / (V[j+1]-V[j])  (0 on zero-width segments)
 // padded with +inf (NK > n_knots) so a branch-free binary search counts the
 // knots <= x.
+template <bool VEC>
 struct WindPhys {
+  static constexpr bool kVec = VEC;
+  using Geom = TileGeomT<VEC>;
   const float* wnd;
   const float* aux;
   const float* curve;  // device, 4 * NK floats
   int64_t S;
-  int nx;
   int method;
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
@@ -39,10 +41,10 @@ struct WindPhys {
     for (int i = threadIdx.x; i < 4 * NK; i += blockDim.x) smem[i] = curve[i];
     __syncthreads();
   }
-  __device__ void init(Cell&, const TileGeom&, const float*) const {}
-  __device__ void load(const Cell&, const TileGeom& g, int t, Raw& r) const {
-    load4(wnd, S, nx, g, t, r.w);
-    if (method != ATL_WIND_NONE) load4(aux, S, nx, g, t, r.a);
+  __device__ void init(Cell&, const Geom&, const float*) const {}
+  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const {
+    load4(wnd, S, g, t, r.w);
+    if (method != ATL_WIND_NONE) load4(aux, S, g, t, r.a);
   }
   __device__ __forceinline__ float interp(float x, const float* sm) const {
     const float* xcmp = sm;
@@ -59,7 +61,7 @@ struct WindPhys {
     r = (cnt >= n_knots) ? f[n_knots - 1] : r;
     return (x != x) ? x : r;
   }
-  __device__ void compute(const Cell&, const TileGeom& g, int, const Raw& r, float (&v)[4],
+  __device__ void compute(const Cell&, const Geom& g, int, const Raw& r, float (&v)[4],
                           const float* sm) const {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -90,13 +92,13 @@ struct AtlWindOp {
   float* d_curve = nullptr;
 };
 
-static WindPhys make_phys(const AtlWindOp* op, const AtlWindFields* f) {
-  WindPhys p;
+template <bool VEC>
+static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
+  WindPhys<VEC> p;
   p.wnd = f->wnd;
   p.aux = f->aux;
   p.curve = op->d_curve;
   p.S = op->grid.S;
-  p.nx = op->grid.nx;
   p.method = op->method;
   p.n_knots = op->n_knots;
   p.NK = op->NK;
@@ -197,7 +199,9 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
   ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
               "plan / operator grid mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
-  return launch_reduce(make_phys(op, f), plan, out_dev, nt, (cudaStream_t)stream);
+  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
+  return dispatch_reduce(make, plan, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt,
+                         (cudaStream_t)stream);
 }
 
 int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, float* out_dev,
@@ -206,7 +210,9 @@ int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, floa
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  return launch_cells(make_phys(op, f), op->grid, out_dev, 0, nt, false, (cudaStream_t)stream);
+  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
+  return dispatch_cells(make, op->grid, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt, false,
+                        (cudaStream_t)stream);
 }
 
 int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, float* out_dev,
@@ -215,7 +221,9 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, fl
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  return launch_cells(make_phys(op, f), op->grid, out_dev, 0, nt, true, (cudaStream_t)stream);
+  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
+  return dispatch_cells(make, op->grid, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt, true,
+                        (cudaStream_t)stream);
 }
 
 }  // extern "C"

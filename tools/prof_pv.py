@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Kernel-only timing / ncu target for the fused kernels on device-resident data.
+
+    ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat] [small|big] [reps]
+
+small = 200x200x8760 -> 100 shapes (bench workload); big = 1440x720x438 -> 3000 shapes.
+Prints one JSON line with the median CUDA-event time and achieved GB/s.
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import atlite_b200 as ab  # noqa: E402
+from atlite_b200 import engine, synthetic as syn  # noqa: E402
+from atlite_b200.convert import _HeatSpec, _PvSpec, _WindSpec  # noqa: E402
+
+warnings.simplefilter("ignore")
+kind = sys.argv[1] if len(sys.argv) > 1 else "pv"
+size = sys.argv[2] if len(sys.argv) > 2 else "small"
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
+dev = torch.device("cuda", 0)
+if size == "small":
+    nx, ny, nt, nbus, x0, y0 = 200, 200, 8760, 100, 0.0, 30.0
+else:
+    nx, ny, nt, nbus, x0, y0 = 1440, 720, 432, 3000, -180.0, -90.0
+x, y = syn.make_coords(nx, ny, x0, y0)
+tm = syn.make_time(nt + 24 * 170)[24 * 170:] if size == "big" else syn.make_time(nt)
+plan = engine.get_plan(syn.make_shapes(nx, ny, nbus), ny, nx)
+f = syn.make_pv_fields_device(tm, x, y, dev, seed=7)
+coords = dict(time=tm, x=x, y=y, lon=x, lat=y)
+if kind == "pv":
+    spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
+    fn, bpc = (lambda: spec.op.reduce(plan, spec.fields)), 20
+elif kind == "wind":
+    ds = ab.Dataset({"wnd100m": (f["temperature"] - 255.0) * 0.5, "roughness": f["albedo"] * 0.5 + 1e-3}, coords=coords)
+    ws = _WindSpec(ds, ab.get_windturbineconfig("Vestas_V112_3MW"))
+    fn, bpc = (lambda: ws.op.reduce(plan, ws.wnd, ws.aux)), 8
+else:
+    hs = _HeatSpec(ab.Dataset({"temperature": f["temperature"]}, coords=coords), 15.0, 1.0, 0.0, 0.0)
+    fn, bpc = (lambda: hs.op.reduce(plan, hs.temp, hs.day_start)), 4
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+for a, b in ev:
+    a.record()
+    fn()
+    b.record()
+torch.cuda.synchronize()
+ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+cts = float(nx) * ny * nt
+print(json.dumps({"kind": kind, "size": size, "variant": os.environ.get("ATL_VARIANT", "0"),
+                  "tb": os.environ.get("ATL_TB", "auto"), "ms": round(ms, 4),
+                  "cell_ts_per_s": cts / ms * 1e3, "GBs": round(cts * bpc / ms / 1e6, 1),
+                  "frac_6573": round(cts * bpc / ms / 1e6 / 6573.5, 4), "plan": plan.info["slots_per_active_tile"]}))
