@@ -20,23 +20,34 @@ struct HeatParams {
 
 constexpr int HEAT_UNROLL = 6;
 
-// daily mean + degree-day formula for the lane's 4 cells of day d
+// One chunk of up to HEAT_UNROLL consecutive time steps for the lane's 4 cells.
+template <bool VEC>
+__device__ __forceinline__ void heat_load_chunk(const HeatParams& hp, const TileGeomT<VEC>& g, int s,
+                                                int s1, float (&x)[HEAT_UNROLL][4]) {
+#pragma unroll
+  for (int u = 0; u < HEAT_UNROLL; ++u) {
+    if (s + u < s1) {
+      load4(hp.temp, hp.S, g, s + u, x[u]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) x[u][r] = __int_as_float(0x7fc00000);  // NaN: skipped
+    }
+  }
+}
+
+// daily mean + degree-day formula for the lane's 4 cells of day d.  The loads of
+// chunk k+1 are issued before chunk k is accumulated (register double buffer).
 template <bool VEC>
 __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<VEC>& g, int d,
                                          float (&v)[4]) {
   const int s0 = __ldg(hp.day_start + d) - hp.base, s1 = __ldg(hp.day_start + d + 1) - hp.base;
   float sum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
+  float x[HEAT_UNROLL][4], y[HEAT_UNROLL][4];
+  heat_load_chunk(hp, g, s0, s1, x);
+#pragma unroll 1
   for (int s = s0; s < s1; s += HEAT_UNROLL) {
-    float x[HEAT_UNROLL][4];
-#pragma unroll
-    for (int u = 0; u < HEAT_UNROLL; ++u) {
-      if (s + u < s1) {
-        load4(hp.temp, hp.S, g, s + u, x[u]);
-      } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) x[u][r] = __int_as_float(0x7fc00000);  // NaN: skipped
-      }
-    }
+    const bool more = s + HEAT_UNROLL < s1;
+    if (more) heat_load_chunk(hp, g, s + HEAT_UNROLL, s1, y);
 #pragma unroll
     for (int u = 0; u < HEAT_UNROLL; ++u)
 #pragma unroll
@@ -45,6 +56,12 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<V
         sum[r] += ok ? x[u][r] : 0.f;
         cnt[r] += ok ? 1.f : 0.f;
       }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < HEAT_UNROLL; ++u)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[u][r] = y[u][r];
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {

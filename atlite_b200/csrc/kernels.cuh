@@ -6,6 +6,7 @@
 //   struct Cell;   per-thread constants (geometry of the lane's 4 cells)
 //   struct Raw;    the raw field values of one time step (4 cells)
 //   static constexpr int kSmemFloats;        CTA-shared lookup tables
+//   static constexpr int kBatch, kMinBlocks; time steps per batch / CTAs per SM
 //   __device__ void stage(float* smem) const;            (whole CTA, before use)
 //   __device__ void init(Cell&, const Geom&, const float* smem) const;
 //   __device__ void load(const Cell&, const Geom&, int t, Raw&) const;
@@ -25,7 +26,16 @@
 
 namespace atl {
 
-template <class Phys, int PREFETCH, int MINB>
+// A warp owns one 32x4 tile and walks `tb` consecutive time steps in batches of
+// B.  Per batch: the arithmetic of the B resident steps runs first, then the
+// loads of the NEXT batch are issued into the now-dead raw registers, and only
+// then the shuffle-reduce + atomics of the current batch execute -- so B steps of
+// loads are in flight across the whole reduce phase at no extra register cost.
+// Steps are reduced pairwise with one butterfly (reduce_slots2).  B is chosen per
+// physics so that B x (#fields) 16-byte loads per lane cover the HBM latency
+// (PV: 2 x 5, wind: 4 x 2, SpMM: 4 x 1).  MINB = CTAs/SM the register allocator
+// must allow.
+template <class Phys, int B, int MINB>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
     k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
                    float* __restrict__ out, int nt, int tb) {
@@ -40,32 +50,30 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
   const int t0 = blockIdx.y * tb;
   const int t1 = min(nt, t0 + tb);
+  const int nb = plan.n_bus;
 
   typename Phys::Cell c;
   phys.init(c, g, smem);
-  float v[4];
-  if (PREFETCH) {
-    typename Phys::Raw ra, rb;
-    phys.load(c, g, t0, ra);
+  typename Phys::Raw r[B];
+  float v[B][4];
+#pragma unroll
+  for (int j = 0; j < B; ++j)
+    if (t0 + j < t1) phys.load(c, g, t0 + j, r[j]);
 #pragma unroll 1
-    for (int t = t0; t < t1; t += 2) {
-      const bool has_b = t + 1 < t1;
-      if (has_b) phys.load(c, g, t + 1, rb);
-      phys.compute(c, g, t, ra, v, smem);
-      reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
-      if (has_b) {
-        if (t + 2 < t1) phys.load(c, g, t + 2, ra);
-        phys.compute(c, g, t + 1, rb, v, smem);
-        reduce_slots(v, s_beg, s_end, plan, out + (size_t)(t + 1) * plan.n_bus, lane);
-      }
-    }
-  } else {
-    typename Phys::Raw ra;
-#pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
-      phys.load(c, g, t, ra);
-      phys.compute(c, g, t, ra, v, smem);
-      reduce_slots(v, s_beg, s_end, plan, out + (size_t)t * plan.n_bus, lane);
+  for (int t = t0; t < t1; t += B) {
+#pragma unroll
+    for (int j = 0; j < B; ++j)
+      if (t + j < t1) phys.compute(c, g, t + j, r[j], v[j], smem);
+#pragma unroll
+    for (int j = 0; j < B; ++j)
+      if (t + B + j < t1) phys.load(c, g, t + B + j, r[j]);
+#pragma unroll
+    for (int j = 0; j < B; j += 2) {
+      if (j + 1 < B && t + j + 1 < t1)
+        reduce_slots2(v[j], v[j + 1 < B ? j + 1 : j], s_beg, s_end, plan,
+                      out + (size_t)(t + j) * nb, lane);
+      else if (t + j < t1)
+        reduce_slots(v[j], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
     }
   }
 }
@@ -166,20 +174,16 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
   const size_t smem = Phys::kSmemFloats * sizeof(float);
   const GridDev gd = plan->grid;
   const PlanDev pd = plan->dev();
-  switch (tuning().variant) {
-    case 1:
-      k_fused_reduce<Phys, 1, 4><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
-      break;
-    case 2:
-      k_fused_reduce<Phys, 0, 8><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
-      break;
-    case 3:
-      k_fused_reduce<Phys, 1, 6><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
-      break;
-    default:
-      k_fused_reduce<Phys, 0, 6><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb);
-      break;
+#define ATL_LAUNCH_FUSED(B, MINB) \
+  k_fused_reduce<Phys, B, MINB><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb)
+  switch (tuning().variant) {  // experiments; 0 = the functor's own choice
+    case 1: ATL_LAUNCH_FUSED(1, 8); break;
+    case 2: ATL_LAUNCH_FUSED(2, 6); break;
+    case 3: ATL_LAUNCH_FUSED(4, 6); break;
+    case 4: ATL_LAUNCH_FUSED(4, 8); break;
+    default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks); break;
   }
+#undef ATL_LAUNCH_FUSED
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   return ATL_OK;

@@ -79,6 +79,7 @@ struct IdentityPhys {
     float v[4];
   };
   static constexpr int kSmemFloats = 0;
+  static constexpr int kBatch = 4, kMinBlocks = 8;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
   __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const { load4(f, S, g, t, r.v); }

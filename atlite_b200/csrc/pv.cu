@@ -72,6 +72,7 @@ struct PvPhys {
     float toa[4], a[4], b[4], alb[4], temp[4], hum[4], salt[4], saz[4];
   };
   static constexpr int kSmemFloats = 0;
+  static constexpr int kBatch = FAST ? 2 : 1, kMinBlocks = FAST ? 5 : 4;
   __device__ void stage(float*) const {}
 
   __device__ void init(Cell& c, const Geom& g, const float*) const {

@@ -11,14 +11,15 @@
 
 namespace atl {
 
-// Power curve in shared memory: 4 arrays of NK (power of two >= n_knots):
-//   xcmp  knot abscissae rounded UP to float  -> `x >= xcmp[j]` is exactly the
-//         float64 comparison `x >= V[j]` of numpy's binary search for float x
-//   xval  knot abscissae rounded to nearest   (for x - V[j])
-//   f     POW[j] / P
-//   slope (f[j+1]-f[j]) / (V[j+1]-V[j])  (0 on zero-width segments)
-// padded with +inf (NK > n_knots) so a branch-free binary search counts the
-// knots <= x.
+// Power curve in shared memory (NK = power of two > n_knots):
+//   xcmp[NK]   knot abscissae rounded UP to float -> `xcmp[j] <= x` is exactly the
+//              float64 comparison `V[j] <= x` of numpy's binary search for a float
+//              x; padded with +inf so a branch-free binary search counts the
+//              knots <= x
+//   seg[NK+1]  float4 {x0, f0, slope, -} indexed by that COUNT c: c = 0 -> left
+//              clamp f[0]; 1 <= c < n -> segment [V[c-1], V[c]) with x0 = V[c-1]
+//              (nearest float), slope = 0 on zero-width (duplicate-knot)
+//              segments; c >= n -> right clamp f[n-1]      (np.interp semantics)
 template <bool VEC>
 struct WindPhys {
   static constexpr bool kVec = VEC;
@@ -30,15 +31,17 @@ struct WindPhys {
   int method;
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
+  float x_lo, x_hi;
 
   struct Cell {};
   struct Raw {
     float w[4], a[4];
   };
-  static constexpr int kSmemFloats = 4 * 256;
+  static constexpr int kSmemFloats = 256 + 4 * 257 + 3;
+  static constexpr int kBatch = 4, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
-    for (int i = threadIdx.x; i < 4 * NK; i += blockDim.x) smem[i] = curve[i];
+    for (int i = threadIdx.x; i < NK + 4 * (NK + 1); i += blockDim.x) smem[i] = curve[i];
     __syncthreads();
   }
   __device__ void init(Cell&, const Geom&, const float*) const {}
@@ -46,36 +49,45 @@ struct WindPhys {
     load4(wnd, S, g, t, r.w);
     if (method != ATL_WIND_NONE) load4(aux, S, g, t, r.a);
   }
-  __device__ __forceinline__ float interp(float x, const float* sm) const {
+  // np.interp for the lane's 4 values at once: the four binary searches advance
+  // in lock step (4 independent shared-memory loads in flight per step).
+  __device__ __forceinline__ void interp4(const float (&x)[4], float (&r)[4], const float* sm) const {
     const float* xcmp = sm;
-    const float* xval = sm + NK;
-    const float* f = sm + 2 * NK;
-    const float* slope = sm + 3 * NK;
-    int cnt = 0;  // number of knots <= x
-    for (int step = NK >> 1; step >= 1; step >>= 1)
-      if (xcmp[cnt + step - 1] <= x) cnt += step;
-    // np.interp: x < V[0] -> f[0]; x >= V[n-1] -> f[n-1]; else linear on [j, j+1)
-    const int j = max(cnt - 1, 0);
-    float r = fmaf(slope[j], x - xval[j], f[j]);
-    r = (cnt == 0) ? f[0] : r;
-    r = (cnt >= n_knots) ? f[n_knots - 1] : r;
-    return (x != x) ? x : r;
+    const float4* seg = reinterpret_cast<const float4*>(sm + NK);
+    int cnt[4] = {0, 0, 0, 0};  // number of knots <= x  (NaN compares false -> 0)
+#pragma unroll 1
+    for (int step = NK >> 1; step >= 1; step >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (xcmp[cnt[i] + step - 1] <= x[i]) cnt[i] += step;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 s = seg[min(cnt[i], n_knots)];
+      // clamp keeps inf * 0 out of the clamped ends; NaN is restored below
+      const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
+      const float y = fmaf(s.z, xc - s.x, s.y);
+      r[i] = (x[i] != x[i]) ? x[i] : y;
+    }
   }
   __device__ void compute(const Cell&, const Geom& g, int, const Raw& r, float (&v)[4],
                           const float* sm) const {
+    float x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float x = r.w[i];
+      x[i] = r.w[i];
       if (method == ATL_WIND_LOG) {
         // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
         const float L = __log2f(r.a[i]);
-        x = x * __fdividef(lg2_to - L, lg2_from - L);
+        x[i] = x[i] * __fdividef(lg2_to - L, lg2_from - L);
       } else if (method == ATL_WIND_POWER) {
-        x = x * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
+        x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
-      const float p = interp(x, sm);
-      v[i] = ((g.valid >> i) & 1u) ? p : 0.f;
     }
+    float p[4];
+    interp4(x, p, sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ((g.valid >> i) & 1u) ? p[i] : 0.f;
   }
 };
 
@@ -89,6 +101,7 @@ struct AtlWindOp {
   int method;
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
+  float x_lo, x_hi;
   float* d_curve = nullptr;
 };
 
@@ -105,6 +118,8 @@ static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
   p.lg2_to = op->lg2_to;
   p.lg2_from = op->lg2_from;
   p.lg2_ratio = op->lg2_ratio;
+  p.x_lo = op->x_lo;
+  p.x_hi = op->x_hi;
   return p;
 }
 
@@ -131,7 +146,10 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
 
   int NK = 2;  // strictly more slots than knots: the search counts up to NK-1
   while (NK <= cfg->n_knots) NK <<= 1;
-  std::vector<float> curve((size_t)4 * NK);
+  // xcmp[NK] followed by seg[NK + 1] (float4), see WindPhys; NK * 4 bytes keeps
+  // the float4 part 16-byte aligned (NK >= 4)
+  if (NK < 4) NK = 4;
+  std::vector<float> curve((size_t)NK + 4 * ((size_t)NK + 1), 0.f);
   const int n = cfg->n_knots;
   for (int j = 0; j < NK; ++j) {
     if (j < n) {
@@ -139,18 +157,30 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
       float xc = (float)x;
       if ((double)xc < x) xc = nextafterf(xc, INFINITY);  // round up
       curve[j] = xc;
-      curve[NK + j] = (float)x;
-      curve[2 * NK + j] = (float)cfg->POW_norm[j];
-      double sl = 0.0;
-      if (j + 1 < n && cfg->V[j + 1] > cfg->V[j])
-        sl = (cfg->POW_norm[j + 1] - cfg->POW_norm[j]) / (cfg->V[j + 1] - cfg->V[j]);
-      curve[3 * NK + j] = (float)sl;
     } else {
       curve[j] = INFINITY;
-      curve[NK + j] = 0.f;
-      curve[2 * NK + j] = 0.f;
-      curve[3 * NK + j] = 0.f;
     }
+  }
+  float* seg = curve.data() + NK;
+  for (int c = 0; c <= NK; ++c) {
+    float x0 = 0.f, f0 = 0.f, sl = 0.f;
+    if (c == 0) {
+      x0 = (float)cfg->V[0];
+      f0 = (float)cfg->POW_norm[0];
+    } else if (c >= n) {
+      x0 = (float)cfg->V[n - 1];
+      f0 = (float)cfg->POW_norm[n - 1];
+    } else {
+      const int j = c - 1;
+      x0 = (float)cfg->V[j];
+      f0 = (float)cfg->POW_norm[j];
+      if (cfg->V[j + 1] > cfg->V[j])
+        sl = (float)((cfg->POW_norm[j + 1] - cfg->POW_norm[j]) / (cfg->V[j + 1] - cfg->V[j]));
+    }
+    seg[4 * c + 0] = x0;
+    seg[4 * c + 1] = f0;
+    seg[4 * c + 2] = sl;
+    seg[4 * c + 3] = 0.f;
   }
   AtlWindOp* op = new AtlWindOp();
   op->device = device;
@@ -159,6 +189,8 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
   op->n_knots = n;
   op->NK = NK;
   op->lg2_to = op->lg2_from = op->lg2_ratio = 0.f;
+  op->x_lo = (float)cfg->V[0];
+  op->x_hi = (float)cfg->V[n - 1];
   if (cfg->method != ATL_WIND_NONE) {
     op->lg2_to = (float)std::log2(cfg->to_height);
     op->lg2_from = (float)std::log2(cfg->from_height);

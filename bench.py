@@ -53,30 +53,33 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every
+    ~2 ms; nvidia-smi -lms 200 is too coarse for millisecond steps)."""
 
     def __init__(self, index=0):
         self.index, self.rows, self._stop = index, [], threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), int(rs)))
+                self._stop.wait(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
 
     def __enter__(self):
         self._t.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
@@ -84,20 +87,12 @@ class ClockSampler:
         self._t.join(timeout=10)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:  # noqa: BLE001
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                "sw_thermal_slowdown": 0x20}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for _, rs in self.rows for n, b in bits.items() if rs & b})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sm), **({"error": self.error} if hasattr(self, "error") else {})}
 
 
 # ----------------------------------------------------------------------------

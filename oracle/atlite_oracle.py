@@ -9,12 +9,15 @@ reference`` leg may import it, and only as the checker / CPU baseline.  The
 product path (``atlite_b200``) never imports it and fails loudly if the CUDA
 library is missing.
 
-Pinning status: the reference's own tests hold NO numeric golden vectors for
-this path and ``import atlite`` is impossible in the build
-container (xarray/dask/geopandas absent).  The oracle is therefore pinned
-against *the reference's own source modules executed here* under a minimal
-xarray/dask stand-in (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``,
-checked by ``tests/test_oracle_vs_reference.py``); see DESIGN.md "Oracle".
+Pinning status: PINNED against the reference's own source executed in the build
+container.  The reference's tests hold no numeric golden vectors for this path
+ and ``import atlite`` is impossible here (xarray / dask /
+geopandas are not installed, no network), so ``tests/golden/make_golden.py``
+loads the reference's hot-path modules from their files under a minimal
+xarray/dask container stand-in (``tests/golden/xr_shim.py``), runs 32 cases and
+stores inputs + outputs in ``tests/golden/reference_outputs.npz``;
+``tests/test_oracle_vs_reference.py`` holds this oracle to them at 1e-9
+relative.  Not pinned against genuine xarray/dask objects.
 
 Conventions (same as the reference):
   * ``ds`` is a mapping name -> ndarray.  Fields are ``(time, y, x)``
