@@ -83,7 +83,7 @@ template <>
 struct TileGeomT<false> {
   int x, y0;
   unsigned valid;
-  int off[4];
+  int64_t boff[4];  // BYTE offset (float fields) of the lane's 4 cells inside a time slab
   __host__ __device__ int cell_x(int) const { return x; }
   __host__ __device__ int cell_y(int i) const { return y0 + i; }
 };
@@ -91,7 +91,7 @@ template <>
 struct TileGeomT<true> {
   int x0, y;
   unsigned valid;
-  int off;  // flat offset of the first of the 4 cells (multiple of 4)
+  int64_t boff;  // BYTE offset (float fields) of the first of the 4 cells (16-byte multiple)
   __host__ __device__ int cell_x(int i) const { return x0 + i; }
   __host__ __device__ int cell_y(int) const { return y; }
 };
@@ -121,7 +121,8 @@ __device__ __forceinline__ TileGeomT<false> make_geom<false>(int tile, int lane,
   g.valid = v;
   const int xc = min(g.x, gd.nx - 1);
 #pragma unroll
-  for (int r = 0; r < TILE_Y; ++r) g.off[r] = min(g.y0 + r, gd.ny - 1) * gd.nx + xc;
+  for (int r = 0; r < TILE_Y; ++r)
+    g.boff[r] = 4 * (int64_t)(min(g.y0 + r, gd.ny - 1) * gd.nx + xc);
   return g;
 }
 template <>
@@ -131,7 +132,7 @@ __device__ __forceinline__ TileGeomT<true> make_geom<true>(int tile, int lane, c
   g.x0 = tx * TILE_X + 4 * (lane & 7);
   g.y = ty * TILE_Y + (lane >> 3);
   g.valid = (g.x0 < gd.nx && g.y < gd.ny) ? 0xFu : 0u;  // nx % 4 == 0: all 4 or none
-  g.off = min(g.y, gd.ny - 1) * gd.nx + min(g.x0, gd.nx - 4);
+  g.boff = 4 * (int64_t)(min(g.y, gd.ny - 1) * gd.nx + min(g.x0, gd.nx - 4));
   return g;
 }
 
@@ -162,28 +163,34 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   return v;
 }
 
-// Load the lane's 4 cells of one field at time step t (slab-relative): one
-// warp-uniform slab pointer + 32-bit per-lane offsets.
-__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t S,
-                                      const TileGeomT<false>& g, int t, float (&o)[4]) {
-  const float* p = f + (int64_t)t * S;
-#pragma unroll
-  for (int r = 0; r < TILE_Y; ++r) o[r] = ld_stream(p + g.off[r]);
+// Load the lane's 4 cells of one field.  `tb` = BYTE offset of the time slab
+// (t * S * 4 for float fields), kept as a running 64-bit value by the caller so a
+// load costs one 64-bit add (uniform field base + per-lane offset) and no
+// multiply.  float64 fields (stored solar position) scale the offset by 2.
+__device__ __forceinline__ const float* at_bytes(const float* f, int64_t b) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(f) + b);
 }
-__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t S,
-                                      const TileGeomT<true>& g, int t, float (&o)[4]) {
-  const float4 v = ld_stream4(f + (int64_t)t * S + g.off);
+__device__ __forceinline__ const double* at_bytes(const double* f, int64_t b) {
+  return reinterpret_cast<const double*>(reinterpret_cast<const char*>(f) + 2 * b);
+}
+__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t tb,
+                                      const TileGeomT<false>& g, float (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < TILE_Y; ++r) o[r] = ld_stream(at_bytes(f, tb + g.boff[r]));
+}
+__device__ __forceinline__ void load4(const float* __restrict__ f, int64_t tb,
+                                      const TileGeomT<true>& g, float (&o)[4]) {
+  const float4 v = ld_stream4(at_bytes(f, tb + g.boff));
   o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
-__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t S,
-                                      const TileGeomT<false>& g, int t, float (&o)[4]) {
-  const double* p = f + (int64_t)t * S;
+__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t tb,
+                                      const TileGeomT<false>& g, float (&o)[4]) {
 #pragma unroll
-  for (int r = 0; r < TILE_Y; ++r) o[r] = (float)ld_stream(p + g.off[r]);
+  for (int r = 0; r < TILE_Y; ++r) o[r] = (float)ld_stream(at_bytes(f, tb + g.boff[r]));
 }
-__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t S,
-                                      const TileGeomT<true>& g, int t, float (&o)[4]) {
-  const double* p = f + (int64_t)t * S + g.off;
+__device__ __forceinline__ void load4(const double* __restrict__ f, int64_t tb,
+                                      const TileGeomT<true>& g, float (&o)[4]) {
+  const double* p = at_bytes(f, tb + g.boff);
 #pragma unroll
   for (int r = 0; r < 4; ++r) o[r] = (float)ld_stream(p + r);
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ void heat_load_chunk(const HeatParams& hp, const Tile
 #pragma unroll
   for (int u = 0; u < HEAT_UNROLL; ++u) {
     if (s + u < s1) {
-      load4(hp.temp, hp.S, g, s + u, x[u]);
+      load4(hp.temp, (int64_t)(s + u) * (hp.S * 4), g, x[u]);
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r) x[u][r] = __int_as_float(0x7fc00000);  // NaN: skipped
@@ -69,7 +69,7 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<V
     float h = hp.a * (hp.thr_k - mean);  // convert.py:413-414
     h = (h == h) ? fmaxf(h, 0.f) : h;    // .clip(min=0) keeps NaN  :416
     h = hp.constant + h;                 // :418
-    v[r] = ((g.valid >> r) & 1u) ? h : 0.f;
+    v[r] = h;
   }
 }
 

@@ -9,9 +9,12 @@
 //   static constexpr int kBatch, kMinBlocks; time steps per batch / CTAs per SM
 //   __device__ void stage(float* smem) const;            (whole CTA, before use)
 //   __device__ void init(Cell&, const Geom&, const float* smem) const;
-//   __device__ void load(const Cell&, const Geom&, int t, Raw&) const;
+//   __device__ void load(const Cell&, const Geom&, int64_t tb, Raw&) const;
+//        tb = byte offset of the time slab (t * S * 4), maintained by the caller
 //   __device__ void compute(const Cell&, const Geom&, int t, const Raw&,
 //                           float (&v)[4], const float* smem) const;
+//        values of out-of-grid lanes are unspecified (finite border copies): they
+//        carry zero weight in every slot and are never stored
 // `t` is relative to the slab the functor's field pointers address.
 //
 // Loop structure: a warp owns one 32x4 tile and walks a block of `tb`
@@ -56,25 +59,35 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   phys.init(c, g, smem);
   typename Phys::Raw r[B];
   float v[B][4];
+  const int64_t S4 = gd.S * 4;
+  int64_t sb = (int64_t)t0 * S4;  // byte offset of the next slab to LOAD
+  const int nfull = (t1 - t0) / B;
+  int t = t0;
+  if (nfull > 0) {
 #pragma unroll
-  for (int j = 0; j < B; ++j)
-    if (t0 + j < t1) phys.load(c, g, t0 + j, r[j]);
+    for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
+    sb += B * S4;
 #pragma unroll 1
-  for (int t = t0; t < t1; t += B) {
+    for (int k = 0; k < nfull; ++k, t += B) {
 #pragma unroll
-    for (int j = 0; j < B; ++j)
-      if (t + j < t1) phys.compute(c, g, t + j, r[j], v[j], smem);
+      for (int j = 0; j < B; ++j) phys.compute(c, g, t + j, r[j], v[j], smem);
+      if (k + 1 < nfull) {
 #pragma unroll
-    for (int j = 0; j < B; ++j)
-      if (t + B + j < t1) phys.load(c, g, t + B + j, r[j]);
+        for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
+        sb += B * S4;
+      }
 #pragma unroll
-    for (int j = 0; j < B; j += 2) {
-      if (j + 1 < B && t + j + 1 < t1)
-        reduce_slots2(v[j], v[j + 1 < B ? j + 1 : j], s_beg, s_end, plan,
-                      out + (size_t)(t + j) * nb, lane);
-      else if (t + j < t1)
-        reduce_slots(v[j], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+      for (int j = 0; j + 1 < B; j += 2)
+        reduce_slots2(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+      if (B & 1) reduce_slots(v[B - 1], s_beg, s_end, plan, out + (size_t)(t + B - 1) * nb, lane);
     }
+  }
+  // tail: fewer than B steps left
+#pragma unroll 1
+  for (; t < t1; ++t, sb += S4) {
+    phys.load(c, g, sb, r[0]);
+    phys.compute(c, g, t, r[0], v[0], smem);
+    reduce_slots(v[0], s_beg, s_end, plan, out + (size_t)t * nb, lane);
   }
 }
 
@@ -98,9 +111,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 4)
   typename Phys::Raw ra;
   float v[4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t S4 = gd.S * 4;
+  int64_t sb = (int64_t)t0 * S4;
 #pragma unroll 1
-  for (int t = t0; t < t1; ++t) {
-    phys.load(c, g, t, ra);
+  for (int t = t0; t < t1; ++t, sb += S4) {
+    phys.load(c, g, sb, ra);
     phys.compute(c, g, t, ra, v, smem);
     if (MODE == 0) {
       store4(out + (int64_t)(t - t_begin) * gd.S, gd, g, v);

@@ -82,11 +82,11 @@ struct IdentityPhys {
   static constexpr int kBatch = 4, kMinBlocks = 8;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
-  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const { load4(f, S, g, t, r.v); }
-  __device__ void compute(const Cell&, const Geom& g, int, const Raw& r, float (&v)[4],
+  __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const { load4(f, tb, g, r.v); }
+  __device__ void compute(const Cell&, const Geom&, int, const Raw& r, float (&v)[4],
                           const float*) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = ((g.valid >> i) & 1u) ? r.v[i] : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = r.v[i];
   }
 };
 

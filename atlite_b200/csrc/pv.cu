@@ -34,8 +34,9 @@ enum {  // panel coefficient slots (float, device)
 
 // FAST = the ERA5 default configuration compiled to constants: fixed panel
 // (tracking None), solar position computed in-kernel, influx_direct +
-// influx_diffuse + albedo variables.  FAST=false keeps every switch at run
-// time (stored solar position, Reindl split, outflux albedo, tracking modes).
+// influx_diffuse + albedo variables, simple trigon model, Huld panel.
+// FAST=false keeps every switch at run time (stored solar position, Reindl
+// split, outflux albedo, tracking modes, Hay-Davies, Bofinger).
 template <bool FAST, bool VEC>
 struct PvPhys {
   static constexpr bool kVec = VEC;
@@ -53,11 +54,13 @@ struct PvPhys {
   int64_t S;
   int nx, ny;
   int t_off;
-  int tracking_, trigon, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model;
+  int tracking_, trigon_, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model_;
   float sin_thr, alt_thr;
   float pc[12];
 
   __device__ __forceinline__ int tracking() const { return FAST ? ATL_TRACK_NONE : tracking_; }
+  __device__ __forceinline__ int trigon() const { return FAST ? ATL_TRIGON_SIMPLE : trigon_; }
+  __device__ __forceinline__ int panel_model() const { return FAST ? ATL_PANEL_HULD : panel_model_; }
   __device__ __forceinline__ int irr_branch() const {
     return FAST ? ATL_IRR_DIRECT_DIFFUSE : irr_branch_;
   }
@@ -94,29 +97,29 @@ struct PvPhys {
     }
   }
 
-  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const {
-    load4(toa, S, g, t, r.toa);
+  __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
+    load4(toa, tb, g, r.toa);
     if (irr_branch() == ATL_IRR_DIRECT_DIFFUSE) {
-      load4(dir, S, g, t, r.a);
-      load4(dif, S, g, t, r.b);
+      load4(dir, tb, g, r.a);
+      load4(dif, tb, g, r.b);
     } else {
-      load4(influx, S, g, t, r.a);
-      if (clearsky == ATL_CLEARSKY_ENHANCED) load4(hum, S, g, t, r.hum);
+      load4(influx, tb, g, r.a);
+      if (clearsky == ATL_CLEARSKY_ENHANCED) load4(hum, tb, g, r.hum);
     }
-    load4(albedo_src() == ATL_ALBEDO_VAR ? alb : outflux, S, g, t, r.alb);
-    load4(temp, S, g, t, r.temp);
+    load4(albedo_src() == ATL_ALBEDO_VAR ? alb : outflux, tb, g, r.alb);
+    load4(temp, tb, g, r.temp);
     if (solar_src() == ATL_SOLAR_STORED_F32) {
-      load4((const float*)salt, S, g, t, r.salt);
-      load4((const float*)saz, S, g, t, r.saz);
+      load4((const float*)salt, tb, g, r.salt);
+      load4((const float*)saz, tb, g, r.saz);
     } else if (solar_src() == ATL_SOLAR_STORED_F64) {
-      load4((const double*)salt, S, g, t, r.salt);
-      load4((const double*)saz, S, g, t, r.saz);
+      load4((const double*)salt, tb, g, r.salt);
+      load4((const double*)saz, tb, g, r.saz);
     }
   }
 
   // pv/solar_panel_model.py:12-44 (huld), 47-74 (bofinger)
   __device__ __forceinline__ float panel(float G, float T) const {
-    if (panel_model == ATL_PANEL_HULD) {
+    if (panel_model() == ATL_PANEL_HULD) {
       const float T_ = fmaf(pc[PC_C_AMB], T, fmaf(pc[PC_C_IRR], G, -pc[PC_R_TMOD]));
       const float G_ = G * pc[PC_INV_R_IRR];
       const float lg = __logf(G_);  // G_ <= 0 -> -inf/NaN -> eff NaN/-inf -> 0 below
@@ -135,7 +138,7 @@ struct PvPhys {
     }
   }
 
-  __device__ void compute(const Cell& c, const Geom& g, int t, const Raw& r, float (&v)[4],
+  __device__ void compute(const Cell& c, const Geom&, int t, const Raw& r, float (&v)[4],
                           const float*) const {
     float sd = 0.f, cd = 0.f, ch[NXC], sh[NXC];
     if (solar_src() == ATL_SOLAR_COMPUTED) {
@@ -154,7 +157,7 @@ struct PvPhys {
       // ---- solar position (pv/solar_position.py:103-114)
       float sinalt, cosalt, X, Y;
       if (solar_src() == ATL_SOLAR_COMPUTED) {
-        sinalt = fminf(fmaxf(fmaf(cd * c.cl[b], ch[a], sd * c.sl[b]), -1.f), 1.f);
+        sinalt = fmaf(cd * c.cl[b], ch[a], sd * c.sl[b]);  // no asin taken: the [-1,1] clip is moot
         X = fmaf(-(cd * c.sl[b]), ch[a], sd * c.cl[b]);
         Y = -cd * sh[a];
         cosalt = sqrtf(fmaxf(fmaf(-sinalt, sinalt, 1.f), 0.f));
@@ -177,7 +180,7 @@ struct PvPhys {
         cslope = c.cs[b];
       } else if (trk == ATL_TRACK_DUAL) {
         cosinc = 1.f;
-        cslope = (trigon == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[b];  // irradiation.py:216-219
+        cslope = (trigon() == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[b];  // irradiation.py:216-219
       } else {
         // q = cos a sin(az - phi), p = cos a cos(az - phi)
         const float q = fmaf(Y, c.cph[b], -X * c.sph[b]);
@@ -239,7 +242,7 @@ struct PvPhys {
       // ---- tilted irradiation (pv/irradiation.py:214-236, 76-125, 142-145)
       const float Rb = __fdividef(cosinc, sinalt);
       float total;
-      if (trigon == ATL_TRIGON_SIMPLE) {
+      if (trigon() == ATL_TRIGON_SIMPLE) {
         total = fmaf(Rb, direct,
                      fmaf(fmaf(0.5f, cslope, 0.5f), diffuse,
                           albedo * influx_ * fmaf(-0.5f, cslope, 0.5f)));
@@ -262,8 +265,7 @@ struct PvPhys {
                                                            : (r.salt[i] < alt_thr);
       const bool masked = low || (influx_ <= 0.01f);
       const float G = masked ? 0.f : total;
-      const float pw = panel(G, r.temp[i]);
-      v[i] = ((g.valid >> i) & 1u) ? pw : 0.f;
+      v[i] = panel(G, r.temp[i]);
     }
   }
 };
@@ -306,12 +308,12 @@ static PvPhys<FAST, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int6
   p.ny = op->grid.ny;
   p.t_off = (int)t0;
   p.tracking_ = op->tracking;
-  p.trigon = op->trigon;
+  p.trigon_ = op->trigon;
   p.clearsky = op->clearsky;
   p.irr_branch_ = op->irr_branch;
   p.albedo_src_ = op->albedo_src;
   p.solar_src_ = op->solar_src;
-  p.panel_model = op->panel_model;
+  p.panel_model_ = op->panel_model;
   p.sin_thr = op->sin_thr;
   p.alt_thr = op->alt_thr;
   for (int i = 0; i < 12; ++i) p.pc[i] = op->pc[i];
@@ -382,7 +384,8 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   op->sin_thr = (float)std::sin(cfg->altitude_threshold_deg * D2R);
   op->alt_thr = (float)(cfg->altitude_threshold_deg * D2R);
   op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
-             cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR;
+             cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR &&
+             cfg->trigon_model == ATL_TRIGON_SIMPLE && cfg->panel_model == ATL_PANEL_HULD;
   const double* P = cfg->panel;
   for (int i = 0; i < 12; ++i) op->pc[i] = 0.f;
   if (cfg->panel_model == ATL_PANEL_HULD) {

@@ -32,26 +32,48 @@ struct WindPhys {
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
+  int use_lut, n_stage;  // LUT mode: `curve` holds 2 float4 per bucket
+  float inv_w;
 
   struct Cell {};
   struct Raw {
     float w[4], a[4];
   };
-  static constexpr int kSmemFloats = 256 + 4 * 257 + 3;
-  static constexpr int kBatch = 4, kMinBlocks = 6;
+  static constexpr int kSmemFloats = 8 * 513 + 4;  // LUT: 2 float4 x (512 + 1) buckets
+  static constexpr int kBatch = 2, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
-    for (int i = threadIdx.x; i < NK + 4 * (NK + 1); i += blockDim.x) smem[i] = curve[i];
+    for (int i = threadIdx.x; i < n_stage; i += blockDim.x) smem[i] = curve[i];
     __syncthreads();
   }
   __device__ void init(Cell&, const Geom&, const float*) const {}
-  __device__ void load(const Cell&, const Geom& g, int t, Raw& r) const {
-    load4(wnd, S, g, t, r.w);
-    if (method != ATL_WIND_NONE) load4(aux, S, g, t, r.a);
+  __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
+    load4(wnd, tb, g, r.w);
+    if (method != ATL_WIND_NONE) load4(aux, tb, g, r.a);
   }
-  // np.interp for the lane's 4 values at once: the four binary searches advance
-  // in lock step (4 independent shared-memory loads in flight per step).
+  // np.interp for the lane's 4 values at once.
+  //  LUT mode (the normal case): a uniform grid over [V0, Vn-1], shifted by half a
+  //  bucket, in which every bucket holds at most one distinct knot value and no
+  //  knot lies within 1e-3 of a bucket edge (checked on the host).  A bucket stores
+  //  {thr, segment below thr} and {segment from thr on}; `x >= thr` with thr rounded
+  //  UP to float is exactly NumPy's float64 comparison, so one compare selects the
+  //  same segment as NumPy's binary search -- including duplicate knots (cut-out).
+  //  Fallback: branch-free binary search, the four searches in lock step.
   __device__ __forceinline__ void interp4(const float (&x)[4], float (&r)[4], const float* sm) const {
+    if (use_lut) {
+      const float4* lut = reinterpret_cast<const float4*>(sm);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
+        const int b = __float2int_rd(fmaf(xc - x_lo, inv_w, 0.5f));
+        const float4 A = lut[2 * b], Bv = lut[2 * b + 1];
+        const bool ge = x[i] >= A.x;
+        const float x0 = ge ? Bv.x : A.y, f0 = ge ? Bv.y : A.z, sl = ge ? Bv.z : A.w;
+        const float y = fmaf(sl, xc - x0, f0);
+        r[i] = (x[i] != x[i]) ? x[i] : y;
+      }
+      return;
+    }
     const float* xcmp = sm;
     const float4* seg = reinterpret_cast<const float4*>(sm + NK);
     int cnt[4] = {0, 0, 0, 0};  // number of knots <= x  (NaN compares false -> 0)
@@ -70,7 +92,7 @@ struct WindPhys {
       r[i] = (x[i] != x[i]) ? x[i] : y;
     }
   }
-  __device__ void compute(const Cell&, const Geom& g, int, const Raw& r, float (&v)[4],
+  __device__ void compute(const Cell&, const Geom&, int, const Raw& r, float (&v)[4],
                           const float* sm) const {
     float x[4];
 #pragma unroll
@@ -84,10 +106,7 @@ struct WindPhys {
         x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
     }
-    float p[4];
-    interp4(x, p, sm);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = ((g.valid >> i) & 1u) ? p[i] : 0.f;
+    interp4(x, v, sm);
   }
 };
 
@@ -102,6 +121,8 @@ struct AtlWindOp {
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
+  int use_lut, n_stage;
+  float inv_w;
   float* d_curve = nullptr;
 };
 
@@ -120,6 +141,9 @@ static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
   p.lg2_ratio = op->lg2_ratio;
   p.x_lo = op->x_lo;
   p.x_hi = op->x_hi;
+  p.use_lut = op->use_lut;
+  p.n_stage = op->n_stage;
+  p.inv_w = op->inv_w;
   return p;
 }
 
@@ -182,6 +206,52 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
     seg[4 * c + 2] = sl;
     seg[4 * c + 3] = 0.f;
   }
+  // ---- uniform-bucket LUT over the count-indexed segment table (see interp4)
+  int use_lut = 0;
+  float inv_w = 0.f;
+  {
+    auto ceil_f32 = [](double x) {
+      float c = (float)x;
+      if ((double)c < x) c = nextafterf(c, INFINITY);
+      return c;
+    };
+    const double lo = cfg->V[0], hi = cfg->V[n - 1];
+    for (int NB = 64; NB <= 512 && !use_lut && hi > lo; NB *= 2) {
+      const double wdt = (hi - lo) / NB;
+      std::vector<int> bucket_of(n);
+      std::vector<double> knot_in((size_t)NB + 1, std::nan(""));
+      bool ok = true;
+      for (int j = 0; j < n && ok; ++j) {
+        const double pos = (cfg->V[j] - lo) / wdt + 0.5;
+        const int b = (int)std::floor(pos);
+        const double frac = pos - b;
+        if (b < 0 || b > NB || frac < 1e-3 || frac > 1.0 - 1e-3) ok = false;
+        else if (!std::isnan(knot_in[b]) && knot_in[b] != cfg->V[j]) ok = false;  // 2 distinct knots
+        else {
+          knot_in[b] = cfg->V[j];
+          bucket_of[j] = b;
+        }
+      }
+      if (!ok) continue;
+      std::vector<float> lut((size_t)8 * (NB + 1), 0.f);
+      int c_lo = 0;  // knots in buckets < b
+      for (int b = 0; b <= NB; ++b) {
+        int c_hi = c_lo;
+        while (c_hi < n && bucket_of[c_hi] == b) ++c_hi;
+        const float* slo = seg + 4 * c_lo;
+        const float* shi = seg + 4 * c_hi;
+        float* e = &lut[(size_t)8 * b];
+        e[0] = std::isnan(knot_in[b]) ? INFINITY : ceil_f32(knot_in[b]);
+        e[1] = slo[0]; e[2] = slo[1]; e[3] = slo[2];
+        e[4] = shi[0]; e[5] = shi[1]; e[6] = shi[2]; e[7] = 0.f;
+        c_lo = c_hi;
+      }
+      curve.swap(lut);
+      use_lut = 1;
+      inv_w = (float)(1.0 / wdt);
+    }
+  }
+
   AtlWindOp* op = new AtlWindOp();
   op->device = device;
   op->grid = make_grid(cfg->ny, cfg->nx);
@@ -191,6 +261,9 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
   op->lg2_to = op->lg2_from = op->lg2_ratio = 0.f;
   op->x_lo = (float)cfg->V[0];
   op->x_hi = (float)cfg->V[n - 1];
+  op->use_lut = use_lut;
+  op->n_stage = (int)curve.size();
+  op->inv_w = inv_w;
   if (cfg->method != ATL_WIND_NONE) {
     op->lg2_to = (float)std::log2(cfg->to_height);
     op->lg2_from = (float)std::log2(cfg->from_height);

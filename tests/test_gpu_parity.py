@@ -103,6 +103,21 @@ def test_wind_interp_edges():
     assert_parity(got, want, cap_of(m), what="NaN routing")
 
 
+def test_wind_interp_binary_search_fallback():
+    """Knots too close for the uniform-bucket LUT -> branch-free binary search path."""
+    ds = syn.make_dataset(40, 8, 6, kinds=("wind",))
+    curve = dict(V=[0.0, 1.0, 1.0001, 3.0, 3.0, 7.5, 12.0, 25.0, 25.0],
+                 POW=[0.0, 0.0, 0.1, 0.4, 0.5, 1.5, 2.0, 2.0, 0.0], P=2.0, hub_height=100)
+    got = np.asarray(ab.Cutout(data=ds).to_device().wind(dict(curve), aggregate_time=None).values)
+    want = O.convert_wind(oracle_ds(ds), ab.get_windturbineconfig(dict(curve)))
+    assert_parity(got, want, what="binary search fallback")
+    m = syn.make_shapes(40, 8, 3)
+    got = bt(ab.Cutout(data=ds).wind(dict(curve, hub_height=80), matrix=m, aggregate_time=None))
+    want = O.convert_and_aggregate(oracle_ds(ds), O.convert_wind, matrix=m, aggregate_time=None,
+                                   turbine=ab.get_windturbineconfig(dict(curve, hub_height=80)))
+    assert_parity(got, want, cap_of(m), what="binary search fallback, reduce")
+
+
 # ------------------------------------------------------------------ pv
 
 
