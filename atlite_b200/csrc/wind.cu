@@ -5,6 +5,7 @@
 // Algorithmic traffic: 8 B per cell-timestep (wnd + roughness | shear
 // exponent), 4 B in the wnd{hub}m fast lane (wind.py:75-78).
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "kernels.cuh"
@@ -32,14 +33,14 @@ struct WindPhys {
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
-  int use_lut, n_stage;  // LUT mode: `curve` holds 2 float4 per bucket
+  int use_lut, n_stage;  // LUT mode: a byte table follows xcmp | seg in `curve`
   float inv_w;
 
   struct Cell {};
   struct Raw {
     float w[4], a[4];
   };
-  static constexpr int kSmemFloats = 8 * 513 + 4;  // LUT: 2 float4 x (512 + 1) buckets
+  static constexpr int kSmemFloats = 256 + 4 * 257 + 132;  // xcmp | seg | byte LUT (<= 513 B)
   static constexpr int kBatch = 2, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
@@ -51,31 +52,34 @@ struct WindPhys {
     load4(wnd, tb, g, r.w);
     if (method != ATL_WIND_NONE) load4(aux, tb, g, r.a);
   }
-  // np.interp for the lane's 4 values at once.
-  //  LUT mode (the normal case): a uniform grid over [V0, Vn-1], shifted by half a
-  //  bucket, in which every bucket holds at most one distinct knot value and no
-  //  knot lies within 1e-3 of a bucket edge (checked on the host).  A bucket stores
-  //  {thr, segment below thr} and {segment from thr on}; `x >= thr` with thr rounded
-  //  UP to float is exactly NumPy's float64 comparison, so one compare selects the
-  //  same segment as NumPy's binary search -- including duplicate knots (cut-out).
+  // np.interp for the lane's 4 values at once: find cnt = #knots <= x, then
+  // evaluate segment seg[cnt].  `xcmp[j] <= x` with xcmp rounded UP to float is
+  // exactly NumPy's float64 comparison, so the same segment is selected --
+  // including duplicate knots (cut-out) and the clamped ends.
+  //  LUT mode (the normal case): a byte table over a uniform grid on [V0, Vn-1]
+  //  (shifted by half a bucket) gives a start count that is never too high and
+  //  at most 2 short (host-checked: <= 2 knots can lie between a bucket's lower
+  //  edge and any x mapped to it); two compares against the knot array finish
+  //  the search.  All accesses are 1- or 4-byte and conflict-free for <= 32 knots.
   //  Fallback: branch-free binary search, the four searches in lock step.
   __device__ __forceinline__ void interp4(const float (&x)[4], float (&r)[4], const float* sm) const {
+    const float* xcmp = sm;
+    const float4* seg = reinterpret_cast<const float4*>(sm + NK);
     if (use_lut) {
-      const float4* lut = reinterpret_cast<const float4*>(sm);
+      const unsigned char* lo8 = reinterpret_cast<const unsigned char*>(sm + NK + 4 * (NK + 1));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
         const int b = __float2int_rd(fmaf(xc - x_lo, inv_w, 0.5f));
-        const float4 A = lut[2 * b], Bv = lut[2 * b + 1];
-        const bool ge = x[i] >= A.x;
-        const float x0 = ge ? Bv.x : A.y, f0 = ge ? Bv.y : A.z, sl = ge ? Bv.z : A.w;
-        const float y = fmaf(sl, xc - x0, f0);
+        int cnt = lo8[b];
+        cnt += (xcmp[cnt] <= x[i]) ? 1 : 0;
+        cnt += (xcmp[cnt] <= x[i]) ? 1 : 0;
+        const float4 s = seg[cnt];  // cnt <= n_knots: xcmp is +inf-padded
+        const float y = fmaf(s.z, xc - s.x, s.y);
         r[i] = (x[i] != x[i]) ? x[i] : y;
       }
       return;
     }
-    const float* xcmp = sm;
-    const float4* seg = reinterpret_cast<const float4*>(sm + NK);
     int cnt[4] = {0, 0, 0, 0};  // number of knots <= x  (NaN compares false -> 0)
 #pragma unroll 1
     for (int step = NK >> 1; step >= 1; step >>= 1) {
@@ -206,47 +210,30 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
     seg[4 * c + 2] = sl;
     seg[4 * c + 3] = 0.f;
   }
-  // ---- uniform-bucket LUT over the count-indexed segment table (see interp4)
+  // ---- uniform-bucket start-count LUT (see interp4)
   int use_lut = 0;
   float inv_w = 0.f;
   {
-    auto ceil_f32 = [](double x) {
-      float c = (float)x;
-      if ((double)c < x) c = nextafterf(c, INFINITY);
-      return c;
-    };
     const double lo = cfg->V[0], hi = cfg->V[n - 1];
-    for (int NB = 64; NB <= 512 && !use_lut && hi > lo; NB *= 2) {
-      const double wdt = (hi - lo) / NB;
-      std::vector<int> bucket_of(n);
-      std::vector<double> knot_in((size_t)NB + 1, std::nan(""));
+    for (int NB = 32; NB <= 512 && !use_lut && hi > lo && n <= 250; NB *= 2) {
+      const double wdt = (hi - lo) / NB, delta = 1e-3 * wdt;
+      std::vector<unsigned char> lut((size_t)NB + 1);
       bool ok = true;
-      for (int j = 0; j < n && ok; ++j) {
-        const double pos = (cfg->V[j] - lo) / wdt + 0.5;
-        const int b = (int)std::floor(pos);
-        const double frac = pos - b;
-        if (b < 0 || b > NB || frac < 1e-3 || frac > 1.0 - 1e-3) ok = false;
-        else if (!std::isnan(knot_in[b]) && knot_in[b] != cfg->V[j]) ok = false;  // 2 distinct knots
-        else {
-          knot_in[b] = cfg->V[j];
-          bucket_of[j] = b;
+      for (int b = 0; b <= NB && ok; ++b) {
+        const double e_lo = lo + (b - 0.5) * wdt - delta, e_hi = lo + (b + 0.5) * wdt + delta;
+        int start = 0, reach = 0;  // knots surely <= any x of the bucket / knots possibly <= it
+        for (int j = 0; j < n; ++j) {
+          if (cfg->V[j] < e_lo) ++start;
+          if (cfg->V[j] <= e_hi) ++reach;
         }
+        if (reach - start > 2) ok = false;
+        lut[(size_t)b] = (unsigned char)start;
       }
       if (!ok) continue;
-      std::vector<float> lut((size_t)8 * (NB + 1), 0.f);
-      int c_lo = 0;  // knots in buckets < b
-      for (int b = 0; b <= NB; ++b) {
-        int c_hi = c_lo;
-        while (c_hi < n && bucket_of[c_hi] == b) ++c_hi;
-        const float* slo = seg + 4 * c_lo;
-        const float* shi = seg + 4 * c_hi;
-        float* e = &lut[(size_t)8 * b];
-        e[0] = std::isnan(knot_in[b]) ? INFINITY : ceil_f32(knot_in[b]);
-        e[1] = slo[0]; e[2] = slo[1]; e[3] = slo[2];
-        e[4] = shi[0]; e[5] = shi[1]; e[6] = shi[2]; e[7] = 0.f;
-        c_lo = c_hi;
-      }
-      curve.swap(lut);
+      const size_t words = ((size_t)NB + 1 + 3) / 4;
+      const size_t base = curve.size();
+      curve.resize(base + words, 0.f);
+      std::memcpy(curve.data() + base, lut.data(), lut.size());
       use_lut = 1;
       inv_w = (float)(1.0 / wdt);
     }
