@@ -122,6 +122,7 @@ _SIGNATURES = {
     "atl_launch_count": (C.c_int64, []),
     "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "atl_plan_tiling_host": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(PlanInfo), _P, _P, _P, C.c_int64]),
     "atl_plan_destroy": (None, [_P]),
     "atl_spmm": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "atl_pv_create": (C.c_int, [C.c_int, C.POINTER(PvConfig), C.POINTER(_P)]),

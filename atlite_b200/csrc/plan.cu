@@ -107,13 +107,26 @@ int atl_device_count(int* count_out) {
   return ATL_OK;
 }
 
-int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
-                    const int64_t* indptr, const int32_t* indices, const double* data,
-                    AtlPlan** plan_out) {
-  ATL_REQUIRE(plan_out, "plan_out is NULL");
-  *plan_out = nullptr;
+}  // extern "C"
+
+namespace atl {
+
+// Host-side tiling of the CSR matrix (no CUDA involved; also exported through
+// atl_plan_tiling_host for CPU tests).
+struct Tiling {
+  GridDev gd;
+  bool vec = false, fused = false;
+  int64_t nnz = 0, n_slots = 0;
+  int32_t n_tiles = 0, n_active = 0;
+  std::vector<int32_t> tile_slot_ptr, slot_row, active;
+  std::vector<float> w;  // n_slots * 128 weights in lane order (only if fused)
+};
+
+static int build_tiling(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr,
+                        const int32_t* indices, const double* data, bool force_arrays,
+                        Tiling& T) {
   ATL_REQUIRE(ny > 0 && nx > 0 && n_bus >= 0, "bad plan shape");
-  ATL_REQUIRE((int64_t)ny * nx < (1LL << 31), "grid too large (ny*nx must fit int32)");
+  ATL_REQUIRE((int64_t)ny * nx < (1LL << 29), "grid too large (ny*nx must be < 2^29)");
   ATL_REQUIRE(indptr && (n_bus == 0 || indptr[n_bus] == 0 || (indices && data)),
               "CSR arrays missing");
   const GridDev gd = make_grid(ny, nx);
@@ -121,10 +134,9 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
   const int64_t nnz_in = n_bus ? indptr[n_bus] : 0;
   const int64_t n_tiles = (int64_t)gd.n_tx * gd.n_ty;
 
-  // (tile, bus) key of every stored entry
   struct Ent {
-    int64_t key;
-    int32_t local;  // lane * 4 + row-in-tile
+    int64_t key;    // tile * n_bus + bus
+    int32_t local;  // position inside the tile's 128-entry weight vector
     float w;
   };
   std::vector<Ent> ents;
@@ -145,44 +157,109 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
   }
   std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.key < b.key; });
 
-  std::vector<int32_t> tile_slot_ptr((size_t)n_tiles + 1, 0);
-  std::vector<int32_t> slot_row;
-  int64_t n_slots = 0;
+  int64_t n_slots = 0, n_active = 0;
   {
-    int64_t prev = -1;
-    for (const Ent& e : ents)
+    int64_t prev = -1, prev_tile = -1;
+    for (const Ent& e : ents) {
       if (e.key != prev) {
         prev = e.key;
         ++n_slots;
-      }
-  }
-  ATL_REQUIRE(n_slots < (1LL << 31) / 1, "too many (tile,bus) slots");
-  // A matrix "tiles well" when the padded slot work is within a small factor
-  // of nnz; otherwise (e.g. one bus per cell) use the two-pass CSR path.
-  int64_t n_active = 0;
-  {
-    int64_t prev_tile = -1;
-    for (const Ent& e : ents) {
-      const int64_t tile = e.key / std::max<int64_t>(n_bus, 1);
-      if (tile != prev_tile) {
-        prev_tile = tile;
-        ++n_active;
+        const int64_t tile = e.key / n_bus;
+        if (tile != prev_tile) {
+          prev_tile = tile;
+          ++n_active;
+        }
       }
     }
   }
+  ATL_REQUIRE(n_slots < (1LL << 31), "too many (tile,bus) slots");
+  // A matrix "tiles well" when a tile is touched by few buses; otherwise (e.g.
+  // one bus per cell) the padded slot work explodes: use the two-pass CSR path.
   const double spt = n_active ? (double)n_slots / (double)n_active : 0.0;
-  const bool fused = spt <= 24.0 && (double)n_slots * TILE_CELLS * 4.0 <= 4.0e9;
+  T.gd = gd;
+  T.vec = vec;
+  T.fused = spt <= 24.0 && (double)n_slots * TILE_CELLS * 4.0 <= 4.0e9;
+  T.nnz = nnz_in;
+  T.n_slots = n_slots;
+  T.n_tiles = (int32_t)n_tiles;
+  T.n_active = (int32_t)n_active;
+  if (!(T.fused || force_arrays)) return ATL_OK;
+
+  T.tile_slot_ptr.assign((size_t)n_tiles + 1, 0);
+  T.slot_row.resize((size_t)n_slots);
+  T.w.assign((size_t)n_slots * TILE_CELLS, 0.f);
+  T.active.clear();
+  T.active.reserve((size_t)n_active);
+  int64_t s = -1, prev = -1, prev_tile = -1;
+  for (const Ent& e : ents) {
+    if (e.key != prev) {
+      prev = e.key;
+      ++s;
+      const int64_t tile = e.key / n_bus;
+      T.slot_row[(size_t)s] = (int32_t)(e.key - tile * n_bus);
+      T.tile_slot_ptr[(size_t)tile + 1]++;
+      if (tile != prev_tile) {
+        prev_tile = tile;
+        T.active.push_back((int32_t)tile);
+      }
+    }
+    T.w[(size_t)s * TILE_CELLS + e.local] += e.w;  // duplicates sum (csr_matrix semantics)
+  }
+  for (int64_t t = 0; t < n_tiles; ++t) T.tile_slot_ptr[(size_t)t + 1] += T.tile_slot_ptr[(size_t)t];
+  return ATL_OK;
+}
+
+}  // namespace atl
+
+extern "C" {
+
+int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr,
+                         const int32_t* indices, const double* data, AtlPlanInfo* info,
+                         int32_t* tile_slot_ptr_out, int32_t* slot_row_out, float* slot_w_out,
+                         int64_t slot_capacity) {
+  ATL_REQUIRE(info, "info is NULL");
+  Tiling T;
+  const bool want = tile_slot_ptr_out || slot_row_out || slot_w_out;
+  int rc = build_tiling(ny, nx, n_bus, indptr, indices, data, want, T);
+  if (rc) return rc;
+  info->ny = ny;
+  info->nx = nx;
+  info->n_bus = n_bus;
+  info->nnz = T.nnz;
+  info->n_tiles = T.n_tiles;
+  info->n_active_tiles = T.n_active;
+  info->n_slots = T.n_slots;
+  info->slots_per_active_tile = T.n_active ? (double)T.n_slots / T.n_active : 0.0;
+  info->fused = T.fused ? 1 : 0;
+  if (!want) return ATL_OK;
+  ATL_REQUIRE(tile_slot_ptr_out && slot_row_out && slot_w_out, "all three output arrays are needed");
+  ATL_REQUIRE(slot_capacity >= T.n_slots, "slot_capacity too small");
+  std::memcpy(tile_slot_ptr_out, T.tile_slot_ptr.data(), T.tile_slot_ptr.size() * 4);
+  std::memcpy(slot_row_out, T.slot_row.data(), T.slot_row.size() * 4);
+  std::memcpy(slot_w_out, T.w.data(), T.w.size() * 4);
+  return ATL_OK;
+}
+
+int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
+                    const int64_t* indptr, const int32_t* indices, const double* data,
+                    AtlPlan** plan_out) {
+  ATL_REQUIRE(plan_out, "plan_out is NULL");
+  *plan_out = nullptr;
+  Tiling T;
+  int rc0 = build_tiling(ny, nx, n_bus, indptr, indices, data, false, T);
+  if (rc0) return rc0;
+  const int64_t nnz_in = T.nnz;
 
   AtlPlan* p = new AtlPlan();
   p->device = device;
-  p->grid = gd;
+  p->grid = T.gd;
   p->n_bus = n_bus;
   p->nnz = nnz_in;
-  p->n_tiles = (int32_t)n_tiles;
-  p->n_active = (int32_t)n_active;
-  p->n_slots = n_slots;
-  p->fused = fused;
-  p->vec = vec;
+  p->n_tiles = T.n_tiles;
+  p->n_active = T.n_active;
+  p->n_slots = T.n_slots;
+  p->fused = T.fused;
+  p->vec = T.vec;
 
   auto fail = [&](int rc) {
     atl_plan_destroy(p);
@@ -197,37 +274,17 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
     if (_e != cudaSuccess) return fail(cuda_fail(_e, #call)); \
   } while (0)
 
-  if (fused) {
-    slot_row.resize((size_t)n_slots);
-    std::vector<float> w((size_t)n_slots * TILE_CELLS, 0.f);
-    std::vector<int32_t> active;
-    active.reserve((size_t)n_active);
-    int64_t s = -1, prev = -1, prev_tile = -1;
-    for (const Ent& e : ents) {
-      if (e.key != prev) {
-        prev = e.key;
-        ++s;
-        const int64_t tile = e.key / n_bus;
-        slot_row[(size_t)s] = (int32_t)(e.key - tile * n_bus);
-        tile_slot_ptr[(size_t)tile + 1]++;
-        if (tile != prev_tile) {
-          prev_tile = tile;
-          active.push_back((int32_t)tile);
-        }
-      }
-      w[(size_t)s * TILE_CELLS + e.local] += e.w;  // duplicates sum (csr_matrix semantics)
-    }
-    for (int64_t t = 0; t < n_tiles; ++t) tile_slot_ptr[(size_t)t + 1] += tile_slot_ptr[(size_t)t];
-    PLAN_CUDA(cudaMalloc((void**)&p->d_tile_slot_ptr, tile_slot_ptr.size() * 4));
-    PLAN_CUDA(cudaMemcpy(p->d_tile_slot_ptr, tile_slot_ptr.data(), tile_slot_ptr.size() * 4,
+  if (T.fused) {
+    PLAN_CUDA(cudaMalloc((void**)&p->d_tile_slot_ptr, T.tile_slot_ptr.size() * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_tile_slot_ptr, T.tile_slot_ptr.data(), T.tile_slot_ptr.size() * 4,
                          cudaMemcpyHostToDevice));
-    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_row, std::max<size_t>(slot_row.size(), 1) * 4));
-    PLAN_CUDA(cudaMemcpy(p->d_slot_row, slot_row.data(), slot_row.size() * 4,
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_row, std::max<size_t>(T.slot_row.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_slot_row, T.slot_row.data(), T.slot_row.size() * 4,
                          cudaMemcpyHostToDevice));
-    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, std::max<size_t>(w.size(), 4) * 4));
-    PLAN_CUDA(cudaMemcpy(p->d_slot_w4, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
-    PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(active.size(), 1) * 4));
-    PLAN_CUDA(cudaMemcpy(p->d_active, active.data(), active.size() * 4,
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, std::max<size_t>(T.w.size(), 4) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_slot_w4, T.w.data(), T.w.size() * 4, cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(T.active.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_active, T.active.data(), T.active.size() * 4,
                          cudaMemcpyHostToDevice));
   }
   {

@@ -48,18 +48,22 @@ class TimeShard:
             return t if t.is_cuda else t.cuda()
         return t.cpu()
 
-    def gather_time(self, local, labels=None):
+    def gather_time(self, local, labels=None, counts=None):
         """Concatenate per-rank (nt_r, ...) results along time, in rank order.
-        ``labels=None`` skips the (host-side, pickled) gather of the time labels."""
+        ``labels=None`` skips the (host-side, pickled) gather of the time labels;
+        ``counts`` (steps per rank, when the caller knows the shard layout) skips
+        the size exchange and its host synchronisation."""
         import torch
         import torch.distributed as dist
 
         t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
         t = self._device_for_comm(t.contiguous())
-        n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        counts = [torch.zeros_like(n_local) for _ in range(self.world)]
-        dist.all_gather(counts, n_local, group=self.group)
-        counts = [int(c.item()) for c in counts]
+        if counts is None:
+            n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+            cl = [torch.zeros_like(n_local) for _ in range(self.world)]
+            dist.all_gather(cl, n_local, group=self.group)
+            counts = [int(c.item()) for c in cl]
+        assert len(counts) == self.world and counts[self.rank] == t.shape[0]
         if len(set(counts)) == 1:
             out = torch.empty((self.world * counts[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t, group=self.group)

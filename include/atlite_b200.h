@@ -77,6 +77,16 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
                     const int64_t* indptr_host, const int32_t* indices_host,
                     const double* data_host, AtlPlan** plan_out);
 int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info_out);
+/* Host-only view of the tiling (no CUDA needed; used by the CPU tests and for
+ * inspection): fills *info_out; when the three output arrays are given
+ * (slot_capacity >= n_slots) also tile_slot_ptr[n_tiles+1], slot_row[n_slots] and
+ * slot_w[n_slots*128] (weights in lane order; VEC layout iff nx % 4 == 0:
+ * cell (iy, ix) of a tile sits at ((iy%4)*8 + (ix%32)/4)*4 + ix%4, else at
+ * (ix%32)*4 + iy%4). */
+int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr_host,
+                         const int32_t* indices_host, const double* data_host,
+                         AtlPlanInfo* info_out, int32_t* tile_slot_ptr_out,
+                         int32_t* slot_row_out, float* slot_w_out, int64_t slot_capacity);
 void atl_plan_destroy(AtlPlan* plan);
 
 /* Generic (time, S) dense  x  CSR^T  ->  (time, n_bus)  (aggregate.py:24-32):

@@ -1,0 +1,106 @@
+"""CPU tests of the aggregation-plan tiling (atl_plan_tiling_host, no GPU): the
+(tile, bus) slots with their 128-entry weight vectors must reproduce the CSR
+matrix EXACTLY (float32 weights), for both lane layouts, ragged grids,
+duplicates, explicit zeros and empty rows."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from hypothesis import given, settings, strategies as st
+
+from atlite_b200 import _lib, synthetic as syn
+
+
+def tiling(m, ny, nx):
+    lib = _lib.load()
+    m = sp.csr_matrix(m)
+    indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    idx = np.ascontiguousarray(m.indices, dtype=np.int32)
+    dat = np.ascontiguousarray(m.data, dtype=np.float64)
+    info = _lib.PlanInfo()
+    _lib.check(lib.atl_plan_tiling_host(ny, nx, m.shape[0], _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat),
+                                        C.byref(info), None, None, None, 0))
+    ns = max(int(info.n_slots), 1)
+    tsp = np.zeros(info.n_tiles + 1, dtype=np.int32)
+    row = np.zeros(ns, dtype=np.int32)
+    w = np.zeros(ns * 128, dtype=np.float32)
+    _lib.check(lib.atl_plan_tiling_host(ny, nx, m.shape[0], _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat),
+                                        C.byref(info), _lib.ptr(tsp), _lib.ptr(row), _lib.ptr(w), ns))
+    return info, tsp, row[: info.n_slots], w[: info.n_slots * 128].reshape(-1, 128)
+
+
+def dense_from_tiling(info, tsp, row, w, n_bus, ny, nx):
+    """Invert the lane layout documented in include/atlite_b200.h."""
+    vec = nx % 4 == 0
+    n_tx = -(-nx // 32)
+    out = np.zeros((n_bus, ny * nx), dtype=np.float64)
+    for tile in range(info.n_tiles):
+        ty, tx = divmod(tile, n_tx)
+        for s in range(tsp[tile], tsp[tile + 1]):
+            for ly in range(4):
+                for lx in range(32):
+                    iy, ix = ty * 4 + ly, tx * 32 + lx
+                    loc = ((ly * 8 + lx // 4) * 4 + (lx & 3)) if vec else (lx * 4 + ly)
+                    if iy < ny and ix < nx:
+                        out[row[s], iy * nx + ix] += w[s, loc]
+                    else:
+                        assert w[s, loc] == 0.0, "weight on an out-of-grid cell"
+    return out
+
+
+@settings(max_examples=40, deadline=None)
+@given(ny=st.integers(1, 11), nx=st.integers(1, 70), n_bus=st.integers(1, 6),
+       density=st.floats(0.01, 0.6), seed=st.integers(0, 10_000))
+def test_tiling_reproduces_csr(ny, nx, n_bus, density, seed):
+    rng = np.random.default_rng(seed)
+    S = ny * nx
+    m = sp.random(n_bus, S, density=density, random_state=seed, format="csr",
+                  data_rvs=lambda k: rng.uniform(-2, 2, k))
+    info, tsp, row, w = tiling(m, ny, nx)
+    want = np.asarray(m.astype(np.float32).todense(), dtype=np.float64)
+    got = dense_from_tiling(info, tsp, row, w, n_bus, ny, nx)
+    np.testing.assert_array_equal(got, want)
+    assert info.nnz == m.nnz and tsp[-1] == info.n_slots
+    assert (np.diff(tsp) >= 0).all()
+    # slots of a tile are distinct buses in ascending order
+    for t in range(info.n_tiles):
+        r = row[tsp[t]:tsp[t + 1]]
+        assert (np.diff(r) > 0).all()
+
+
+def test_duplicates_zeros_and_empty_rows():
+    ny, nx = 6, 40
+    S = ny * nx
+    m = sp.csr_matrix((np.array([1.0, 2.0, 0.0, -3.0, 0.5]), (np.array([0, 0, 1, 3, 3]), np.array([5, 5, 7, S - 1, S - 1]))),
+                      shape=(4, S))  # COO duplicates are summed by csr_matrix
+    info, tsp, row, w = tiling(m, ny, nx)
+    got = dense_from_tiling(info, tsp, row, w, 4, ny, nx)
+    np.testing.assert_array_equal(got, np.asarray(m.todense()))
+    assert got[0, 5] == 3.0 and got[3, S - 1] == -2.5 and not got[2].any()
+
+
+def test_shape_like_matrices_fuse_and_identity_does_not():
+    info, *_ = tiling(syn.make_shapes(200, 200, 100), 200, 200)
+    assert info.fused == 1 and 2.0 < info.slots_per_active_tile < 5.0
+    assert info.n_active_tiles == info.n_tiles == 7 * 50
+    info, *_ = tiling(sp.identity(64 * 8, format="csr"), 8, 64)
+    assert info.fused == 0  # one bus per cell: two-pass CSR path
+    info, *_ = tiling(sp.csr_matrix((3, 64 * 8)), 8, 64)
+    assert info.n_active_tiles == 0 and info.n_slots == 0
+    # land mask: tiles without any entry are inactive (their inputs are never read)
+    m = syn.make_shapes(128, 64, 10).tolil()
+    m[:, : 64 * 128 // 2] = 0
+    info, *_ = tiling(m.tocsr(), 64, 128)
+    assert info.n_active_tiles == info.n_tiles // 2
+
+
+def test_bad_input_is_rejected():
+    lib = _lib.load()
+    info = _lib.PlanInfo()
+    indptr = np.array([0, 1], dtype=np.int64)
+    idx = np.array([99], dtype=np.int32)
+    dat = np.array([1.0])
+    rc = lib.atl_plan_tiling_host(2, 4, 1, _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat), C.byref(info), None, None, None, 0)
+    assert rc == -1 and b"out of range" in lib.atl_last_error()
