@@ -7,12 +7,28 @@ hand-written sm_100a CUDA kernels in ``libatlite_b200.so``.
 
 from . import resource
 from .convert import (
+    coefficient_of_performance,
     convert_and_aggregate,
+    convert_coefficient_of_performance,
+    convert_cooling_demand,
+    convert_dewpoint_temperature,
     convert_heat_demand,
+    convert_irradiation,
     convert_pv,
+    convert_runoff,
+    convert_soil_temperature,
+    convert_solar_thermal,
+    convert_temperature,
     convert_wind,
+    cooling_demand,
+    dewpoint_temperature,
     heat_demand,
+    irradiation,
     pv,
+    runoff,
+    soil_temperature,
+    solar_thermal,
+    temperature,
     wind,
 )
 from .cutout import Cutout

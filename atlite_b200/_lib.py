@@ -24,6 +24,7 @@ IRR_DIRECT_DIFFUSE, IRR_INFLUX = 0, 1
 ALBEDO_VAR, ALBEDO_OUTFLUX = 0, 1
 SOLAR_COMPUTED, SOLAR_STORED_F32, SOLAR_STORED_F64 = 0, 1, 2
 PANEL = {"huld": 0, "bofinger": 1}
+OUTPUT = {"panel": 0, "total": 1, "direct": 2, "diffuse": 3, "ground": 4, "solar_thermal": 5}
 WIND_NONE, WIND_LOG, WIND_POWER = 0, 1, 2
 
 
@@ -65,6 +66,8 @@ class PvConfig(C.Structure):
         ("panel_model", C.c_int32),
         ("altitude_threshold_deg", C.c_double),
         ("panel", C.c_double * 16),
+        ("output", C.c_int32),
+        ("thermal", C.c_double * 3),
     ]
 
 
@@ -110,6 +113,22 @@ class HeatConfig(C.Structure):
         ("threshold_c", C.c_double),
         ("a", C.c_double),
         ("constant", C.c_double),
+        ("cooling", C.c_int32),
+    ]
+
+
+class PointwiseConfig(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("shift", C.c_double),
+        ("nan_to_zero", C.c_int32),
+        ("poly", C.c_int32),
+        ("sink", C.c_double),
+        ("c0", C.c_double),
+        ("c1", C.c_double),
+        ("c2", C.c_double),
+        ("cell_scale", C.c_void_p),
     ]
 
 
@@ -146,6 +165,13 @@ _SIGNATURES = {
     "atl_heat_timesum": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "atl_heat_reduce_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int64]),
     "atl_heat_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
+    "atl_pointwise_create": (C.c_int, [C.c_int, C.POINTER(PointwiseConfig), C.POINTER(_P)]),
+    "atl_pointwise_destroy": (None, [_P]),
+    "atl_pointwise_reduce": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "atl_pointwise_cells": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "atl_pointwise_timesum": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "atl_pointwise_reduce_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64]),
+    "atl_pointwise_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -113,7 +113,7 @@ class _PvSpec(_Spec):
     name = "specific generation"
 
     def __init__(self, ds, panel, orientation, tracking=None, trigon_model="simple",
-                 clearsky_model="simple"):
+                 clearsky_model="simple", output="panel", thermal=(0.0, 0.0, 0.0)):
         ny, nx = _grid_shape(ds)
         self.ds = ds
         self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
@@ -175,6 +175,8 @@ class _PvSpec(_Spec):
         trigon = _lib.TRIGON_SIMPLE if trigon_model == "simple" else _lib.TRIGON_HAY_DAVIES
 
         names = ["influx_toa", "temperature"]
+        if output in ("total", "direct", "diffuse", "ground") and not _has(ds, "temperature"):
+            names = ["influx_toa"]  # irradiation needs no temperature (convert.py:748-767)
         names += ["influx"] if irr_branch == _lib.IRR_INFLUX else ["influx_direct", "influx_diffuse"]
         if irr_branch == _lib.IRR_INFLUX and clearsky == 1:
             names.append("humidity")
@@ -182,10 +184,12 @@ class _PvSpec(_Spec):
         if solar_src != _lib.SOLAR_COMPUTED:
             names += ["solar_altitude", "solar_azimuth"]
         self.fields = {n: _raw(ds, n) for n in names}
+        self.fields.setdefault("temperature", self.fields["influx_toa"])  # unused placeholder
         self.op = engine.PvOp(
             ny=ny, nx=nx, time=self.time_labels, lon=lon, lat=lat, slope=slope, azimuth=azimuth,
             tracking=tracking, trigon_model=trigon, clearsky_model=clearsky,
             irr_branch=irr_branch, albedo_src=albedo_src, solar_src=solar_src, panel=panel,
+            output=output, thermal=thermal,
         )
 
     def reduce(self, plan):
@@ -193,6 +197,83 @@ class _PvSpec(_Spec):
 
     def cells(self, timesum=False):
         return self.op.cells(self._device_fields(self.fields), timesum=timesum)
+
+
+class _IrradiationSpec(_PvSpec):
+    """convert_irradiation (convert.py:748-767): the PV operator without the panel."""
+
+    units = "W m**-2"
+
+    def __init__(self, ds, orientation, tracking=None, irradiation="total", trigon_model="simple",
+                 clearsky_model="simple"):
+        if irradiation not in ("total", "direct", "diffuse", "ground"):
+            raise ValueError(f"irradiation must be total, direct, diffuse or ground, not {irradiation!r}")
+        super().__init__(ds, None, orientation, tracking, trigon_model, clearsky_model, output=irradiation)
+        self.name = f"{irradiation} tilted"
+
+
+class _SolarThermalSpec(_PvSpec):
+    """convert_solar_thermal (convert.py:550-573)."""
+
+    def __init__(self, ds, orientation, trigon_model, clearsky_model, c0, c1, t_store):
+        super().__init__(ds, None, orientation, None, trigon_model, clearsky_model,
+                         output="solar_thermal", thermal=(c0, c1, t_store))
+        self.name = None
+
+
+class _PointwiseSpec(_Spec):
+    """Pointwise function of one (time, y, x) variable."""
+
+    def __init__(self, ds, var, shift=0.0, nan_to_zero=False, poly=None, cell_scale=None, name=None):
+        ny, nx = _grid_shape(ds)
+        if not _has(ds, var):
+            raise KeyError(var)
+        self.field = _raw(ds, var)
+        self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
+        self.name = name
+        self.op = engine.PointwiseOp(ny=ny, nx=nx, shift=shift, nan_to_zero=nan_to_zero, poly=poly,
+                                     cell_scale=cell_scale)
+
+    def reduce(self, plan):
+        return self.op.reduce(plan, self.field)
+
+    def cells(self, timesum=False):
+        f = self._device_fields({"f": self.field})
+        return self.op.cells(f["f"], timesum=timesum)
+
+
+def _temperature_spec(ds):
+    return _PointwiseSpec(ds, "temperature", shift=-273.15, name="temperature")
+
+
+def _soil_temperature_spec(ds):
+    return _PointwiseSpec(ds, "soil temperature", shift=-273.15, nan_to_zero=True, name="soil temperature")
+
+
+def _dewpoint_temperature_spec(ds):
+    return _PointwiseSpec(ds, "dewpoint temperature", shift=-273.15, name="dewpoint temperature")
+
+
+def _cop_spec(ds, source, sink_T, c0, c1, c2):
+    assert source in ["air", "soil"], NotImplementedError("'source' must be one of  ['air', 'soil']")
+    if source == "air":  # convert.py:343-350
+        d = (6.81, -0.121, 0.000630)
+        var, nz = "temperature", False
+    else:  # convert.py:351-358
+        d = (8.77, -0.150, 0.000734)
+        var, nz = "soil temperature", True
+    c0, c1, c2 = (dv if v is None else v for v, dv in zip((c0, c1, c2), d))
+    return _PointwiseSpec(ds, var, shift=-273.15, nan_to_zero=nz, poly=(sink_T, c0, c1, c2))
+
+
+def _runoff_spec(ds, weight_with_height=True):
+    scale = None
+    if weight_with_height:
+        h = _raw(ds, "height")
+        scale = _to_host(h)
+        if scale.ndim == 3:
+            scale = scale[0]
+    return _PointwiseSpec(ds, "runoff", cell_scale=scale, name="runoff")
 
 
 class _WindSpec(_Spec):
@@ -265,12 +346,14 @@ def day_bins(time, hour_shift):
 
 class _HeatSpec(_Spec):
     name = "heat_demand"
+    cooling = False
 
     def __init__(self, ds, threshold, a, constant, hour_shift):
         ny, nx = _grid_shape(ds)
         self.temp = _raw(ds, "temperature")
         self.time_labels, self.day_start = day_bins(_coord(ds, "time"), hour_shift)
-        self.op = engine.HeatOp(ny=ny, nx=nx, threshold=threshold, a=a, constant=constant)
+        self.op = engine.HeatOp(ny=ny, nx=nx, threshold=threshold, a=a, constant=constant,
+                                cooling=self.cooling)
 
     def reduce(self, plan):
         return self.op.reduce(plan, self.temp, self.day_start)
@@ -278,6 +361,13 @@ class _HeatSpec(_Spec):
     def cells(self, timesum=False):
         f = self._device_fields({"t": self.temp})
         return self.op.cells(f["t"], self.day_start, timesum=timesum)
+
+
+class _CoolingSpec(_HeatSpec):
+    """convert_cooling_demand (convert.py:475-491): a * (Tmean - threshold)."""
+
+    name = "cooling_demand"
+    cooling = True
 
 
 # --------------------------------------------------------------------------
@@ -309,7 +399,63 @@ def convert_heat_demand(ds, threshold, a, constant, hour_shift):
     return _wrap_cells(ds, spec, spec.cells())
 
 
-_SPECS = {"convert_pv": _PvSpec, "convert_wind": _WindSpec, "convert_heat_demand": _HeatSpec}
+def convert_irradiation(ds, orientation, tracking=None, irradiation="total", trigon_model="simple",
+                        clearsky_model="simple"):
+    """Per-cell tilted irradiation (time, y, x); convert.py:748-767."""
+    spec = _IrradiationSpec(ds, orientation, tracking, irradiation, trigon_model, clearsky_model)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_solar_thermal(ds, orientation, trigon_model, clearsky_model, c0, c1, t_store):
+    """Per-cell solar thermal collector output; convert.py:550-573."""
+    spec = _SolarThermalSpec(ds, orientation, trigon_model, clearsky_model, c0, c1, t_store)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_temperature(ds):
+    """Outside temperature in deg C; convert.py:292-298."""
+    spec = _temperature_spec(ds)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_soil_temperature(ds):
+    """Soil temperature in deg C, 0 over sea; convert.py:306-316."""
+    spec = _soil_temperature_spec(ds)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_dewpoint_temperature(ds):
+    """Dewpoint temperature in deg C; convert.py:324-329."""
+    spec = _dewpoint_temperature_spec(ds)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_coefficient_of_performance(ds, source, sink_T, c0, c1, c2):
+    """Heat pump COP; convert.py:338-366."""
+    spec = _cop_spec(ds, source, sink_T, c0, c1, c2)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_cooling_demand(ds, threshold, a, constant, hour_shift):
+    """Per-cell daily cooling demand; convert.py:475-491."""
+    spec = _CoolingSpec(ds, threshold, a, constant, hour_shift)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+def convert_runoff(ds, weight_with_height=True):
+    """Runoff (optionally weighted with height); convert.py:1028-1034."""
+    spec = _runoff_spec(ds, weight_with_height)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
+_SPECS = {
+    "convert_pv": _PvSpec, "convert_wind": _WindSpec, "convert_heat_demand": _HeatSpec,
+    "convert_irradiation": _IrradiationSpec, "convert_solar_thermal": _SolarThermalSpec,
+    "convert_temperature": _temperature_spec, "convert_soil_temperature": _soil_temperature_spec,
+    "convert_dewpoint_temperature": _dewpoint_temperature_spec,
+    "convert_coefficient_of_performance": _cop_spec, "convert_cooling_demand": _CoolingSpec,
+    "convert_runoff": _runoff_spec,
+}
 
 
 def _known_spec(convert_func):
@@ -587,3 +733,103 @@ def pv(cutout, panel, orientation, tracking=None, clearsky_model=None, **params)
         clearsky_model=clearsky_model,
         **params,
     )
+
+
+# --------------------------------------------------------------------------
+# further technology wrappers on the same path
+# --------------------------------------------------------------------------
+
+
+def temperature(cutout, **params):
+    """convert.py:301-302"""
+    return cutout.convert_and_aggregate(convert_func=convert_temperature, **params)
+
+
+def soil_temperature(cutout, **params):
+    """convert.py:319-320"""
+    return cutout.convert_and_aggregate(convert_func=convert_soil_temperature, **params)
+
+
+def dewpoint_temperature(cutout, **params):
+    """convert.py:332-335"""
+    return cutout.convert_and_aggregate(convert_func=convert_dewpoint_temperature, **params)
+
+
+def coefficient_of_performance(cutout, source="air", sink_T=55.0, c0=None, c1=None, c2=None, **params):
+    """Air- or ground-sourced heat pump COP (convert.py:369-401)."""
+    return cutout.convert_and_aggregate(
+        convert_func=convert_coefficient_of_performance,
+        source=source, sink_T=sink_T, c0=c0, c1=c1, c2=c2, **params,
+    )
+
+
+def cooling_demand(cutout, threshold=23.0, a=1.0, constant=0.0, hour_shift=0.0, **params):
+    """Daily cooling demand by the degree-day approximation (convert.py:494-546)."""
+    return cutout.convert_and_aggregate(
+        convert_func=convert_cooling_demand,
+        threshold=threshold, a=a, constant=constant, hour_shift=hour_shift, **params,
+    )
+
+
+def solar_thermal(cutout, orientation={"slope": 45.0, "azimuth": 180.0}, trigon_model="simple",
+                  clearsky_model="simple", c0=0.8, c1=3.0, t_store=80.0, **params):
+    """Solar thermal collector time series (convert.py:576-630)."""
+    if not callable(orientation):
+        orientation = get_orientation(orientation)
+    return cutout.convert_and_aggregate(
+        convert_func=convert_solar_thermal,
+        orientation=orientation, trigon_model=trigon_model, clearsky_model=clearsky_model,
+        c0=c0, c1=c1, t_store=t_store, **params,
+    )
+
+
+def irradiation(cutout, orientation, irradiation="total", tracking=None, clearsky_model=None, **params):
+    """Total / direct / diffuse / ground irradiation on a tilted surface (convert.py:770-836)."""
+    if not callable(orientation):
+        orientation = get_orientation(orientation)
+    return cutout.convert_and_aggregate(
+        convert_func=convert_irradiation,
+        orientation=orientation, tracking=tracking, irradiation=irradiation,
+        clearsky_model=clearsky_model, **params,
+    )
+
+
+def runoff(cutout, smooth=None, lower_threshold_quantile=None, normalize_using_yearly=None, **params):
+    """Runoff aggregated to buses with the reference's optional post-processing
+    (rolling mean, lower-quantile cut, yearly normalisation; convert.py:1037-1084)."""
+    result = cutout.convert_and_aggregate(convert_func=convert_runoff, **params)
+    res, cap = (result if isinstance(result, tuple) else (result, None))
+    if "time" not in res.dims or (smooth is None and lower_threshold_quantile is None
+                                  and normalize_using_yearly is None):
+        return result
+    tax = list(res.dims).index("time")
+    vals = np.asarray(res.values, dtype=np.float64)
+    if smooth is not None:
+        if smooth is True:
+            smooth = 24 * 7
+        frame = pd.DataFrame(np.moveaxis(vals, tax, 0).reshape(vals.shape[tax], -1))
+        sm = frame.rolling(smooth, min_periods=1).mean().values
+        vals = np.moveaxis(sm.reshape(np.moveaxis(vals, tax, 0).shape), 0, tax)
+    if lower_threshold_quantile is not None:
+        if lower_threshold_quantile is True:
+            lower_threshold_quantile = 5e-3
+        lower = pd.Series(vals.ravel()).quantile(lower_threshold_quantile)
+        vals = np.where(vals >= lower, vals, 0.0)
+    if normalize_using_yearly is not None:
+        idx = normalize_using_yearly.index
+        idx = idx.year if isinstance(idx, pd.DatetimeIndex) else idx.astype(int)
+        tyears = pd.DatetimeIndex(np.asarray(res.coords["time"])).year
+        full = pd.Series(tyears).value_counts().loc[lambda x: x > 8700].index.intersection(idx)
+        assert len(full), "Need at least a full year of data (more is better)"
+        sel = (tyears >= min(full)) & (tyears <= max(full))
+        norm = normalize_using_yearly.copy()
+        norm.index = idx
+        target = norm.loc[min(full):max(full)].sum()
+        other = [d for d in res.dims if d != "time"][0]
+        target = target.reindex(pd.Index(np.asarray(res.coords[other]))).values
+        have = np.take(vals, np.flatnonzero(sel), axis=tax).sum(axis=tax)
+        factor = target / have
+        vals = vals * (factor[:, None] if tax == 1 else factor[None, :])
+    out = make_dataarray(vals, tuple(res.dims), {d: np.asarray(res.coords[d]) for d in res.dims},
+                         dict(res.attrs), getattr(res, "name", None))
+    return (out, cap) if cap is not None else out

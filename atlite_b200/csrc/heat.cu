@@ -16,6 +16,7 @@ struct HeatParams {
   int64_t S;
   int nx;
   float thr_k, a, constant;
+  int cooling;  // 1: a * (Tmean - threshold)   (convert.py:475-491)
 };
 
 constexpr int HEAT_UNROLL = 6;
@@ -66,7 +67,7 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<V
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const float mean = sum[r] / cnt[r];  // empty bin -> NaN, as xarray
-    float h = hp.a * (hp.thr_k - mean);  // convert.py:413-414
+    float h = hp.a * (hp.cooling ? (mean - hp.thr_k) : (hp.thr_k - mean));  // convert.py:413-414 / 484-485
     h = (h == h) ? fmaxf(h, 0.f) : h;    // .clip(min=0) keeps NaN  :416
     h = hp.constant + h;                 // :418
     v[r] = h;
@@ -118,6 +119,7 @@ struct AtlHeatOp {
   int device;
   GridDev grid;
   float thr_k, a, constant;
+  int cooling;  // 1: a * (Tmean - threshold)   (convert.py:475-491)
 };
 
 static int upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out,
@@ -188,6 +190,7 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   hp.thr_k = op->thr_k;
   hp.a = op->a;
   hp.constant = op->constant;
+  hp.cooling = op->cooling;
   int db = (int)((n_days * gx + 148LL * 4 * 8 - 1) / (148LL * 4 * 8));
   db = db < 1 ? 1 : (db > 8 ? 8 : db);
   dim3 grid(gx, (unsigned)((n_days + db - 1) / db));
@@ -252,6 +255,7 @@ int atl_heat_create(int device, const AtlHeatConfig* cfg, AtlHeatOp** op_out) {
   op->thr_k = (float)(cfg->threshold_c + 273.15);
   op->a = (float)cfg->a;
   op->constant = (float)cfg->constant;
+  op->cooling = cfg->cooling ? 1 : 0;
   *op_out = op;
   return ATL_OK;
 }

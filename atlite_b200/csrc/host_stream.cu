@@ -235,6 +235,23 @@ int atl_wind_reduce_host(const AtlWindOp* op, const AtlPlan* plan, const AtlWind
                       out_host, launch);
 }
 
+int atl_pointwise_reduce_host(const AtlPointwiseOp* op, const AtlPlan* plan,
+                              const float* field_host, int64_t nt, float* out_host,
+                              int64_t chunk_steps) {
+  ATL_REQUIRE(op && plan && field_host, "NULL argument");
+  int32_t device, ny, nx;
+  atl_pointwise_op_info(op, &device, &ny, &nx);
+  std::vector<SlabField> fields = {{(const char*)field_host, 4}};
+  auto launch = [&](const std::vector<void*>& d, int64_t, int64_t n, float* out_dev,
+                    cudaStream_t st) {
+    return atl_pointwise_reduce(op, plan, (const float*)d[0], n, out_dev, (void*)st);
+  };
+  AtlPlanInfo pi;
+  atl_plan_info(plan, &pi);
+  return stream_slabs(device, fields, (int64_t)ny * nx, nt, nullptr, chunk_steps, pi.n_bus,
+                      out_host, launch);
+}
+
 int atl_heat_reduce_host(const AtlHeatOp* op, const AtlPlan* plan, const float* temperature,
                          const int64_t* day_start, int64_t n_days, float* out_host,
                          int64_t chunk_days) {

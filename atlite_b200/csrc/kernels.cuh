@@ -143,12 +143,13 @@ struct Tuning {
 const Tuning& tuning();
 
 inline int pick_tb(int n_cta_x, int64_t nt) {
-  // aim for >= ~8 waves of 148 SMs x 6 resident CTAs, but keep the per-CTA
-  // prologue (geometry + slot setup) amortised over >= 8 steps
-  const int64_t want = 148LL * 6 * 8;
+  // time steps per CTA: aim for ~24 CTAs per resident slot (148 SMs x 5 CTAs) so
+  // the tail wave is small, but keep the per-CTA prologue (geometry, slot setup)
+  // amortised over >= 16 steps.  Measured optimum 32..128 (profiles/r1_tb_sweep.log).
+  const int64_t want = 148LL * 5 * 24;
   int64_t tb = (nt * n_cta_x + want - 1) / want;
-  if (tb < 8) tb = 8;
-  if (tb > 64) tb = 64;
+  if (tb < 16) tb = 16;
+  if (tb > 128) tb = 128;
   tb += tb & 1;
   if (tb > nt) tb = nt > 0 ? nt : 1;
   return (int)tb;

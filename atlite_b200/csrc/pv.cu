@@ -54,13 +54,15 @@ struct PvPhys {
   int64_t S;
   int nx, ny;
   int t_off;
-  int tracking_, trigon_, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model_;
+  int tracking_, trigon_, clearsky, irr_branch_, albedo_src_, solar_src_, panel_model_, output_;
   float sin_thr, alt_thr;
   float pc[12];
+  float th_c0, th_c1, th_tstore;  // solar thermal (convert.py:565-573), t_store in K
 
   __device__ __forceinline__ int tracking() const { return FAST ? ATL_TRACK_NONE : tracking_; }
   __device__ __forceinline__ int trigon() const { return FAST ? ATL_TRIGON_SIMPLE : trigon_; }
   __device__ __forceinline__ int panel_model() const { return FAST ? ATL_PANEL_HULD : panel_model_; }
+  __device__ __forceinline__ int output() const { return FAST ? ATL_OUT_PANEL : output_; }
   __device__ __forceinline__ int irr_branch() const {
     return FAST ? ATL_IRR_DIRECT_DIFFUSE : irr_branch_;
   }
@@ -241,11 +243,11 @@ struct PvPhys {
 
       // ---- tilted irradiation (pv/irradiation.py:214-236, 76-125, 142-145)
       const float Rb = __fdividef(cosinc, sinalt);
-      float total;
+      const float direct_t = Rb * direct;
+      const float ground_t = albedo * influx_ * fmaf(-0.5f, cslope, 0.5f);
+      float diffuse_t;
       if (trigon() == ATL_TRIGON_SIMPLE) {
-        total = fmaf(Rb, direct,
-                     fmaf(fmaf(0.5f, cslope, 0.5f), diffuse,
-                          albedo * influx_ * fmaf(-0.5f, cslope, 0.5f)));
+        diffuse_t = fmaf(0.5f, cslope, 0.5f) * diffuse;
       } else {
         float hd3 = c.hd3[b];
         if (trk == ATL_TRACK_HORIZONTAL || trk == ATL_TRACK_TILTED_HORIZONTAL) {
@@ -254,18 +256,31 @@ struct PvPhys {
         }
         const float f = influx_ > 0.f ? sqrtf(__fdividef(direct, influx_)) : 0.f;
         const float A = direct / toa_;
-        float dt = fmaf(A, Rb, (1.f - A) * fmaf(0.5f, cslope, 0.5f) * fmaf(f, hd3, 1.f)) * diffuse;
-        dt = fmaxf(dt, 0.f);  // clip(min=0).fillna(0): fmaxf drops NaN
-        total = fmaf(Rb, direct, dt) + influx_ * albedo * fmaf(-0.5f, cslope, 0.5f);
+        diffuse_t = fmaf(A, Rb, (1.f - A) * fmaf(0.5f, cslope, 0.5f) * fmaf(f, hd3, 1.f)) * diffuse;
+        diffuse_t = fmaxf(diffuse_t, 0.f);  // clip(min=0).fillna(0): fmaxf drops NaN
       }
-      // altitude / darkness mask  :251-252
+      float total = direct_t + diffuse_t + ground_t;
+      const int out = output();
+      if (out == ATL_OUT_DIRECT) total = direct_t;         // pv/irradiation.py:238-245
+      else if (out == ATL_OUT_DIFFUSE) total = diffuse_t;
+      else if (out == ATL_OUT_GROUND) total = ground_t;
       // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
       // stored mode compares the stored altitude itself, as the reference does
       const bool low = (solar_src() == ATL_SOLAR_COMPUTED) ? (sinalt < sin_thr)
                                                            : (r.salt[i] < alt_thr);
       const bool masked = low || (influx_ <= 0.01f);
       const float G = masked ? 0.f : total;
-      v[i] = panel(G, r.temp[i]);
+      if (out == ATL_OUT_PANEL) {
+        v[i] = panel(G, r.temp[i]);
+      } else if (out == ATL_OUT_SOLAR_THERMAL) {
+        // eta = c0 - c1 * ((t_store - T) / irr.where(irr != 0)).fillna(0); output.where(> 0, 0)
+        const float q = (th_tstore - r.temp[i]) / G;
+        const float eta = th_c0 - th_c1 * ((G != 0.f && q == q) ? q : 0.f);
+        const float o = G * eta;
+        v[i] = (o > 0.f) ? o : 0.f;
+      } else {
+        v[i] = G;
+      }
     }
   }
 };
@@ -278,7 +293,8 @@ struct AtlPvOp {
   int device;
   GridDev grid;
   int64_t nt;
-  int tracking, trigon, clearsky, irr_branch, albedo_src, solar_src, panel_model;
+  int tracking, trigon, clearsky, irr_branch, albedo_src, solar_src, panel_model, output;
+  float th_c0, th_c1, th_tstore;
   float sin_thr, alt_thr;
   float pc[12];
   float4* d_tt = nullptr;
@@ -314,6 +330,10 @@ static PvPhys<FAST, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int6
   p.albedo_src_ = op->albedo_src;
   p.solar_src_ = op->solar_src;
   p.panel_model_ = op->panel_model;
+  p.output_ = op->output;
+  p.th_c0 = op->th_c0;
+  p.th_c1 = op->th_c1;
+  p.th_tstore = op->th_tstore;
   p.sin_thr = op->sin_thr;
   p.alt_thr = op->alt_thr;
   for (int i = 0; i < 12; ++i) p.pc[i] = op->pc[i];
@@ -367,6 +387,7 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   ATL_REQUIRE(cfg->albedo_src >= 0 && cfg->albedo_src <= 1, "bad albedo source");
   ATL_REQUIRE(cfg->solar_src >= 0 && cfg->solar_src <= 2, "bad solar source");
   ATL_REQUIRE(cfg->panel_model >= 0 && cfg->panel_model <= 1, "Unknown panel model");
+  ATL_REQUIRE(cfg->output >= ATL_OUT_PANEL && cfg->output <= ATL_OUT_SOLAR_THERMAL, "bad output kind");
 
   const double PI = 3.14159265358979323846;
   const double D2R = PI / 180.0;
@@ -381,11 +402,16 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   op->albedo_src = cfg->albedo_src;
   op->solar_src = cfg->solar_src;
   op->panel_model = cfg->panel_model;
+  op->output = cfg->output;
+  op->th_c0 = (float)cfg->thermal[0];
+  op->th_c1 = (float)cfg->thermal[1];
+  op->th_tstore = (float)(cfg->thermal[2] + 273.15);
   op->sin_thr = (float)std::sin(cfg->altitude_threshold_deg * D2R);
   op->alt_thr = (float)(cfg->altitude_threshold_deg * D2R);
   op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
              cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR &&
-             cfg->trigon_model == ATL_TRIGON_SIMPLE && cfg->panel_model == ATL_PANEL_HULD;
+             cfg->trigon_model == ATL_TRIGON_SIMPLE && cfg->panel_model == ATL_PANEL_HULD &&
+             cfg->output == ATL_OUT_PANEL;
   const double* P = cfg->panel;
   for (int i = 0; i < 12; ++i) op->pc[i] = 0.f;
   if (cfg->panel_model == ATL_PANEL_HULD) {

@@ -139,5 +139,13 @@ class Cutout:
     # ---- conversion and aggregation (cutout.py:653-689)
     convert_and_aggregate = _convert.convert_and_aggregate
     heat_demand = _convert.heat_demand
+    cooling_demand = _convert.cooling_demand
+    temperature = _convert.temperature
+    soil_temperature = _convert.soil_temperature
+    dewpoint_temperature = _convert.dewpoint_temperature
+    coefficient_of_performance = _convert.coefficient_of_performance
+    solar_thermal = _convert.solar_thermal
+    irradiation = _convert.irradiation
     wind = _convert.wind
     pv = _convert.pv
+    runoff = _convert.runoff

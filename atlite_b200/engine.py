@@ -179,8 +179,8 @@ class PvOp(_Op):
     FIELD_NAMES = tuple(n for n, _ in _lib.PvFields._fields_)
 
     def __init__(self, *, ny, nx, time, lon, lat, slope, azimuth, tracking, trigon_model,
-                 clearsky_model, irr_branch, albedo_src, solar_src, panel, time_shift="0h",
-                 altitude_threshold=1.0, device=None):
+                 clearsky_model, irr_branch, albedo_src, solar_src, panel=None, time_shift="0h",
+                 altitude_threshold=1.0, output="panel", thermal=(0.0, 0.0, 0.0), device=None):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
@@ -199,12 +199,17 @@ class PvOp(_Op):
         cfg.trigon_model = trigon_model
         cfg.clearsky_model = clearsky_model
         cfg.irr_branch, cfg.albedo_src, cfg.solar_src = irr_branch, albedo_src, solar_src
-        model = panel.get("model", "huld")
+        cfg.output = _lib.OUTPUT[output]
+        for i, v in enumerate(thermal):
+            cfg.thermal[i] = float(v)
+        cfg.altitude_threshold_deg = altitude_threshold
+        model = "huld" if panel is None else panel.get("model", "huld")
         if model not in _lib.PANEL:
             raise AssertionError(f"Unknown panel model: {model}")
         cfg.panel_model = _lib.PANEL[model]
-        cfg.altitude_threshold_deg = altitude_threshold
-        if model == "huld":
+        if panel is None:
+            vals = []
+        elif model == "huld":
             vals = [panel["c_temp_amb"], panel["c_temp_irrad"], panel["r_tmod"], panel["r_irradiance"]]
             vals += [panel[f"k_{i}"] for i in range(1, 7)]
             vals += [panel.get("inverter_efficiency", 1.0)]
@@ -336,13 +341,14 @@ class HeatOp(_Op):
 
     _destroy = "atl_heat_destroy"
 
-    def __init__(self, *, ny, nx, threshold, a, constant, device=None):
+    def __init__(self, *, ny, nx, threshold, a, constant, cooling=False, device=None):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
         cfg = _lib.HeatConfig()
         cfg.ny, cfg.nx = ny, nx
         cfg.threshold_c, cfg.a, cfg.constant = float(threshold), float(a), float(constant)
+        cfg.cooling = 1 if cooling else 0
         h = C.c_void_p()
         _lib.check(lib.atl_heat_create(self.device, C.byref(cfg), C.byref(h)))
         self.handle = h
@@ -373,4 +379,58 @@ class HeatOp(_Op):
         else:
             out = self._out((nd, self.ny, self.nx), t)
             _lib.check(lib.atl_heat_cells(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
+        return out
+
+
+class PointwiseOp(_Op):
+    """Pointwise function of one field (temperature family, COP, runoff x height);
+    see include/atlite_b200.h."""
+
+    _destroy = "atl_pointwise_destroy"
+
+    def __init__(self, *, ny, nx, shift=0.0, nan_to_zero=False, poly=None, cell_scale=None, device=None):
+        lib = _lib.load()
+        self.device = current_device() if device is None else device
+        self.ny, self.nx = ny, nx
+        cfg = _lib.PointwiseConfig()
+        cfg.ny, cfg.nx = ny, nx
+        cfg.shift = float(shift)
+        cfg.nan_to_zero = 1 if nan_to_zero else 0
+        cfg.poly = 0 if poly is None else 1
+        if poly is not None:
+            cfg.sink, cfg.c0, cfg.c1, cfg.c2 = (float(v) for v in poly)
+        self._scale = None
+        if cell_scale is not None:
+            self._scale = host_f32(cell_scale)
+            if self._scale.shape != (ny, nx):
+                raise ValueError(f"cell_scale must have shape {(ny, nx)}, has {self._scale.shape}")
+            cfg.cell_scale = self._scale.ctypes.data
+        h = C.c_void_p()
+        _lib.check(lib.atl_pointwise_create(self.device, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    def reduce(self, plan, field, chunk_steps=0):
+        lib = _lib.load()
+        nt = field.shape[0]
+        if _is_torch(field):
+            f = field.contiguous()
+            out = self._out((nt, plan.n_bus), f)
+            _lib.check(lib.atl_pointwise_reduce(self.handle, plan.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
+            return out
+        f = host_f32(field)
+        out = np.empty((nt, plan.n_bus), dtype=np.float32)
+        _lib.check(lib.atl_pointwise_reduce_host(self.handle, plan.handle, _hptr(f), nt, _hptr(out), chunk_steps))
+        return out
+
+    def cells(self, field, timesum=False):
+        lib = _lib.load()
+        f = field.contiguous()
+        nt = f.shape[0]
+        torch = _torch()
+        if timesum:
+            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=f.device)
+            _lib.check(lib.atl_pointwise_timesum(self.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
+        else:
+            out = self._out((nt, self.ny, self.nx), f)
+            _lib.check(lib.atl_pointwise_cells(self.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
         return out

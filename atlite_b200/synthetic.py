@@ -26,7 +26,7 @@ import scipy.sparse as sp
 from .labelled import Dataset
 
 SEEDS = dict(kt=1, fd=2, albedo=3, temperature=4, wnd100m=5, roughness=6, layout=7, shapes=8,
-             wnd_shear_exp=9, humidity=10, outflux=11)
+             wnd_shear_exp=9, humidity=10, outflux=11, soil=12, dewpoint=13, runoff=14, height=15)
 _BLOCK = 24  # RNG block length in time steps
 
 
@@ -99,7 +99,8 @@ def _gen_var(var, nt, ny, nx, t_offset, fn, workers=8):
 def make_fields(time, x, y, kinds=("pv", "wind", "temperature"), t_offset=0, extra=()):
     """Dict of float32 (time, y, x) fields.  ``t_offset``: index of ``time[0]``
     in the full axis (for time shards).  ``extra``: additional variables among
-    'wnd_shear_exp', 'humidity', 'influx', 'outflux', 'solar'."""
+    'wnd_shear_exp', 'humidity', 'influx', 'outflux', 'soil temperature',
+    'dewpoint temperature', 'runoff' (adds the static (y, x) field 'height')."""
     nt, ny, nx = len(time), len(y), len(x)
     f = {}
     if "pv" in kinds:
@@ -132,6 +133,18 @@ def make_fields(time, x, y, kinds=("pv", "wind", "temperature"), t_offset=0, ext
     if "humidity" in extra:
         f["humidity"] = _gen_var("humidity", nt, ny, nx, t_offset,
                                  lambda v, b, sh: _uniform_block(v, b, sh, 0.2, 1.0))
+    if "soil temperature" in extra:  # NaN over "sea" like ERA5 stl4 (convert.py:311-314)
+        st = _gen_var("soil", nt, ny, nx, t_offset, lambda v, b, sh: _uniform_block(v, b, sh, 270.0, 300.0))
+        sea = np.random.default_rng(SEEDS["soil"]).uniform(size=(ny, nx)) < 0.3
+        st[:, sea] = np.nan
+        f["soil temperature"] = st
+    if "dewpoint temperature" in extra:
+        f["dewpoint temperature"] = _gen_var("dewpoint", nt, ny, nx, t_offset,
+                                             lambda v, b, sh: _uniform_block(v, b, sh, 250.0, 295.0))
+    if "runoff" in extra:
+        f["runoff"] = _gen_var("runoff", nt, ny, nx, t_offset,
+                               lambda v, b, sh: _rng(v, b).exponential(2e-4, size=sh).astype(np.float32))
+        f["height"] = np.random.default_rng(SEEDS["height"]).uniform(0.0, 2000.0, size=(ny, nx)).astype(np.float32)
     if "influx" in extra:  # total influx instead of the direct/diffuse pair
         f["influx"] = f.pop("influx_direct") + f.pop("influx_diffuse")
     if "outflux" in extra:

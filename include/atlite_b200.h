@@ -14,6 +14,11 @@
  *   convert.py:840-854  convert_pv  (+ pv/*.py)                 atl_pv_create, atl_pv_reduce/cells/timesum
  *   convert.py:634-662  convert_wind (+ wind.py:24-128)         atl_wind_create, atl_wind_*
  *   convert.py:405-418  convert_heat_demand                     atl_heat_create, atl_heat_*
+ *   convert.py:475-491  convert_cooling_demand                  atl_heat_* with AtlHeatConfig.cooling = 1
+ *   convert.py:748-767  convert_irradiation                     atl_pv_* with AtlPvConfig.output = ATL_OUT_TOTAL..GROUND
+ *   convert.py:550-573  convert_solar_thermal                   atl_pv_* with AtlPvConfig.output = ATL_OUT_SOLAR_THERMAL
+ *   convert.py:292-366  temperature / soil / dewpoint / COP     atl_pointwise_*
+ *   convert.py:1028-1034 convert_runoff                         atl_pointwise_* with cell_scale = height
  *   convert.py:200-211  no-matrix branch (_aggregate_time)      *_cells, *_timesum
  *   convert.py:257-271  reduce + time aggregation               *_reduce (+ host finalisation in Python)
  *
@@ -49,7 +54,7 @@ extern "C" {
 #define ATL_ERR_CUDA (-2)    /* CUDA runtime error (see atl_last_error) */
 #define ATL_ERR_NOMEM (-3)
 
-#define ATL_ABI_VERSION 1
+#define ATL_ABI_VERSION 2
 
 int atl_abi_version(void);
 const char* atl_last_error(void);
@@ -106,6 +111,11 @@ enum { ATL_IRR_DIRECT_DIFFUSE = 0, ATL_IRR_INFLUX = 1 };    /* pv/irradiation.py
 enum { ATL_ALBEDO_VAR = 0, ATL_ALBEDO_OUTFLUX = 1 };        /* pv/irradiation.py:128-139 */
 enum { ATL_SOLAR_COMPUTED = 0, ATL_SOLAR_STORED_F32 = 1, ATL_SOLAR_STORED_F64 = 2 }; /* pv/solar_position.py:54-60 vs 69-116 */
 enum { ATL_PANEL_HULD = 0, ATL_PANEL_BOFINGER = 1 };        /* pv/solar_panel_model.py:12-74 */
+/* what the PV operator emits: panel power (convert_pv), one tilted-irradiation
+ * component (convert_irradiation, pv/irradiation.py:238-245), or solar-thermal
+ * collector output (convert_solar_thermal, convert.py:565-573) */
+enum { ATL_OUT_PANEL = 0, ATL_OUT_TOTAL = 1, ATL_OUT_DIRECT = 2, ATL_OUT_DIFFUSE = 3,
+       ATL_OUT_GROUND = 4, ATL_OUT_SOLAR_THERMAL = 5 };
 
 typedef struct {
   int32_t ny, nx;
@@ -122,6 +132,8 @@ typedef struct {
   /* Huld: c_temp_amb, c_temp_irrad, r_tmod, r_irradiance, k_1..k_6, inverter_efficiency
    * Bofinger: A, B, C, D, NOCT, Tamb, Intc, Tstd, ta, threshold, inverter_efficiency */
   double panel[16];
+  int32_t output;             /* ATL_OUT_*; panel[] is ignored unless ATL_OUT_PANEL */
+  double thermal[3];          /* ATL_OUT_SOLAR_THERMAL: c0, c1, t_store in deg C  */
 } AtlPvConfig;
 
 typedef struct { /* device pointers to (nt_slab, ny, nx) slabs; unused = NULL */
@@ -188,6 +200,7 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt,
 typedef struct {
   int32_t ny, nx;
   double threshold_c, a, constant; /* convert.py:413-418 (threshold in deg C) */
+  int32_t cooling;                 /* 1: a * (Tmean - threshold), convert.py:475-491 */
 } AtlHeatConfig;
 
 typedef struct AtlHeatOp AtlHeatOp;
@@ -204,6 +217,37 @@ int atl_heat_cells(const AtlHeatOp* op, const float* temperature_dev,
 int atl_heat_timesum(const AtlHeatOp* op, const float* temperature_dev,
                      const int64_t* day_start_host, int64_t n_days, float* out_dev,
                      void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Pointwise conversions of ONE (time, y, x) field:                    */
+/*   y = x + shift;  nan_to_zero: y = 0 where NaN;                     */
+/*   poly: d = sink - y, out = c0 + c1 d + c2 d^2  else out = y;       */
+/*   out *= cell_scale[y, x] (optional static (ny, nx) field)          */
+/* temperature / dewpoint (shift = -273.15), soil temperature          */
+/* (+ nan_to_zero), coefficient_of_performance (poly), runoff          */
+/* (cell_scale = height): convert.py:292-366, 1028-1034.               */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int32_t ny, nx;
+  double shift;
+  int32_t nan_to_zero;
+  int32_t poly;
+  double sink, c0, c1, c2;
+  const float* cell_scale; /* host, ny*nx, or NULL */
+} AtlPointwiseConfig;
+
+typedef struct AtlPointwiseOp AtlPointwiseOp;
+int atl_pointwise_create(int device, const AtlPointwiseConfig* cfg, AtlPointwiseOp** op_out);
+void atl_pointwise_destroy(AtlPointwiseOp* op);
+int atl_pointwise_reduce(const AtlPointwiseOp* op, const AtlPlan* plan, const float* field_dev,
+                         int64_t nt, float* out_dev, void* stream);
+int atl_pointwise_cells(const AtlPointwiseOp* op, const float* field_dev, int64_t nt,
+                        float* out_dev, void* stream);
+int atl_pointwise_timesum(const AtlPointwiseOp* op, const float* field_dev, int64_t nt,
+                          float* out_dev, void* stream);
+int atl_pointwise_reduce_host(const AtlPointwiseOp* op, const AtlPlan* plan,
+                              const float* field_host, int64_t nt, float* out_host,
+                              int64_t chunk_steps);
 
 /* ------------------------------------------------------------------ */
 /* Host-buffer entry points: the call the reference-facing Python API  */
@@ -226,6 +270,7 @@ int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
                    int32_t* solar_src);
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
+int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" evidence). */

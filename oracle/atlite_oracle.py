@@ -476,6 +476,90 @@ def convert_pv(
     return solar_panel_model(ds, irr, panel)
 
 
+def convert_irradiation(ds, orientation, tracking=None, irradiation="total",
+                        trigon_model="simple", clearsky_model="simple"):
+    """convert.py:748-767"""
+    sp_ = solar_position(ds)
+    surf = surface_orientation(ds, sp_, orientation, tracking)
+    return tilted_irradiation(ds, sp_, surf, trigon_model=trigon_model,
+                              clearsky_model=clearsky_model, tracking=tracking,
+                              irradiation=irradiation)
+
+
+def convert_solar_thermal(ds, orientation, trigon_model, clearsky_model, c0, c1, t_store):
+    """convert.py:550-573"""
+    t_store = t_store + 273.15
+    sp_ = solar_position(ds)
+    surf = surface_orientation(ds, sp_, orientation)
+    irr = tilted_irradiation(ds, sp_, surf, trigon_model, clearsky_model)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        eta = c0 - c1 * _fillna((t_store - ds["temperature"]) / _where(irr, irr != 0), 0)
+    output = irr * eta
+    return np.where(output > 0.0, output, 0.0)
+
+
+# --------------------------------------------------------------------------
+# convert.py:292-401 temperature family, COP; 475-546 cooling demand; 1028-1034 runoff
+# --------------------------------------------------------------------------
+
+
+def convert_temperature(ds):
+    """convert.py:292-298"""
+    return ds["temperature"] - 273.15
+
+
+def convert_soil_temperature(ds):
+    """convert.py:306-316 (NaN over sea -> 0 so it does not contribute)"""
+    return _fillna(ds["soil temperature"] - 273.15, 0.0)
+
+
+def convert_dewpoint_temperature(ds):
+    """convert.py:324-329"""
+    return ds["dewpoint temperature"] - 273.15
+
+
+def convert_coefficient_of_performance(ds, source, sink_T, c0, c1, c2):
+    """convert.py:338-366"""
+    assert source in ["air", "soil"]
+    if source == "air":
+        source_T = convert_temperature(ds)
+        c0 = 6.81 if c0 is None else c0
+        c1 = -0.121 if c1 is None else c1
+        c2 = 0.000630 if c2 is None else c2
+    else:
+        source_T = convert_soil_temperature(ds)
+        c0 = 8.77 if c0 is None else c0
+        c1 = -0.150 if c1 is None else c1
+        c2 = 0.000734 if c2 is None else c2
+    delta_T = sink_T - source_T
+    return c0 + c1 * delta_T + c2 * delta_T**2
+
+
+def convert_cooling_demand(ds, threshold, a, constant, hour_shift):
+    """convert.py:475-491.  Returns (values (days,ny,nx), day labels)."""
+    T = ds["temperature"]
+    labels, gid = day_bins(ds["time"], hour_shift)
+    nd = len(labels)
+    out = np.full((nd,) + T.shape[1:], np.nan, dtype=T.dtype)
+    for d in range(nd):
+        sel = T[gid == d]
+        if sel.shape[0]:
+            with np.errstate(invalid="ignore"):
+                out[d] = np.nanmean(sel, axis=0)
+    threshold = threshold + 273.15
+    cool = a * (out - threshold)
+    cool = np.where(np.isnan(cool), np.nan, np.maximum(cool, 0.0))
+    return constant + cool, labels
+
+
+def convert_runoff(ds, weight_with_height=True):
+    """convert.py:1028-1034"""
+    runoff = ds["runoff"]
+    if weight_with_height:
+        runoff = runoff * ds["height"]
+    return runoff
+
+
 # --------------------------------------------------------------------------
 # wind.py + convert.py:634-662
 # --------------------------------------------------------------------------
@@ -654,7 +738,7 @@ def convert_and_aggregate(
         return r[0] if isinstance(r, tuple) else r
 
     nt = len(ds["time"])
-    if chunk is None or convert_func is convert_heat_demand:
+    if chunk is None or convert_func in (convert_heat_demand, convert_cooling_demand):
         slabs = [slice(0, nt)]
     else:
         slabs = [slice(i, min(i + chunk, nt)) for i in range(0, nt, chunk)]

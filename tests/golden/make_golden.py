@@ -49,7 +49,7 @@ MockCutout.convert_and_aggregate = conv.convert_and_aggregate  # bound as in cut
 
 
 def ref_dataset(fields, time, x, y):
-    return xr_shim.Dataset({k: (("time", "y", "x"), v) for k, v in fields.items()},
+    return xr_shim.Dataset({k: ((("time", "y", "x") if v.ndim == 3 else ("y", "x")), v) for k, v in fields.items()},
                            coords=dict(time=time, x=x, y=y, lon=x, lat=y), attrs={"module": "era5"})
 
 
@@ -69,7 +69,7 @@ def values_tb(res):
 def main():
     nx, ny, nt, nbus = 14, 9, 54, 5
     base = syn.make_dataset(nx, ny, nt, x0=-8.0, y0=-30.0, dx=1.5, dy=7.5, start="2013-03-09 05:00",
-                            extra=("wnd_shear_exp", "humidity"))
+                            extra=("wnd_shear_exp", "humidity", "soil temperature", "dewpoint temperature", "runoff"))
     x, y, time = base.coords["x"], base.coords["y"], base.coords["time"]
     F = {k: np.asarray(base.raw(k)) for k in base.keys()}
     m = syn.make_shapes(nx, ny, nbus)
@@ -164,6 +164,37 @@ def main():
         run(f"heat|{hs}", conv.heat_demand, ds_t, threshold=17.0, a=1.3, constant=0.2, hour_shift=hs,
             matrix=m, aggregate_time=None)
     run("heat|cells", conv.heat_demand, ds_t, aggregate_time=None)
+
+    # ---- next-row converters on the same path
+    for kind in ("total", "direct", "diffuse", "ground"):
+        run(f"irradiation|{kind}|simple", conv.irradiation, ds_pv, orientation="latitude_optimal",
+            irradiation=kind, matrix=m, aggregate_time=None)
+    run("irradiation|total|other", conv.irradiation, ds_pv, orientation={"slope": 35.0, "azimuth": 160.0},
+        irradiation="total", trigon_model="other", matrix=m, aggregate_time=None)
+    run("irradiation|diffuse|other", conv.irradiation, ds_pv, orientation={"slope": 35.0, "azimuth": 160.0},
+        irradiation="diffuse", trigon_model="other", matrix=m, aggregate_time=None)
+    run("irradiation|total|horizontal", conv.irradiation, ds_pv, orientation={"slope": 0.0, "azimuth": 180.0},
+        irradiation="total", tracking="horizontal", matrix=m, aggregate_time=None)
+    run("irradiation|cells", conv.irradiation, ds_pv, orientation="latitude_optimal", aggregate_time=None)
+    run("solar_thermal|default", conv.solar_thermal, ds_pv, matrix=m, aggregate_time=None)
+    run("solar_thermal|latopt_c", conv.solar_thermal, ds_pv, orientation="latitude_optimal", c0=0.7, c1=2.5,
+        t_store=60.0, matrix=m, aggregate_time=None)
+    ds_tmp = ref_dataset({k: F[k] for k in ("temperature", "soil temperature", "dewpoint temperature")}, time, x, y)
+    run("temperature", conv.temperature, ds_tmp, matrix=m, aggregate_time=None)
+    run("soil_temperature", conv.soil_temperature, ds_tmp, matrix=m, aggregate_time=None)
+    run("dewpoint_temperature", conv.dewpoint_temperature, ds_tmp, matrix=m, aggregate_time=None)
+    run("temperature|cells_mean", conv.temperature, ds_tmp, aggregate_time="mean")
+    run("cop|air", conv.coefficient_of_performance, ds_tmp, matrix=m, aggregate_time=None)
+    run("cop|soil", conv.coefficient_of_performance, ds_tmp, source="soil", sink_T=45.0, matrix=m,
+        aggregate_time=None)
+    run("cop|air_custom", conv.coefficient_of_performance, ds_tmp, sink_T=35.0, c0=7.0, c1=-0.1, c2=0.0005,
+        matrix=m, aggregate_time=None)
+    for hs in (0.0, 3.0):
+        run(f"cooling|{hs}", conv.cooling_demand, ds_t, threshold=5.0, a=1.7, constant=0.3, hour_shift=hs,
+            matrix=m, aggregate_time=None)
+    ds_ro = ref_dataset({"runoff": F["runoff"], "height": F["height"]}, time, x, y)
+    run("runoff|height", conv.runoff, ds_ro, matrix=m, aggregate_time=None)
+    run("runoff|plain", conv.runoff, ds_ro, weight_with_height=False, matrix=m, aggregate_time=None)
 
     out["cases"] = np.array(cases)
     path = os.path.join(HERE, "reference_outputs.npz")

@@ -223,6 +223,105 @@ def test_heat_demand(ds_full, shapes, hour_shift):
     assert list(pd.DatetimeIndex(res.coords["time"])) == list(labels)
 
 
+# ------------------------------------------------------------------ further converters
+
+
+@pytest.fixture(scope="module")
+def ds_more():
+    return syn.make_dataset(44, 26, 60, x0=-6.0, y0=-15.0, dx=0.75, dy=2.0,
+                            extra=("soil temperature", "dewpoint temperature", "runoff"))
+
+
+@pytest.fixture(scope="module")
+def shapes_more():
+    return syn.make_shapes(44, 26, 11)
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("total", {}), ("direct", {}), ("diffuse", {}), ("ground", {}),
+    ("total", dict(trigon_model="other")), ("diffuse", dict(trigon_model="other")),
+    ("total", dict(tracking="horizontal")), ("direct", dict(tracking="tilted_horizontal")),
+    ("total", dict(tracking="dual")),
+])
+def test_irradiation(ds_more, shapes_more, kind, kw):
+    o = {"slope": 30.0, "azimuth": 170.0}
+    res = ab.Cutout(data=ds_more).irradiation(o, irradiation=kind, matrix=shapes_more, aggregate_time=None, **kw)
+    want = O.convert_and_aggregate(oracle_ds(ds_more), O.convert_irradiation, matrix=shapes_more,
+                                   aggregate_time=None, orientation=O.get_orientation(o), irradiation=kind,
+                                   clearsky_model=None, **kw)
+    assert_parity(bt(res), want, cap_of(shapes_more) * 1000.0, what=f"irradiation {kind} {kw}")
+    assert want.sum() > 0
+
+
+def test_solar_thermal(ds_more, shapes_more):
+    c = ab.Cutout(data=ds_more)
+    res = c.solar_thermal(matrix=shapes_more, aggregate_time=None)
+    want = O.convert_and_aggregate(
+        oracle_ds(ds_more), O.convert_solar_thermal, matrix=shapes_more, aggregate_time=None,
+        orientation=O.get_orientation({"slope": 45.0, "azimuth": 180.0}), trigon_model="simple",
+        clearsky_model="simple", c0=0.8, c1=3.0, t_store=80.0)
+    assert_parity(bt(res), want, cap_of(shapes_more) * 1000.0, what="solar thermal")
+    assert want.sum() > 0
+    res = c.solar_thermal("latitude_optimal", c0=0.7, c1=2.0, t_store=40.0, aggregate_time="sum")
+    want = O.convert_solar_thermal(oracle_ds(ds_more), O.get_orientation("latitude_optimal"), "simple", "simple",
+                                   0.7, 2.0, 40.0).sum(0)
+    assert_parity(res.values, want, 60 * 1000.0, what="solar thermal cells sum")
+
+
+def test_temperature_family_and_cop(ds_more, shapes_more):
+    c = ab.Cutout(data=ds_more)
+    od = oracle_ds(ds_more)
+    capk = cap_of(shapes_more) * 300.0
+    for meth, fn in (("temperature", O.convert_temperature), ("soil_temperature", O.convert_soil_temperature),
+                     ("dewpoint_temperature", O.convert_dewpoint_temperature)):
+        res = getattr(c, meth)(matrix=shapes_more, aggregate_time=None)
+        want = O.convert_and_aggregate(od, fn, matrix=shapes_more, aggregate_time=None)
+        assert not np.isnan(want).any() or meth != "soil_temperature"
+        assert_parity(bt(res), want, capk, what=meth)
+    assert_parity(c.temperature(aggregate_time="mean").values, O.convert_temperature(od).mean(0), 300.0,
+                  what="temperature mean")
+    assert_parity(c.to_device().soil_temperature(aggregate_time=None).values, O.convert_soil_temperature(od),
+                  300.0, what="soil cells")
+    for args in (dict(), dict(source="soil", sink_T=45.0), dict(sink_T=35.0, c0=7.0, c1=-0.1, c2=0.0005)):
+        res = c.coefficient_of_performance(matrix=shapes_more, aggregate_time=None, **args)
+        full = dict(dict(source="air", sink_T=55.0, c0=None, c1=None, c2=None), **args)
+        want = O.convert_and_aggregate(od, O.convert_coefficient_of_performance, matrix=shapes_more,
+                                       aggregate_time=None, **full)
+        assert_parity(bt(res), want, cap_of(shapes_more) * 10.0, what=f"cop {args}")
+    with pytest.raises(AssertionError):
+        c.coefficient_of_performance(source="water", aggregate_time="sum")
+
+
+@pytest.mark.parametrize("hour_shift", [0.0, 3.0])
+def test_cooling_demand(ds_more, shapes_more, hour_shift):
+    res = ab.Cutout(data=ds_more).cooling_demand(threshold=5.0, a=1.7, constant=0.3, hour_shift=hour_shift,
+                                                 matrix=shapes_more, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds_more), O.convert_cooling_demand, matrix=shapes_more,
+                                   aggregate_time=None, threshold=5.0, a=1.7, constant=0.3,
+                                   hour_shift=hour_shift)
+    assert_parity(bt(res), want, cap_of(shapes_more) * 50.0, what="cooling")
+    assert want.sum() > 0
+
+
+def test_runoff(ds_more, shapes_more):
+    c = ab.Cutout(data=ds_more)
+    od = oracle_ds(ds_more)
+    idx = pd.Index([f"c{i}" for i in range(11)], name="countries")
+    for wh in (True, False):
+        res = c.runoff(matrix=shapes_more, index=idx, aggregate_time=None, weight_with_height=wh)
+        want = O.convert_and_aggregate(od, O.convert_runoff, matrix=shapes_more, aggregate_time=None,
+                                       weight_with_height=wh)
+        scale = np.abs(want).max(0)
+        assert_parity(bt(res), want, scale * 10, what=f"runoff height={wh}")
+    # post-processing of convert.py:1044-1058: rolling mean (min_periods=1) and lower-quantile cut
+    sm = c.runoff(matrix=shapes_more, index=idx, aggregate_time=None, smooth=5, lower_threshold_quantile=0.1)
+    base = O.convert_and_aggregate(od, O.convert_runoff, matrix=shapes_more, aggregate_time=None)
+    roll = pd.DataFrame(base).rolling(5, min_periods=1).mean().values
+    thr = pd.Series(roll.T.ravel()).quantile(0.1)
+    want = np.where(roll >= thr, roll, 0.0)
+    np.testing.assert_allclose(bt(sm), want, rtol=2e-4, atol=np.abs(want).max() * 1e-5)
+
+
 # ------------------------------------------------------------------ orchestration semantics
 
 
@@ -404,3 +503,85 @@ def test_properties_at_scale():
     cube = c.pv("CSi", "latitude_optimal", aggregate_time=None).values.reshape(nt, -1).astype(np.float64)
     np.testing.assert_allclose(r1, (m @ cube.T).T, rtol=5e-5, atol=1e-4)
     assert (cube >= 0).all() and not np.isnan(cube).any() and cube.max() < 1.2
+
+
+# ------------------------------------------------------------------ BASELINE.json configs
+
+
+def test_config0_wind_50x50x24_one_shape_full_parity():
+    """BASELINE configs[0]: 50x50x24 cutout, convert_wind with 1 shape (the reference's
+    own CPU-runnable plumbing case) -- full parity against the oracle."""
+    ds = syn.make_dataset(50, 50, 24, kinds=("wind",))
+    m = syn.make_shapes(50, 50, 1)
+    res = ab.Cutout(data=ds).wind("Vestas_V112_3MW", matrix=m, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds), O.convert_wind, matrix=m, aggregate_time=None,
+                                   turbine=ab.get_windturbineconfig("Vestas_V112_3MW"))
+    assert_parity(bt(res), want, cap_of(m), what="config 0")
+
+
+def _device_cutout(nx, ny, nt, x0, y0, t_skip=0):
+    import torch
+
+    dev = torch.device("cuda", 0)
+    x, y = syn.make_coords(nx, ny, x0, y0)
+    tm = syn.make_time(nt + t_skip)[t_skip:]
+    f = syn.make_pv_fields_device(tm, x, y, dev, seed=3)
+    f["wnd100m"] = (f["temperature"] - 255.0) * 0.5
+    f["roughness"] = f["albedo"] * 0.5 + 1e-3
+    ds = ab.Dataset(f, coords=dict(time=tm, x=x, y=y, lon=x, lat=y))
+    return ab.Cutout(data=ds), f
+
+
+def test_config1_pv_200x200x8760_full_size_properties():
+    """BASELINE configs[1] at FULL size (3.5e8 cell-timesteps): size-independent
+    properties instead of an oracle pass."""
+    import torch
+
+    nx, ny, nt, nbus = 200, 200, 8760, 100
+    c, f = _device_cutout(nx, ny, nt, 0.0, 30.0)
+    m = syn.make_shapes(nx, ny, nbus)
+    kw = dict(panel="CSi", orientation="latitude_optimal", aggregate_time=None)
+    r = bt(c.pv(matrix=m, **kw))
+    assert r.shape == (nt, nbus) and not np.isnan(r).any() and (r >= 0).all()
+    # (a) border weights sum to 1 per cell -> buses partition the all-cells bus
+    allc = bt(c.pv(matrix=sp.csr_matrix(np.ones((1, nx * ny))), **kw))[:, 0]
+    np.testing.assert_allclose(r.sum(1), allc, rtol=1e-4, atol=1e-2)
+    # (b) linearity in the weights
+    np.testing.assert_allclose(bt(c.pv(matrix=m * 0.25, **kw)), 0.25 * r, rtol=1e-5, atol=1e-6)
+    # (c) any time slab equals the same rows of the whole (slab offsets into the almanac)
+    sub = ab.Cutout(data=ab.Dataset({k: v[4000:4500] for k, v in f.items()},
+                                    coords=dict(time=c.data.coords["time"][4000:4500], x=c.data.coords["x"],
+                                                y=c.data.coords["y"], lon=c.data.coords["x"], lat=c.data.coords["y"])))
+    np.testing.assert_allclose(bt(sub.pv(matrix=m, **kw)), r[4000:4500], rtol=2e-5, atol=1e-6)
+    # (d) fused == per-cell cube reduced on the host, and the oracle on a 3-step sample
+    cube = sub.pv("CSi", "latitude_optimal", aggregate_time=None).values.reshape(500, -1).astype(np.float64)
+    np.testing.assert_allclose(r[4000:4500], (m @ cube.T).T, rtol=5e-5, atol=1e-4)
+    od = {k: v[4200:4203].cpu().numpy() for k, v in f.items() if k not in ("wnd100m", "roughness")}
+    od.update(time=c.data.coords["time"][4200:4203], lon=c.data.coords["x"], lat=c.data.coords["y"])
+    want = O.convert_and_aggregate(od, O.convert_pv, matrix=m, aggregate_time=None,
+                                   panel=ab.get_solarpanelconfig("CSi"), orientation=O.get_orientation("latitude_optimal"))
+    assert_parity(r[4200:4203], want, cap_of(m), what="config 1 sample vs oracle")
+    # night rows are exactly zero somewhere in the year
+    assert (r == 0).any() and r.max() > 0
+
+
+def test_config2_3_wind_heat_1440x720_3000_shapes_properties():
+    """BASELINE configs[2,3] at full spatial size (1440x720 -> 3000 shapes), 240 steps."""
+    nx, ny, nt, nbus = 1440, 720, 240, 3000
+    c, f = _device_cutout(nx, ny, nt, -180.0, -90.0, t_skip=24 * 100)
+    m = syn.make_shapes(nx, ny, nbus)
+    ones = sp.csr_matrix(np.ones((1, nx * ny)))
+    w = bt(c.wind("Vestas_V112_3MW", matrix=m, aggregate_time=None))
+    assert w.shape == (nt, nbus) and not np.isnan(w).any()
+    np.testing.assert_allclose(w.sum(1), bt(c.wind("Vestas_V112_3MW", matrix=ones, aggregate_time=None))[:, 0],
+                               rtol=1e-4)
+    cap = cap_of(m)
+    assert (w <= cap[None, :] * (1 + 1e-5)).all() and (w >= 0).all()  # capacity factor in [0, 1]
+    h = bt(c.heat_demand(matrix=m, aggregate_time=None))
+    assert h.shape == (10, nbus)
+    np.testing.assert_allclose(h.sum(1), bt(c.heat_demand(matrix=ones, aggregate_time=None))[:, 0], rtol=1e-4)
+    # oracle on one day for 5 buses' worth of cells is too slow at this size: check the
+    # daily-mean identity instead: a=1, constant=0, huge threshold => thr+273.15 - mean(T)
+    hh = bt(c.heat_demand(threshold=1000.0, matrix=ones, aggregate_time=None))[:, 0]
+    tmean = f["temperature"].reshape(10, 24, -1).double().mean(1).sum(1).cpu().numpy()
+    np.testing.assert_allclose(hh, (1273.15 * nx * ny - tmean), rtol=1e-5)
