@@ -197,6 +197,7 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
     case 2: ATL_LAUNCH_FUSED(2, 6); break;
     case 3: ATL_LAUNCH_FUSED(4, 6); break;
     case 4: ATL_LAUNCH_FUSED(4, 8); break;
+    case 5: ATL_LAUNCH_FUSED(2, 4); break;
     default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks); break;
   }
 #undef ATL_LAUNCH_FUSED

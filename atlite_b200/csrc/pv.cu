@@ -259,11 +259,15 @@ struct PvPhys {
         diffuse_t = fmaf(A, Rb, (1.f - A) * fmaf(0.5f, cslope, 0.5f) * fmaf(f, hd3, 1.f)) * diffuse;
         diffuse_t = fmaxf(diffuse_t, 0.f);  // clip(min=0).fillna(0): fmaxf drops NaN
       }
-      float total = direct_t + diffuse_t + ground_t;
       const int out = output();
-      if (out == ATL_OUT_DIRECT) total = direct_t;         // pv/irradiation.py:238-245
+      float total;
+      if (out == ATL_OUT_DIRECT) total = direct_t;  // pv/irradiation.py:238-245
       else if (out == ATL_OUT_DIFFUSE) total = diffuse_t;
       else if (out == ATL_OUT_GROUND) total = ground_t;
+      else if (trigon() == ATL_TRIGON_SIMPLE)  // one FMA chain on the hot path
+        total = fmaf(Rb, direct, fmaf(fmaf(0.5f, cslope, 0.5f), diffuse, ground_t));
+      else
+        total = fmaf(Rb, direct, diffuse_t) + ground_t;
       // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
       // stored mode compares the stored altitude itself, as the reference does
       const bool low = (solar_src() == ATL_SOLAR_COMPUTED) ? (sinalt < sin_thr)
