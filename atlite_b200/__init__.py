@@ -6,6 +6,7 @@ hand-written sm_100a CUDA kernels in ``libatlite_b200.so``.
 """
 
 from . import resource
+from ._lib import set_deterministic
 from .convert import (
     coefficient_of_performance,
     convert_and_aggregate,
@@ -48,5 +49,5 @@ __all__ = [
     "Cutout", "Dataset", "DataArray", "convert_and_aggregate", "convert_pv", "convert_wind",
     "convert_heat_demand", "pv", "wind", "heat_demand", "get_orientation",
     "get_windturbineconfig", "get_solarpanelconfig", "windturbine_smooth", "windturbines",
-    "solarpanels", "resource",
+    "solarpanels", "resource", "set_deterministic",
 ]

@@ -139,6 +139,7 @@ _SIGNATURES = {
     "atl_last_error": (C.c_char_p, []),
     "atl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "atl_launch_count": (C.c_int64, []),
+    "atl_set_deterministic": (C.c_int, [C.c_int]),
     "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "atl_plan_tiling_host": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(PlanInfo), _P, _P, _P, C.c_int64]),
@@ -203,6 +204,11 @@ def check(rc):
     if rc != ATL_OK:
         msg = load().atl_last_error()
         raise AtlError(f"libatlite_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def set_deterministic(on=True):
+    """Bitwise-repeatable fused reductions (fixed summation order); returns the previous setting."""
+    return bool(load().atl_set_deterministic(1 if on else 0))
 
 
 def launch_count():

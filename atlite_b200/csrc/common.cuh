@@ -308,6 +308,10 @@ struct AtlPlan {
   int32_t* d_slot_row = nullptr;
   float4* d_slot_w4 = nullptr;
   int32_t* d_active = nullptr;
+  // deterministic mode: identity slot index + (bus -> slots) lists
+  int32_t* d_slot_ident = nullptr;
+  int32_t* d_row_slot_ptr = nullptr;
+  int32_t* d_row_slots = nullptr;
   // CSR copy for the two-pass fallback / generic SpMM
   int64_t* d_indptr = nullptr;
   int32_t* d_indices = nullptr;
@@ -320,6 +324,15 @@ struct AtlPlan {
     p.active_tiles = d_active;
     p.n_active = n_active;
     p.n_bus = n_bus;
+    return p;
+  }
+  // Deterministic mode: every (slot, step) partial goes to its own address
+  // (exactly one writer -> the float atomics become order-independent); a
+  // second kernel sums each bus's slots in a fixed order.
+  atl::PlanDev dev_partial() const {
+    atl::PlanDev p = dev();
+    p.slot_row = d_slot_ident;
+    p.n_bus = (int32_t)n_slots;
     return p;
   }
 };

@@ -150,6 +150,7 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   ATL_CUDA(cudaSetDevice(op->device));
   PlanDev pd{};
   int gx;
+  float* det_acc = nullptr;
   if (mode == 0) {
     ATL_REQUIRE(plan, "NULL plan");
     ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
@@ -159,6 +160,11 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
       if (plan->n_active == 0) return ATL_OK;
       pd = plan->dev();
       gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+      if (deterministic()) {  // see launch_fused: one writer per (slot, day), fixed-order gather
+        ATL_CUDA(cudaMallocAsync((void**)&det_acc, (size_t)n_days * plan->n_slots * sizeof(float), st));
+        ATL_CUDA(cudaMemsetAsync(det_acc, 0, (size_t)n_days * plan->n_slots * sizeof(float), st));
+        pd = plan->dev_partial();
+      }
     } else {
       // two-pass fallback: per-cell daily values, then CSR gather
       ATL_REQUIRE(day_start_host, "two-pass fallback needs the host day table");
@@ -204,14 +210,14 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   }
   if (vec) {
     if (mode == 0)
-      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, det_acc ? det_acc : out, (int)n_days, db);
     else if (mode == 1)
       k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
     else
       k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
   } else {
     if (mode == 0)
-      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, det_acc ? det_acc : out, (int)n_days, db);
     else if (mode == 1)
       k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
     else
@@ -219,6 +225,11 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   }
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
+  if (det_acc) {
+    int rc = launch_gather_slots(plan, det_acc, n_days, out, st);
+    cudaFreeAsync(det_acc, st);
+    return rc;
+  }
   return ATL_OK;
 }
 

@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 4)
   if (MODE == 1) atomic_add4(out, gd, g, acc);
 }
 
+// Deterministic reduce mode (atl_set_deterministic): bitwise-repeatable results.
+bool deterministic();
+
 // Generic CSR gather SpMM: out[t, row] = sum_k val[k] * dense[t, col[k]]
 // (aggregate.py:24-32 on an already materialised field).  One warp per
 // (row, t); used for plans that do not tile well and as second pass of the
@@ -141,6 +144,12 @@ struct Tuning {
   int tb = 0;
 };
 const Tuning& tuning();
+
+__global__ void k_gather_slots(const float* __restrict__ partial, const int32_t* __restrict__ row_slot_ptr,
+                               const int32_t* __restrict__ row_slots, float* __restrict__ out,
+                               int n_bus, int64_t n_slots, int nt);
+int launch_gather_slots(const AtlPlan* plan, const float* partial, int64_t nt, float* out,
+                        cudaStream_t st);
 
 inline int pick_tb(int n_cta_x, int64_t nt) {
   // time steps per CTA: aim for ~24 CTAs per resident slot (148 SMs x 5 CTAs) so
@@ -163,7 +172,8 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
   if (t_end <= t_begin) return ATL_OK;
   const int n_tiles = gd.n_tx * gd.n_ty;
   const int gx = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  const int tb = pick_tb(gx, t_end - t_begin);
+  // deterministic time sums: one time block, so every cell receives exactly one add
+  const int tb = (timesum && deterministic()) ? (int)(t_end - t_begin) : pick_tb(gx, t_end - t_begin);
   const int gy = (int)((t_end - t_begin + tb - 1) / tb);
   dim3 grid(gx, gy);
   const size_t smem = Phys::kSmemFloats * sizeof(float);
@@ -182,16 +192,26 @@ int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* 
 // Fused path of one slab.  `Phys` must use the plan's lane layout.
 template <class Phys>
 int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, cudaStream_t st) {
-  ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * plan->n_bus * sizeof(float), st));
-  if (plan->n_active == 0) return ATL_OK;
+  const bool det = deterministic() && plan->n_slots > 0;
+  float* acc = out;  // where the per-(slot, step) partial sums are accumulated
+  PlanDev pd = plan->dev();
+  if (det) {
+    ATL_CUDA(cudaMallocAsync((void**)&acc, (size_t)nt * plan->n_slots * sizeof(float), st));
+    pd = plan->dev_partial();
+  }
+  ATL_CUDA(cudaMemsetAsync(acc, 0, (size_t)nt * pd.n_bus * sizeof(float), st));
+  if (plan->n_active == 0) {
+    if (det) ATL_CUDA(cudaFreeAsync(acc, st));
+    if (det) ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * plan->n_bus * sizeof(float), st));
+    return ATL_OK;
+  }
   const int gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   const int tb = tuning().tb > 0 ? tuning().tb : pick_tb(gx, nt);
   dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
   const size_t smem = Phys::kSmemFloats * sizeof(float);
   const GridDev gd = plan->grid;
-  const PlanDev pd = plan->dev();
 #define ATL_LAUNCH_FUSED(B, MINB) \
-  k_fused_reduce<Phys, B, MINB><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, out, (int)nt, tb)
+  k_fused_reduce<Phys, B, MINB><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb)
   switch (tuning().variant) {  // experiments; 0 = the functor's own choice
     case 1: ATL_LAUNCH_FUSED(1, 8); break;
     case 2: ATL_LAUNCH_FUSED(2, 6); break;
@@ -203,6 +223,11 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
 #undef ATL_LAUNCH_FUSED
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
+  if (det) {
+    int rc = launch_gather_slots(plan, acc, nt, out, st);
+    cudaFreeAsync(acc, st);
+    return rc;
+  }
   return ATL_OK;
 }
 

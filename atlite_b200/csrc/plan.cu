@@ -19,6 +19,45 @@ namespace atl {
 static thread_local std::string g_err;
 int64_t g_launches = 0;
 
+static bool g_deterministic = [] {
+  const char* v = getenv("ATL_DETERMINISTIC");
+  return v && atoi(v) != 0;
+}();
+bool deterministic() { return g_deterministic; }
+
+// out[t, bus] = sum of the bus's slot partials, always in the same order.
+__global__ void k_gather_slots(const float* __restrict__ partial, const int32_t* __restrict__ row_slot_ptr,
+                               const int32_t* __restrict__ row_slots, float* __restrict__ out,
+                               int n_bus, int64_t n_slots, int nt) {
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y * (blockDim.x >> 5) + warp;
+  if (t >= nt) return;
+  const int b = row_slot_ptr[row], e = row_slot_ptr[row + 1];
+  const float* p = partial + (size_t)t * n_slots;
+  float acc = 0.f;
+  for (int k = b + lane; k < e; k += 32) acc += p[row_slots[k]];
+  acc = warp_sum(acc);
+  if (lane == 0) out[(size_t)t * n_bus + row] = acc;
+}
+
+int launch_gather_slots(const AtlPlan* plan, const float* partial, int64_t nt, float* out,
+                        cudaStream_t st) {
+  if (nt <= 0 || plan->n_bus == 0) return ATL_OK;
+  const int wpb = 8;
+  for (int64_t t = 0; t < nt; t += 65535LL * wpb) {
+    const int64_t n = std::min<int64_t>(nt - t, 65535LL * wpb);
+    dim3 grid(plan->n_bus, (unsigned)((n + wpb - 1) / wpb));
+    k_gather_slots<<<grid, 32 * wpb, 0, st>>>(partial + (size_t)t * plan->n_slots,
+                                              plan->d_row_slot_ptr, plan->d_row_slots,
+                                              out + (size_t)t * plan->n_bus, plan->n_bus,
+                                              plan->n_slots, (int)n);
+    ++g_launches;
+    ATL_CUDA(cudaGetLastError());
+  }
+  return ATL_OK;
+}
+
 const Tuning& tuning() {
   static Tuning t = [] {
     Tuning x;
@@ -97,6 +136,11 @@ using namespace atl;
 extern "C" {
 
 int atl_abi_version(void) { return ATL_ABI_VERSION; }
+int atl_set_deterministic(int on) {
+  const int prev = g_deterministic ? 1 : 0;
+  g_deterministic = on != 0;
+  return prev;
+}
 const char* atl_last_error(void) { return g_err.c_str(); }
 int64_t atl_launch_count(void) { return g_launches; }
 
@@ -286,6 +330,23 @@ int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
     PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(T.active.size(), 1) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_active, T.active.data(), T.active.size() * 4,
                          cudaMemcpyHostToDevice));
+    // deterministic mode: identity slot index and the slots of every bus (ascending tile)
+    std::vector<int32_t> ident((size_t)T.n_slots), rsp((size_t)n_bus + 1, 0), rs((size_t)T.n_slots);
+    for (int64_t s = 0; s < T.n_slots; ++s) {
+      ident[(size_t)s] = (int32_t)s;
+      rsp[(size_t)T.slot_row[(size_t)s] + 1]++;
+    }
+    for (int32_t r = 0; r < n_bus; ++r) rsp[(size_t)r + 1] += rsp[(size_t)r];
+    {
+      std::vector<int32_t> cur(rsp.begin(), rsp.end() - 1);
+      for (int64_t s = 0; s < T.n_slots; ++s) rs[(size_t)cur[(size_t)T.slot_row[(size_t)s]]++] = (int32_t)s;
+    }
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_ident, std::max<size_t>(ident.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_slot_ident, ident.data(), ident.size() * 4, cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_row_slot_ptr, rsp.size() * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_row_slot_ptr, rsp.data(), rsp.size() * 4, cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMalloc((void**)&p->d_row_slots, std::max<size_t>(rs.size(), 1) * 4));
+    PLAN_CUDA(cudaMemcpy(p->d_row_slots, rs.data(), rs.size() * 4, cudaMemcpyHostToDevice));
   }
   {
     // CSR copy (float weights) for the gather SpMM
@@ -326,6 +387,9 @@ void atl_plan_destroy(AtlPlan* p) {
   cudaFree(p->d_slot_row);
   cudaFree(p->d_slot_w4);
   cudaFree(p->d_active);
+  cudaFree(p->d_slot_ident);
+  cudaFree(p->d_row_slot_ptr);
+  cudaFree(p->d_row_slots);
   cudaFree(p->d_indptr);
   cudaFree(p->d_indices);
   cudaFree(p->d_vals);

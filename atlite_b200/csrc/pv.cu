@@ -72,6 +72,7 @@ struct PvPhys {
   struct Cell {
     float clon[NXC], slon[NXC];
     float sl[NYC], cl[NYC], cs[NYC], u[NYC], v[NYC], ss[NYC], cph[NYC], sph[NYC], hd3[NYC];
+    float e1[NYC], e2[NYC];  // u cl + cs sl,  cs cl - u sl  (fixed-panel incidence, see compute)
   };
   struct Raw {
     float toa[4], a[4], b[4], alb[4], temp[4], hum[4], salt[4], saz[4];
@@ -96,6 +97,8 @@ struct PvPhys {
       c.cph[b] = p1.x; c.sph[b] = p1.y; c.hd3[b] = p1.z;
       c.u[b] = p0.w * p1.x;  // sin(slope) cos(azimuth)
       c.v[b] = p0.w * p1.y;  // sin(slope) sin(azimuth)
+      c.e1[b] = fmaf(c.u[b], c.cl[b], c.cs[b] * c.sl[b]);
+      c.e2[b] = fmaf(c.cs[b], c.cl[b], -c.u[b] * c.sl[b]);
     }
   }
 
@@ -175,7 +178,13 @@ struct PvPhys {
       const int trk = tracking();
       if (trk == ATL_TRACK_NONE) {
         // sin b cos a cos(phi - az) + cos b sin a, with cos a cos az = X, cos a sin az = Y
-        cosinc = fmaf(c.u[b], X, fmaf(c.v[b], Y, c.cs[b] * sinalt));
+        if (solar_src() == ATL_SOLAR_COMPUTED) {
+          // u X + v Y + cs sinalt is linear in (cos h, sin h):
+          //   sd (u cl + cs sl) + cd (cs cl - u sl) cos h - v cd sin h
+          cosinc = fmaf(-(c.v[b] * cd), sh[a], fmaf(cd * c.e2[b], ch[a], sd * c.e1[b]));
+        } else {
+          cosinc = fmaf(c.u[b], X, fmaf(c.v[b], Y, c.cs[b] * sinalt));
+        }
         cslope = c.cs[b];
       } else if (trk == ATL_TRACK_VERTICAL) {
         cosinc = fmaf(c.ss[b], cosalt, c.cs[b] * sinalt);

@@ -59,6 +59,11 @@ extern "C" {
 int atl_abi_version(void);
 const char* atl_last_error(void);
 int atl_device_count(int* count_out);
+/* Deterministic reduce mode (default off, or env ATL_DETERMINISTIC=1): the fused
+ * kernels accumulate every (tile, bus) partial in a private slot and a second
+ * kernel sums each bus's slots in a fixed order -> bitwise-repeatable results at
+ * ~2 % extra traffic.  Returns the previous setting. */
+int atl_set_deterministic(int on);
 
 /* ------------------------------------------------------------------ */
 /* Aggregation plan: the (n_bus x S) CSR indicator/layout matrix       */

@@ -585,3 +585,36 @@ def test_config2_3_wind_heat_1440x720_3000_shapes_properties():
     hh = bt(c.heat_demand(threshold=1000.0, matrix=ones, aggregate_time=None))[:, 0]
     tmean = f["temperature"].reshape(10, 24, -1).double().mean(1).sum(1).cpu().numpy()
     np.testing.assert_allclose(hh, (1273.15 * nx * ny - tmean), rtol=1e-5)
+
+
+def test_deterministic_mode_is_bitwise_repeatable(ds_full, shapes):
+    """atl_set_deterministic: fixed summation order -> identical bits run to run, same parity."""
+    c = ab.Cutout(data=ds_full).to_device()
+    od = oracle_ds(ds_full)
+    prev = ab.set_deterministic(True)
+    try:
+        runs = [c.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values for _ in range(3)]
+        assert all(np.array_equal(runs[0], r) for r in runs[1:])
+        want = _oracle_pv(ds_full, shapes, dict(panel="CSi", orientation="latitude_optimal"))
+        assert_parity(runs[0].T, want, cap_of(shapes), what="deterministic pv")
+        w1 = c.wind("Vestas_V112_3MW", matrix=shapes, aggregate_time=None).values
+        w2 = c.wind("Vestas_V112_3MW", matrix=shapes, aggregate_time=None).values
+        assert np.array_equal(w1, w2)
+        h1 = c.heat_demand(matrix=shapes, aggregate_time=None).values
+        h2 = c.heat_demand(matrix=shapes, aggregate_time=None).values
+        assert np.array_equal(h1, h2)
+        want = O.convert_and_aggregate(od, O.convert_heat_demand, matrix=shapes, aggregate_time=None,
+                                       threshold=15.0, a=1.0, constant=0.0, hour_shift=0.0)
+        assert_parity(h1.T, want, cap_of(shapes) * 50.0, what="deterministic heat")
+        s1 = c.pv("CSi", "latitude_optimal", aggregate_time="sum").values
+        s2 = c.pv("CSi", "latitude_optimal", aggregate_time="sum").values
+        assert np.array_equal(s1, s2)
+        # empty plan and host-streamed path
+        e = c.wind("Vestas_V112_3MW", matrix=sp.csr_matrix((2, 70 * 45)), aggregate_time=None).values
+        assert (e == 0).all()
+        hs = ab.Cutout(data=ds_full).pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values
+        assert np.array_equal(hs, runs[0])
+    finally:
+        ab.set_deterministic(prev)
+    nd = c.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values
+    np.testing.assert_allclose(nd, runs[0], rtol=2e-5, atol=1e-6)

@@ -27,6 +27,8 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
 dev = torch.device("cuda", 0)
 if size == "small":
     nx, ny, nt, nbus, x0, y0 = 200, 200, 8760, 100, 0.0, 30.0
+elif size == "odd":  # nx % 4 != 0 -> SCALAR lane layout
+    nx, ny, nt, nbus, x0, y0 = 201, 199, 8760, 100, 0.0, 30.0
 else:
     nx, ny, nt, nbus, x0, y0 = 1440, 720, 432, 3000, -180.0, -90.0
 x, y = syn.make_coords(nx, ny, x0, y0)
