@@ -33,14 +33,14 @@ struct WindPhys {
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
-  int use_lut, n_stage;  // LUT mode: a byte table follows xcmp | seg in `curve`
+  int use_lut, n_stage;  // LUT mode: the bucket table follows xcmp | seg in `curve`
   float inv_w;
 
   struct Cell {};
   struct Raw {
     float w[4], a[4];
   };
-  static constexpr int kSmemFloats = 256 + 4 * 257 + 132;  // xcmp | seg | byte LUT (<= 513 B)
+  static constexpr int kSmemFloats = 256 + 4 * 257 + 2 * 1025 + 2;  // xcmp | seg | LUT (<= 1025 x 8 B)
   static constexpr int kBatch = 2, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
@@ -56,25 +56,25 @@ struct WindPhys {
   // evaluate segment seg[cnt].  `xcmp[j] <= x` with xcmp rounded UP to float is
   // exactly NumPy's float64 comparison, so the same segment is selected --
   // including duplicate knots (cut-out) and the clamped ends.
-  //  LUT mode (the normal case): a byte table over a uniform grid on [V0, Vn-1]
-  //  (shifted by half a bucket) gives a start count that is never too high and
-  //  at most 2 short (host-checked: <= 2 knots can lie between a bucket's lower
-  //  edge and any x mapped to it); two compares against the knot array finish
-  //  the search.  All accesses are 1- or 4-byte and conflict-free for <= 32 knots.
+  //  LUT mode (the normal case): a uniform grid on [V0, Vn-1], shifted by half a
+  //  bucket, in which every bucket holds at most ONE distinct knot value, none
+  //  within 1e-3 of a bucket edge (host-checked; else the fallback).  A bucket
+  //  stores that knot (rounded up) and the segment offsets for x below / from it
+  //  on: one 8-byte load, one compare, one 16-byte load.
   //  Fallback: branch-free binary search, the four searches in lock step.
   __device__ __forceinline__ void interp4(const float (&x)[4], float (&r)[4], const float* sm) const {
     const float* xcmp = sm;
     const float4* seg = reinterpret_cast<const float4*>(sm + NK);
     if (use_lut) {
-      const unsigned char* lo8 = reinterpret_cast<const unsigned char*>(sm + NK + 4 * (NK + 1));
+      const float2* lut = reinterpret_cast<const float2*>(sm + NK + 4 * (NK + 1));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
         const int b = __float2int_rd(fmaf(xc - x_lo, inv_w, 0.5f));
-        int cnt = lo8[b];
-        cnt += (xcmp[cnt] <= x[i]) ? 1 : 0;
-        cnt += (xcmp[cnt] <= x[i]) ? 1 : 0;
-        const float4 s = seg[cnt];  // cnt <= n_knots: xcmp is +inf-padded
+        const float2 e = lut[b];  // {knot inside the bucket (+inf if none), packed seg offsets}
+        const unsigned pk = __float_as_uint(e.y);
+        const unsigned off = (x[i] >= e.x) ? (pk >> 16) : (pk & 0xffffu);  // bytes into seg[]
+        const float4 s = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(seg) + off);
         const float y = fmaf(s.z, xc - s.x, s.y);
         r[i] = (x[i] != x[i]) ? x[i] : y;
       }
@@ -210,30 +210,46 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
     seg[4 * c + 2] = sl;
     seg[4 * c + 3] = 0.f;
   }
-  // ---- uniform-bucket start-count LUT (see interp4)
+  // ---- uniform-bucket LUT (see interp4)
   int use_lut = 0;
   float inv_w = 0.f;
   {
     const double lo = cfg->V[0], hi = cfg->V[n - 1];
-    for (int NB = 32; NB <= 512 && !use_lut && hi > lo && n <= 250; NB *= 2) {
-      const double wdt = (hi - lo) / NB, delta = 1e-3 * wdt;
-      std::vector<unsigned char> lut((size_t)NB + 1);
+    for (int NB = 32; NB <= 1024 && !use_lut && hi > lo; NB *= 2) {
+      const double wdt = (hi - lo) / NB;
+      std::vector<int> bucket_of(n);
+      std::vector<double> knot_in((size_t)NB + 1, std::nan(""));
       bool ok = true;
-      for (int b = 0; b <= NB && ok; ++b) {
-        const double e_lo = lo + (b - 0.5) * wdt - delta, e_hi = lo + (b + 0.5) * wdt + delta;
-        int start = 0, reach = 0;  // knots surely <= any x of the bucket / knots possibly <= it
-        for (int j = 0; j < n; ++j) {
-          if (cfg->V[j] < e_lo) ++start;
-          if (cfg->V[j] <= e_hi) ++reach;
+      for (int j = 0; j < n && ok; ++j) {
+        const double pos = (cfg->V[j] - lo) / wdt + 0.5;
+        const int b = (int)std::floor(pos);
+        const double frac = pos - b;
+        if (b < 0 || b > NB || frac < 1e-3 || frac > 1.0 - 1e-3) ok = false;
+        else if (!std::isnan(knot_in[b]) && knot_in[b] != cfg->V[j]) ok = false;  // 2 distinct knots
+        else {
+          knot_in[b] = cfg->V[j];
+          bucket_of[j] = b;
         }
-        if (reach - start > 2) ok = false;
-        lut[(size_t)b] = (unsigned char)start;
       }
       if (!ok) continue;
-      const size_t words = ((size_t)NB + 1 + 3) / 4;
-      const size_t base = curve.size();
-      curve.resize(base + words, 0.f);
-      std::memcpy(curve.data() + base, lut.data(), lut.size());
+      const size_t base = curve.size();  // NK + 4 (NK + 1): even, so the float2 table is 8-byte aligned
+      curve.resize(base + 2 * ((size_t)NB + 1), 0.f);
+      int c_lo = 0;  // knots in buckets < b
+      for (int b = 0; b <= NB; ++b) {
+        int c_hi = c_lo;
+        while (c_hi < n && bucket_of[c_hi] == b) ++c_hi;
+        float thr = INFINITY;
+        if (!std::isnan(knot_in[b])) {
+          thr = (float)knot_in[b];
+          if ((double)thr < knot_in[b]) thr = nextafterf(thr, INFINITY);  // round up
+        }
+        const uint32_t pk = ((uint32_t)(c_hi * 16) << 16) | (uint32_t)(c_lo * 16);
+        float pkf;
+        std::memcpy(&pkf, &pk, 4);
+        curve[base + 2 * (size_t)b] = thr;
+        curve[base + 2 * (size_t)b + 1] = pkf;
+        c_lo = c_hi;
+      }
       use_lut = 1;
       inv_w = (float)(1.0 / wdt);
     }
