@@ -12,6 +12,7 @@ from .convert import (
     convert_and_aggregate,
     convert_coefficient_of_performance,
     convert_cooling_demand,
+    convert_csp,
     convert_dewpoint_temperature,
     convert_heat_demand,
     convert_irradiation,
@@ -22,6 +23,7 @@ from .convert import (
     convert_temperature,
     convert_wind,
     cooling_demand,
+    csp,
     dewpoint_temperature,
     heat_demand,
     irradiation,
@@ -36,6 +38,8 @@ from .cutout import Cutout
 from .labelled import DataArray, Dataset
 from .orientation import get_orientation
 from .resource import (
+    cspinstallations,
+    get_cspinstallationconfig,
     get_solarpanelconfig,
     get_windturbineconfig,
     solarpanels,

@@ -26,6 +26,7 @@ SOLAR_COMPUTED, SOLAR_STORED_F32, SOLAR_STORED_F64 = 0, 1, 2
 PANEL = {"huld": 0, "bofinger": 1}
 OUTPUT = {"panel": 0, "total": 1, "direct": 2, "diffuse": 3, "ground": 4, "solar_thermal": 5}
 WIND_NONE, WIND_LOG, WIND_POWER = 0, 1, 2
+CSP_TECH = {"parabolic trough": 0, "solar tower": 1}
 
 
 class AtlError(RuntimeError):
@@ -132,6 +133,31 @@ class PointwiseConfig(C.Structure):
     ]
 
 
+class CspConfig(C.Structure):
+    _fields_ = [
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("nt", C.c_int64),
+        ("time_ns", C.c_void_p),
+        ("time_shift_ns", C.c_int64),
+        ("lon_deg", C.c_void_p),
+        ("lat_deg", C.c_void_p),
+        ("solar_src", C.c_int32),
+        ("technology", C.c_int32),
+        ("r_irradiance", C.c_double),
+        ("dni_altitude_threshold_deg", C.c_double),
+        ("n_alt", C.c_int32),
+        ("n_az", C.c_int32),
+        ("altitude_rad", C.c_void_p),
+        ("azimuth_rad", C.c_void_p),
+        ("efficiency", C.c_void_p),
+    ]
+
+
+class CspFields(C.Structure):
+    _fields_ = [("influx_direct", C.c_void_p), ("solar_altitude", C.c_void_p), ("solar_azimuth", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/atlite_b200.h
 _P = C.c_void_p
 _SIGNATURES = {
@@ -173,6 +199,13 @@ _SIGNATURES = {
     "atl_pointwise_timesum": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "atl_pointwise_reduce_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64]),
     "atl_pointwise_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
+    "atl_csp_create": (C.c_int, [C.c_int, C.POINTER(CspConfig), C.POINTER(_P)]),
+    "atl_csp_destroy": (None, [_P]),
+    "atl_csp_reduce": (C.c_int, [_P, _P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_csp_cells": (C.c_int, [_P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_csp_timesum": (C.c_int, [_P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_csp_reduce_host": (C.c_int, [_P, _P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, C.c_int64]),
+    "atl_csp_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

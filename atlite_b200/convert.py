@@ -24,7 +24,13 @@ import scipy.sparse as sp
 from . import _lib, engine
 from .labelled import HAVE_XARRAY, DataArray, is_dataarray, make_dataarray
 from .orientation import get_orientation
-from .resource import get_solarpanelconfig, get_windturbineconfig, windturbine_smooth
+from .resource import (
+    EfficiencyTable,
+    get_cspinstallationconfig,
+    get_solarpanelconfig,
+    get_windturbineconfig,
+    windturbine_smooth,
+)
 
 if HAVE_XARRAY:  # pragma: no cover
     import xarray as xr
@@ -276,6 +282,42 @@ def _runoff_spec(ds, weight_with_height=True):
     return _PointwiseSpec(ds, "runoff", cell_scale=scale, name="runoff")
 
 
+class _CspSpec(_Spec):
+    """convert_csp (convert.py:940-972)."""
+
+    name = "specific generation"
+    units = "kWh/kW_ref"
+
+    def __init__(self, ds, installation):
+        ny, nx = _grid_shape(ds)
+        self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
+        tech = installation["technology"]
+        if tech not in _lib.CSP_TECH:
+            raise ValueError(f'Unknown CSP technology option "{tech}".')
+        names = ["influx_direct"]
+        if _has(ds, "solar_azimuth") and _has(ds, "solar_altitude"):
+            dt = np.dtype(str(_raw(ds, "solar_altitude").dtype).replace("torch.", ""))
+            solar_src = _lib.SOLAR_STORED_F64 if dt == np.float64 else _lib.SOLAR_STORED_F32
+            names += ["solar_altitude", "solar_azimuth"]
+        else:
+            warnings.warn(_SOLAR_WARNING, DeprecationWarning)
+            solar_src = _lib.SOLAR_COMPUTED
+        eff = EfficiencyTable.from_any(installation["efficiency"])
+        self.fields = {n: _raw(ds, n) for n in names}
+        self.op = engine.CspOp(
+            ny=ny, nx=nx, time=self.time_labels, lon=_coord(ds, "lon").astype(np.float64),
+            lat=_coord(ds, "lat").astype(np.float64), solar_src=solar_src,
+            technology=_lib.CSP_TECH[tech], r_irradiance=installation["r_irradiance"],
+            altitude=eff.altitude, azimuth=eff.azimuth, efficiency=eff.values,
+        )
+
+    def reduce(self, plan):
+        return self.op.reduce(plan, self.fields)
+
+    def cells(self, timesum=False):
+        return self.op.cells(self._device_fields(self.fields), timesum=timesum)
+
+
 class _WindSpec(_Spec):
     name = "specific generation"
     units = "MWh/MWp"
@@ -442,6 +484,12 @@ def convert_cooling_demand(ds, threshold, a, constant, hour_shift):
     return _wrap_cells(ds, spec, spec.cells())
 
 
+def convert_csp(ds, installation):
+    """Per-cell CSP specific generation; convert.py:940-972."""
+    spec = _CspSpec(ds, installation)
+    return _wrap_cells(ds, spec, spec.cells())
+
+
 def convert_runoff(ds, weight_with_height=True):
     """Runoff (optionally weighted with height); convert.py:1028-1034."""
     spec = _runoff_spec(ds, weight_with_height)
@@ -454,7 +502,7 @@ _SPECS = {
     "convert_temperature": _temperature_spec, "convert_soil_temperature": _soil_temperature_spec,
     "convert_dewpoint_temperature": _dewpoint_temperature_spec,
     "convert_coefficient_of_performance": _cop_spec, "convert_cooling_demand": _CoolingSpec,
-    "convert_runoff": _runoff_spec,
+    "convert_runoff": _runoff_spec, "convert_csp": _CspSpec,
 }
 
 
@@ -792,6 +840,15 @@ def irradiation(cutout, orientation, irradiation="total", tracking=None, clearsk
         orientation=orientation, tracking=tracking, irradiation=irradiation,
         clearsky_model=clearsky_model, **params,
     )
+
+
+def csp(cutout, installation, technology=None, **params):
+    """CSP generation time-series from direct radiation (convert.py:975-1024)."""
+    if isinstance(installation, (str, Path)):
+        installation = get_cspinstallationconfig(installation)
+    if technology is not None:
+        installation = dict(installation, technology=technology)
+    return cutout.convert_and_aggregate(convert_func=convert_csp, installation=installation, **params)
 
 
 def runoff(cutout, smooth=None, lower_threshold_quantile=None, normalize_using_yearly=None, **params):

@@ -276,9 +276,12 @@ __device__ __forceinline__ void reduce_slots2(const float (&v0)[4], const float 
   }
   const bool hi = lane >= 16;
   float* const my_row = out_row0 + (hi ? plan.n_bus : 0);
+  // running pointers: one 64-bit add per slot instead of re-deriving the addresses
+  const float4* wp = plan.slot_w4 + (size_t)s_beg * 32 + lane;
+  const int32_t* rp = plan.slot_row + s_beg;
 #pragma unroll 1
-  for (int s = s_beg; s < s_end; ++s) {
-    const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
+  for (int n = s_end - s_beg; n > 0; --n, wp += 32, ++rp) {
+    const float4 w = __ldg(wp);
     const float p0 = fmaf(w.x, v0[0], fmaf(w.y, v0[1], fmaf(w.z, v0[2], w.w * v0[3])));
     const float p1 = fmaf(w.x, v1[0], fmaf(w.y, v1[1], fmaf(w.z, v1[2], w.w * v1[3])));
     float keep = hi ? p1 : p0;
@@ -286,7 +289,7 @@ __device__ __forceinline__ void reduce_slots2(const float (&v0)[4], const float 
     keep += __shfl_xor_sync(0xffffffffu, send, 16);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-    if ((lane & 15) == 0) atomicAdd(my_row + __ldg(plan.slot_row + s), keep);
+    if ((lane & 15) == 0) atomicAdd(my_row + __ldg(rp), keep);
   }
 }
 #endif  // __CUDACC__

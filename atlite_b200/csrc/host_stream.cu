@@ -235,6 +235,29 @@ int atl_wind_reduce_host(const AtlWindOp* op, const AtlPlan* plan, const AtlWind
                       out_host, launch);
 }
 
+int atl_csp_reduce_host(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* f,
+                        int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps) {
+  ATL_REQUIRE(op && plan && f, "NULL argument");
+  int32_t device, ny, nx, solar_src;
+  atl_csp_op_info(op, &device, &ny, &nx, &solar_src);
+  const size_t sol_elem = solar_src == ATL_SOLAR_STORED_F64 ? 8 : 4;
+  std::vector<SlabField> fields = {{(const char*)f->influx_direct, 4},
+                                   {(const char*)f->solar_altitude, sol_elem},
+                                   {(const char*)f->solar_azimuth, sol_elem}};
+  auto launch = [&](const std::vector<void*>& d, int64_t t_rel, int64_t n, float* out_dev,
+                    cudaStream_t st) {
+    AtlCspFields df;
+    df.influx_direct = (const float*)d[0];
+    df.solar_altitude = d[1];
+    df.solar_azimuth = d[2];
+    return atl_csp_reduce(op, plan, &df, t0 + t_rel, n, out_dev, (void*)st);
+  };
+  AtlPlanInfo pi;
+  atl_plan_info(plan, &pi);
+  return stream_slabs(device, fields, (int64_t)ny * nx, nt, nullptr, chunk_steps, pi.n_bus,
+                      out_host, launch);
+}
+
 int atl_pointwise_reduce_host(const AtlPointwiseOp* op, const AtlPlan* plan,
                               const float* field_host, int64_t nt, float* out_host,
                               int64_t chunk_steps) {

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "solar_host.cuh"
 
 namespace atl {
 
@@ -279,10 +280,12 @@ struct PvPhys {
         total = fmaf(Rb, direct, diffuse_t) + ground_t;
       // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
       // stored mode compares the stored altitude itself, as the reference does
+      // result.where(~(cap_alt | (direct + diffuse <= 0.01)), 0): keep iff NOT(alt < thr) AND
+      // NOT(influx <= 0.01); NaN compares false on both, exactly as in the reference
       const bool low = (solar_src() == ATL_SOLAR_COMPUTED) ? (sinalt < sin_thr)
                                                            : (r.salt[i] < alt_thr);
-      const bool masked = low || (influx_ <= 0.01f);
-      const float G = masked ? 0.f : total;
+      const bool keep_it = !low & !(influx_ <= 0.01f);
+      const float G = keep_it ? total : 0.f;
       if (out == ATL_OUT_PANEL) {
         v[i] = panel(G, r.temp[i]);
       } else if (out == ATL_OUT_SOLAR_THERMAL) {
@@ -452,40 +455,8 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   }
 
   // ---- per-time-step almanac (pv/solar_position.py:71-97), float64 on host
-  std::vector<float4> tt((size_t)std::max<int64_t>(cfg->nt, 1));
-  if (cfg->time_ns) {
-    for (int64_t i = 0; i < cfg->nt; ++i) {
-      const int64_t ns = cfg->time_ns[i] + cfg->time_shift_ns;
-      const int64_t DAY = 86400LL * 1000000000LL;
-      int64_t day = ns / DAY, rem = ns % DAY;
-      if (rem < 0) {
-        rem += DAY;
-        day -= 1;
-      }
-      const int64_t hour = rem / 3600000000000LL;
-      const int64_t minute = (rem / 60000000000LL) % 60;
-      const int64_t second = (rem / 1000000000LL) % 60;
-      const int64_t micro = (rem / 1000LL) % 1000000;
-      const int64_t nano = rem % 1000;
-      // pandas DatetimeIndex.to_julian_date: integer day count + 0.5, then + day fraction
-      const double jd = ((double)day + 2440587.5) +
-                        ((double)hour + (double)minute / 60.0 + (double)second / 3600.0 +
-                         (double)micro / 3600.0 / 1e6 + (double)nano / 3600.0 / 1e9) /
-                            24.0;
-      const double n = jd - 2451545.0;                                   // :74
-      const double L = 280.460 + 0.9856474 * n;                          // :86
-      const double gg = (357.528 + 0.9856003 * n) * D2R;                 // :87
-      const double l = (L + 1.915 * std::sin(gg) + 0.020 * std::sin(2 * gg)) * D2R;  // :88
-      const double ep = (23.439 - 4e-7 * n) * D2R;                       // :89
-      const double ra = std::atan2(std::cos(ep) * std::sin(l), std::cos(l));  // :91
-      const double lmst0 =
-          (6.697375 + ((double)hour + (double)minute / 60.0) + 0.0657098242 * n) * 15.0;  // :92
-      const double H0 = lmst0 * D2R - ra;                                // :95 (without lon)
-      const double dec = std::asin(std::sin(ep) * std::sin(l));          // :97
-      tt[(size_t)i] = make_float4((float)std::sin(dec), (float)std::cos(dec), (float)std::cos(H0),
-                                  (float)std::sin(H0));
-    }
-  }
+  std::vector<float4> tt;
+  solar_almanac(cfg->time_ns, cfg->nt, cfg->time_shift_ns, tt);
   std::vector<float2> xt((size_t)cfg->nx);
   for (int i = 0; i < cfg->nx; ++i) {
     const double lon = cfg->lon_deg[i] * D2R;

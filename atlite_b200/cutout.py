@@ -148,4 +148,5 @@ class Cutout:
     irradiation = _convert.irradiation
     wind = _convert.wind
     pv = _convert.pv
+    csp = _convert.csp
     runoff = _convert.runoff

@@ -434,3 +434,78 @@ class PointwiseOp(_Op):
             out = self._out((nt, self.ny, self.nx), f)
             _lib.check(lib.atl_pointwise_cells(self.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
         return out
+
+
+class CspOp(_Op):
+    """convert_csp (convert.py:940-972) operator."""
+
+    _destroy = "atl_csp_destroy"
+
+    def __init__(self, *, ny, nx, time, lon, lat, solar_src, technology, r_irradiance, altitude, azimuth,
+                 efficiency, time_shift="0h", dni_altitude_threshold=3.75, device=None):
+        lib = _lib.load()
+        self.device = current_device() if device is None else device
+        self.ny, self.nx = ny, nx
+        self._time = time_ns(time)
+        self._lon, self._lat = _lib.as_f64(lon), _lib.as_f64(lat)
+        self._alt, self._az, self._eff = _lib.as_f64(altitude), _lib.as_f64(azimuth), _lib.as_f64(efficiency)
+        cfg = _lib.CspConfig()
+        cfg.ny, cfg.nx, cfg.nt = ny, nx, len(self._time)
+        cfg.time_ns = _lib.ptr(self._time).value
+        cfg.time_shift_ns = int(pd.to_timedelta(time_shift).value)
+        cfg.lon_deg, cfg.lat_deg = _lib.ptr(self._lon).value, _lib.ptr(self._lat).value
+        cfg.solar_src = solar_src
+        cfg.technology = technology
+        cfg.r_irradiance = float(r_irradiance)
+        cfg.dni_altitude_threshold_deg = float(dni_altitude_threshold)
+        cfg.n_alt, cfg.n_az = len(self._alt), len(self._az)
+        cfg.altitude_rad, cfg.azimuth_rad = _lib.ptr(self._alt).value, _lib.ptr(self._az).value
+        cfg.efficiency = _lib.ptr(self._eff).value
+        h = C.c_void_p()
+        _lib.check(lib.atl_csp_create(self.device, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    def _fields(self, fields, host):
+        f = _lib.CspFields()
+        keep = []
+        for n in ("influx_direct", "solar_altitude", "solar_azimuth"):
+            a = fields.get(n)
+            if a is None:
+                setattr(f, n, None)
+            elif host:
+                a = np.ascontiguousarray(a) if (n != "influx_direct" and np.asarray(a).dtype == np.float64) else host_f32(a)
+                keep.append(a)
+                setattr(f, n, a.ctypes.data)
+            else:
+                a = a.contiguous()
+                keep.append(a)
+                setattr(f, n, a.data_ptr())
+        return f, keep
+
+    def reduce(self, plan, fields, t0=0, chunk_steps=0):
+        lib = _lib.load()
+        dev = self._all_device(fields.values())
+        first = fields["influx_direct"]
+        nt = first.shape[0]
+        f, keep = self._fields(fields, host=not dev)
+        if dev:
+            out = self._out((nt, plan.n_bus), first)
+            _lib.check(lib.atl_csp_reduce(self.handle, plan.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+            return out
+        out = np.empty((nt, plan.n_bus), dtype=np.float32)
+        _lib.check(lib.atl_csp_reduce_host(self.handle, plan.handle, C.byref(f), t0, nt, _hptr(out), chunk_steps))
+        return out
+
+    def cells(self, fields, t0=0, timesum=False):
+        lib = _lib.load()
+        first = fields["influx_direct"]
+        nt = first.shape[0]
+        f, keep = self._fields(fields, host=False)
+        torch = _torch()
+        if timesum:
+            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=first.device)
+            _lib.check(lib.atl_csp_timesum(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+        else:
+            out = self._out((nt, self.ny, self.nx), first)
+            _lib.check(lib.atl_csp_cells(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+        return out

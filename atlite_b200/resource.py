@@ -42,9 +42,11 @@ class _Registry(dict):
 
 _TURBINES = _load("turbines.json")
 _PANELS = _load("panels.json")
+_CSP = _load("csp.json")
 # registries map name -> name (the reference maps name -> yaml path)
 windturbines = _Registry({k: k for k in _TURBINES})
 solarpanels = _Registry({k: k for k in _PANELS})
+cspinstallations = _Registry({k: k for k in _CSP})
 
 
 def _read_yaml(path):
@@ -175,3 +177,57 @@ def windturbine_smooth(turbine, params=None):
             sigma,
         )
     return out
+
+
+class EfficiencyTable:
+    """Solar-field efficiency over (altitude, azimuth) in radians / p.u. -- the
+    information of the reference's ``installation["efficiency"]`` DataArray
+    (resource.py:190-220)."""
+
+    dims = ("altitude", "azimuth")
+
+    def __init__(self, altitude, azimuth, values):
+        self.altitude = np.asarray(altitude, dtype=np.float64)
+        self.azimuth = np.asarray(azimuth, dtype=np.float64)
+        self.values = np.asarray(values, dtype=np.float64)
+        if self.values.shape != (len(self.altitude), len(self.azimuth)):
+            raise ValueError("efficiency table shape does not match its coordinates")
+        if np.any(np.diff(self.altitude) <= 0) or np.any(np.diff(self.azimuth) <= 0):
+            raise ValueError("efficiency table coordinates must be strictly increasing")
+
+    @property
+    def coords(self):
+        return {"altitude": self.altitude, "azimuth": self.azimuth}
+
+    @classmethod
+    def from_any(cls, eff):
+        if isinstance(eff, cls):
+            return eff
+        # xarray.DataArray with 'altitude' / 'azimuth' coordinates in rad
+        e = eff.transpose("altitude", "azimuth")
+        return cls(np.asarray(e.coords["altitude"]), np.asarray(e.coords["azimuth"]), np.asarray(e.values))
+
+
+def get_cspinstallationconfig(installation):
+    """CSP installation name | Path to a reference-format YAML -> config dict with
+    'technology', 'r_irradiance' and 'efficiency' (an ``EfficiencyTable`` in rad / p.u.;
+    the reference converts deg -> rad and % -> p.u. the same way, resource.py:200-220)."""
+    assert isinstance(installation, (str, Path))
+    if isinstance(installation, str):
+        name = installation.replace(".yaml", "")
+        if name not in _CSP:
+            raise KeyError(name)
+        d = _CSP[name]
+        alt, az, tab = d["altitude_deg"], d["azimuth_deg"], d["efficiency_percent"]
+        config = {"technology": d["technology"], "r_irradiance": d["r_irradiance"], **d.get("meta", {})}
+    else:
+        import pandas as pd
+
+        d = _read_yaml(installation)
+        df = pd.DataFrame(d["efficiency"]).set_index(["altitude", "azimuth"])["value"].unstack("azimuth")
+        alt, az, tab = df.index.values, df.columns.values, df.values
+        config = {k: v for k, v in d.items() if k != "efficiency"}
+    config["path"] = installation
+    config["efficiency"] = EfficiencyTable(np.radians(np.asarray(alt, float)), np.radians(np.asarray(az, float)),
+                                           np.asarray(tab, float) / 1.0e2)
+    return config

@@ -19,6 +19,7 @@
  *   convert.py:550-573  convert_solar_thermal                   atl_pv_* with AtlPvConfig.output = ATL_OUT_SOLAR_THERMAL
  *   convert.py:292-366  temperature / soil / dewpoint / COP     atl_pointwise_*
  *   convert.py:1028-1034 convert_runoff                         atl_pointwise_* with cell_scale = height
+ *   convert.py:940-972  convert_csp (+ csp.py:18-58)            atl_csp_*
  *   convert.py:200-211  no-matrix branch (_aggregate_time)      *_cells, *_timesum
  *   convert.py:257-271  reduce + time aggregation               *_reduce (+ host finalisation in Python)
  *
@@ -255,6 +256,46 @@ int atl_pointwise_reduce_host(const AtlPointwiseOp* op, const AtlPlan* plan,
                               int64_t chunk_steps);
 
 /* ------------------------------------------------------------------ */
+/* CSP: solar position -> direct irradiation (horizontal | DNI) x        */
+/* efficiency(altitude, azimuth) table (convert.py:940-972, csp.py)     */
+/* ------------------------------------------------------------------ */
+enum { ATL_CSP_PARABOLIC_TROUGH = 0, ATL_CSP_SOLAR_TOWER = 1 };
+typedef struct {
+  int32_t ny, nx;
+  int64_t nt;
+  const int64_t* time_ns;      /* host, nt (needed unless the solar position is stored) */
+  int64_t time_shift_ns;
+  const double* lon_deg;       /* host, nx */
+  const double* lat_deg;       /* host, ny */
+  int32_t solar_src;           /* ATL_SOLAR_* */
+  int32_t technology;          /* ATL_CSP_* */
+  double r_irradiance;         /* W/m^2 */
+  double dni_altitude_threshold_deg; /* csp.py:18, default 3.75 */
+  int32_t n_alt, n_az;         /* efficiency table, each 2..128, product <= 8192 */
+  const double* altitude_rad;  /* host, n_alt, increasing */
+  const double* azimuth_rad;   /* host, n_az, increasing */
+  const double* efficiency;    /* host, n_alt * n_az row-major, p.u. */
+} AtlCspConfig;
+
+typedef struct {
+  const float* influx_direct;
+  const void* solar_altitude; /* float or double per solar_src, or NULL */
+  const void* solar_azimuth;
+} AtlCspFields;
+
+typedef struct AtlCspOp AtlCspOp;
+int atl_csp_create(int device, const AtlCspConfig* cfg, AtlCspOp** op_out);
+void atl_csp_destroy(AtlCspOp* op);
+int atl_csp_reduce(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* f, int64_t t0,
+                   int64_t nt, float* out_dev, void* stream);
+int atl_csp_cells(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t nt,
+                  float* out_dev, void* stream);
+int atl_csp_timesum(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t nt,
+                    float* out_dev, void* stream);
+int atl_csp_reduce_host(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* f_host,
+                        int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps);
+
+/* ------------------------------------------------------------------ */
 /* Host-buffer entry points: the call the reference-facing Python API  */
 /* makes when the cutout lives in host memory (NumPy / NetCDF).  The   */
 /* library streams time slabs through a pinned ring (H2D overlapped    */
@@ -276,6 +317,8 @@ int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny, int32_t* nx);
+int atl_csp_op_info(const AtlCspOp* op, int32_t* device, int32_t* ny, int32_t* nx,
+                    int32_t* solar_src);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" evidence). */

@@ -552,6 +552,42 @@ def convert_cooling_demand(ds, threshold, a, constant, hour_shift):
     return constant + cool, labels
 
 
+def calculate_dni(ds, solar_pos, altitude_threshold=3.75):
+    """csp.py:18-58"""
+    thr = np.radians(altitude_threshold)
+    altitude = solar_pos["altitude"]
+    altitude = _where(altitude, altitude > 0, np.nan)
+    altitude = _where(altitude, altitude > thr, thr)  # NaN > thr is False -> thr (sic, as the reference)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return ds["influx_direct"] / np.sin(altitude)
+
+
+def convert_csp(ds, installation):
+    """convert.py:940-972.  ``installation["efficiency"]``: object with .altitude, .azimuth (rad,
+    ascending) and .values (p.u.); interpolation as xarray's DataArray.interp, i.e.
+    scipy.interpolate.interpn(method="linear", bounds_error=False, fill_value=nan)."""
+    from scipy.interpolate import interpn
+
+    sp_ = solar_position(ds)
+    tech = installation["technology"]
+    if tech == "parabolic trough":
+        irradiation = ds["influx_direct"]
+    elif tech == "solar tower":
+        irradiation = calculate_dni(ds, sp_)
+    else:
+        raise ValueError(f'Unknown CSP technology option "{tech}".')
+    eff = installation["efficiency"]
+    alt, az = np.broadcast_arrays(sp_["altitude"], sp_["azimuth"])
+    xi = np.stack([np.asarray(alt, dtype=np.float64).ravel(), np.asarray(az, dtype=np.float64).ravel()], axis=-1)
+    efficiency = interpn((np.asarray(eff.altitude, float), np.asarray(eff.azimuth, float)),
+                         np.asarray(eff.values, float), xi, method="linear", bounds_error=False,
+                         fill_value=np.nan).reshape(alt.shape)
+    da = efficiency * irradiation
+    da = da / installation["r_irradiance"]
+    da = np.where(np.isnan(da), np.nan, np.minimum(da, 1.0))  # .clip(max=1.0)
+    return _fillna(da, 0.0)
+
+
 def convert_runoff(ds, weight_with_height=True):
     """convert.py:1028-1034"""
     runoff = ds["runoff"]

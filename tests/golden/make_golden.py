@@ -196,6 +196,25 @@ def main():
     run("runoff|height", conv.runoff, ds_ro, matrix=m, aggregate_time=None)
     run("runoff|plain", conv.runoff, ds_ro, weight_with_height=False, matrix=m, aggregate_time=None)
 
+    # ---- CSP (convert.py:940-1024, csp.py:18-58).  The efficiency DataArray is built as
+    # resource.py:190-220 does (deg -> rad, % -> p.u.) from the reference's own YAML.
+    import yaml
+
+    for inst_name in ("SAM_solar_tower", "SAM_parabolic_trough"):
+        cfg = yaml.safe_load(open(f"/root/reference/atlite/resources/cspinstallation/{inst_name}.yaml"))
+        df = pd.DataFrame(cfg["efficiency"]).set_index(["altitude", "azimuth"])["value"].unstack("azimuth")
+        eff = xr_shim.DataArray(df.values / 1.0e2,
+                                {"altitude": np.radians(df.index.values.astype(float)),
+                                 "azimuth": np.radians(df.columns.values.astype(float))},
+                                ("altitude", "azimuth"))
+        inst = {"technology": cfg["technology"], "r_irradiance": cfg["r_irradiance"], "efficiency": eff}
+        run(f"csp|{inst_name}", conv.csp, ds_pv, installation=dict(inst), matrix=m, aggregate_time=None)
+    run("csp|tower_as_trough", conv.csp, ds_pv, installation=dict(inst, technology="solar tower"), matrix=m,
+        aggregate_time=None)
+    run("csp|cells", conv.csp, ds_pv, installation=dict(inst), aggregate_time=None)
+    run("csp|stored_solar", conv.csp, ds_st, installation=dict(inst, technology="solar tower"), matrix=m,
+        aggregate_time=None)
+
     out["cases"] = np.array(cases)
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)

@@ -165,6 +165,7 @@ class DataArray:
     def __mul__(s, o): return s._bin(o, np.multiply)
     def __rmul__(s, o): return s._bin(o, np.multiply, True)
     def __truediv__(s, o): return s._bin(o, np.true_divide)
+    def __itruediv__(s, o): return s._bin(o, np.true_divide)
     def __rtruediv__(s, o): return s._bin(o, np.true_divide, True)
     def __pow__(s, o): return s._bin(o, np.power)
     def __rpow__(s, o): return s._bin(o, np.power, True)
@@ -186,6 +187,8 @@ class DataArray:
 
     # ---- xarray methods used on the path
     def where(self, cond, other=np.nan):
+        if callable(cond):
+            cond = cond(self)
         dims, vals, coords = _unify((self, cond, other))
         res = np.where(vals[1], vals[0], vals[2])
         return DataArray(res, {k: v for k, v in coords.items() if k in dims}, dims, self.name)
@@ -280,6 +283,24 @@ class DataArray:
     def resample(self, time=None):
         assert time == "1D"
         return _DailyResample(self)
+
+    def interp(self, **indexers):
+        """xarray's advanced (pointwise) linear interpolation: DataArray indexers that
+        share dims -> scipy.interpolate.interpn(linear, bounds_error=False, fill_value=nan),
+        which is what xarray delegates to for n-d linear interpolation."""
+        from scipy.interpolate import interpn
+
+        names = list(indexers)
+        assert set(names) == set(self.dims), "shim interp: all dims must be interpolated"
+        table = self.transpose(*names)
+        targets = [indexers[n] for n in names]
+        dims, vals, coords = _unify(targets)
+        shape = np.broadcast_shapes(*[np.shape(v) for v in vals])
+        xi = np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), shape).ravel() for v in vals], axis=-1)
+        pts = tuple(np.asarray(table._coords[n], dtype=np.float64) for n in names)
+        out = interpn(pts, np.asarray(table.values, dtype=np.float64), xi, method="linear",
+                      bounds_error=False, fill_value=np.nan).reshape(shape)
+        return DataArray(out, {k: v for k, v in coords.items() if k in dims}, dims, self.name)
 
     def isel(self, **kw):
         out = self
@@ -498,7 +519,6 @@ def install():
     pkg.__path__ = [REF]
     _module("atlite.gis", spdiag=spdiag, maybe_swap_spatial_dims=lambda ds, *a, **k: ds)
     _module("atlite.datasets", modules={})
-    _module("atlite.csp")
     _module("atlite.hydro")
     pvpkg = _module("atlite.pv")
     pvpkg.__path__ = [REF + "/pv"]
@@ -516,6 +536,7 @@ def install():
     load("atlite.wind", "wind.py")
     for m in ("solar_position", "orientation", "irradiation", "solar_panel_model"):
         load(f"atlite.pv.{m}", f"pv/{m}.py")
+    load("atlite.csp", "csp.py")
     conv = load("atlite.convert", "convert.py")
     conv._shimmed = True
     return conv

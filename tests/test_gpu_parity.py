@@ -303,6 +303,39 @@ def test_cooling_demand(ds_more, shapes_more, hour_shift):
     assert want.sum() > 0
 
 
+@pytest.mark.parametrize("inst,tech", [("SAM_solar_tower", None), ("SAM_parabolic_trough", None),
+                                       ("SAM_parabolic_trough", "solar tower"), ("lossless_installation", "solar tower")])
+def test_csp(ds_full, shapes, inst, tech):
+    c = ab.Cutout(data=ds_full)
+    res = c.csp(inst, technology=tech, matrix=shapes, aggregate_time=None)
+    cfg = ab.get_cspinstallationconfig(inst)
+    if tech is not None:
+        cfg = dict(cfg, technology=tech)
+    want = O.convert_and_aggregate(oracle_ds(ds_full), O.convert_csp, matrix=shapes, aggregate_time=None,
+                                   installation=cfg)
+    assert_parity(bt(res), want, cap_of(shapes), what=f"csp {inst} {tech}")
+    assert want.sum() > 0 and res.attrs["units"] == "MW"
+    with pytest.raises(ValueError, match="Unknown CSP technology"):
+        c.csp("lossless_installation", aggregate_time="sum")
+
+
+def test_csp_cells_and_stored_solar():
+    ds = syn.make_dataset(36, 22, 48, x0=5.0, y0=-10.0, dx=1.0, dy=2.0, kinds=("pv",))
+    cfg = ab.get_cspinstallationconfig("SAM_solar_tower")
+    got = ab.Cutout(data=ds).to_device().csp(cfg, aggregate_time=None)
+    want = O.convert_csp(oracle_ds(ds), cfg)
+    assert_parity(got.values, want, what="csp cells")
+    assert got.attrs["units"] == "kWh/kW_ref"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp_ = O.solar_position(oracle_ds(ds))
+    ds["solar_altitude"], ds["solar_azimuth"] = sp_["altitude"], sp_["azimuth"]  # float64, as ERA5 cutouts store them
+    m = syn.make_shapes(36, 22, 7)
+    got = ab.Cutout(data=ds).csp(cfg, matrix=m, aggregate_time=None)
+    want = O.convert_and_aggregate(oracle_ds(ds), O.convert_csp, matrix=m, aggregate_time=None, installation=cfg)
+    assert_parity(bt(got), want, cap_of(m), what="csp stored solar")
+
+
 def test_runoff(ds_more, shapes_more):
     c = ab.Cutout(data=ds_more)
     od = oracle_ds(ds_more)
