@@ -118,7 +118,9 @@ class Plan:
             dense = torch.from_numpy(host_f32(dense)).to(f"cuda:{self.device}")
         dense = dense.contiguous().to(torch.float32)
         nt = dense.shape[0]
-        out = torch.empty((nt, self.n_bus), dtype=torch.float32, device=dense.device)
+        out = torch.zeros((nt, self.n_bus), dtype=torch.float32, device=dense.device)
+        if nt == 0:
+            return out
         _lib.check(_lib.load().atl_spmm(self.handle, _dptr(dense), nt, _dptr(out), _stream_ptr()))
         return out
 
@@ -170,6 +172,15 @@ class _Op:
     def _out(self, shape, like):
         torch = _torch()
         return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+    @staticmethod
+    def _empty_like(first, shape):
+        """Result for an empty time axis (e.g. a rank whose time shard is empty): no
+        kernel is launched (empty tensors have NULL data pointers)."""
+        if _is_torch(first):
+            torch = _torch()
+            return torch.zeros(shape, dtype=torch.float32, device=first.device)
+        return np.zeros(shape, dtype=np.float32)
 
 
 class PvOp(_Op):
@@ -249,6 +260,8 @@ class PvOp(_Op):
         dev = self._all_device(fields.values())
         first = next(a for a in fields.values() if a is not None)
         nt = first.shape[0] if nt is None else nt
+        if nt == 0:
+            return self._empty_like(first, (0, plan.n_bus))
         f, keep = self._fields(fields, host=not dev)
         if dev:
             out = self._out((nt, plan.n_bus), first)
@@ -263,6 +276,8 @@ class PvOp(_Op):
         lib = _lib.load()
         first = next(a for a in fields.values() if a is not None)
         nt = first.shape[0]
+        if nt == 0:
+            return self._empty_like(first, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(fields, host=False)
         torch = _torch()
         if timesum:
@@ -313,6 +328,8 @@ class WindOp(_Op):
         lib = _lib.load()
         dev = self._all_device([wnd, aux])
         nt = wnd.shape[0]
+        if nt == 0:
+            return self._empty_like(wnd, (0, plan.n_bus))
         f, keep = self._fields(wnd, aux, host=not dev)
         if dev:
             out = self._out((nt, plan.n_bus), wnd)
@@ -325,6 +342,8 @@ class WindOp(_Op):
     def cells(self, wnd, aux=None, timesum=False):
         lib = _lib.load()
         nt = wnd.shape[0]
+        if nt == 0:
+            return self._empty_like(wnd, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(wnd, aux, host=False)
         torch = _torch()
         if timesum:
@@ -357,6 +376,8 @@ class HeatOp(_Op):
         lib = _lib.load()
         ds = np.ascontiguousarray(day_start, dtype=np.int64)
         nd = len(ds) - 1
+        if nd == 0 or temperature.shape[0] == 0:
+            return self._empty_like(temperature, (nd, plan.n_bus))
         if _is_torch(temperature):
             t = temperature.contiguous()
             out = self._out((nd, plan.n_bus), t)
@@ -371,6 +392,8 @@ class HeatOp(_Op):
         lib = _lib.load()
         ds = np.ascontiguousarray(day_start, dtype=np.int64)
         nd = len(ds) - 1
+        if nd == 0 or temperature.shape[0] == 0:
+            return self._empty_like(temperature, (self.ny, self.nx) if timesum else (nd, self.ny, self.nx))
         t = temperature.contiguous()
         torch = _torch()
         if timesum:
@@ -412,6 +435,8 @@ class PointwiseOp(_Op):
     def reduce(self, plan, field, chunk_steps=0):
         lib = _lib.load()
         nt = field.shape[0]
+        if nt == 0:
+            return self._empty_like(field, (0, plan.n_bus))
         if _is_torch(field):
             f = field.contiguous()
             out = self._out((nt, plan.n_bus), f)
@@ -426,6 +451,8 @@ class PointwiseOp(_Op):
         lib = _lib.load()
         f = field.contiguous()
         nt = f.shape[0]
+        if nt == 0:
+            return self._empty_like(f, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         torch = _torch()
         if timesum:
             out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=f.device)
@@ -487,6 +514,8 @@ class CspOp(_Op):
         dev = self._all_device(fields.values())
         first = fields["influx_direct"]
         nt = first.shape[0]
+        if nt == 0:
+            return self._empty_like(first, (0, plan.n_bus))
         f, keep = self._fields(fields, host=not dev)
         if dev:
             out = self._out((nt, plan.n_bus), first)
@@ -500,6 +529,8 @@ class CspOp(_Op):
         lib = _lib.load()
         first = fields["influx_direct"]
         nt = first.shape[0]
+        if nt == 0:
+            return self._empty_like(first, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(fields, host=False)
         torch = _torch()
         if timesum:

@@ -651,3 +651,15 @@ def test_deterministic_mode_is_bitwise_repeatable(ds_full, shapes):
         ab.set_deterministic(prev)
     nd = c.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values
     np.testing.assert_allclose(nd, runs[0], rtol=2e-5, atol=1e-6)
+
+
+def test_empty_time_axis_returns_empty_results(shapes):
+    """A rank whose time shard is empty (e.g. 7 day blocks on 8 GPUs) must not fail."""
+    ds = syn.make_dataset(70, 45, 0, x0=-10.0, y0=-20.0, dx=0.5, dy=1.0, t_offset=72)
+    for c in (ab.Cutout(data=ds), ab.Cutout(data=ds).to_device()):
+        assert c.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).shape == (23, 0)
+        assert c.wind("Vestas_V112_3MW", matrix=shapes, aggregate_time=None).shape == (23, 0)
+        assert c.heat_demand(matrix=shapes, aggregate_time=None).shape == (23, 0)
+        assert c.temperature(matrix=shapes, aggregate_time=None).shape == (23, 0)
+        assert c.csp("SAM_solar_tower", matrix=shapes, aggregate_time=None).shape == (23, 0)
+        assert (c.wind("Vestas_V112_3MW", aggregate_time="sum").values == 0).all()

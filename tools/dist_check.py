@@ -19,7 +19,8 @@ warnings.simplefilter("ignore")
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-nx, ny, nt, nbus = 64, 40, 24 * 7, 9
+nx, ny, nbus = 64, 40, 9
+nt = 24 * int(os.environ.get("DIST_CHECK_DAYS", "7"))  # fewer day blocks than ranks -> EMPTY shards (must work)
 full = syn.make_dataset(nx, ny, nt, x0=0.0, y0=30.0)
 m = syn.make_shapes(nx, ny, nbus)
 lo, hi = shard_bounds(nt, world, rank, align=24)
