@@ -44,6 +44,8 @@ class PlanInfo(C.Structure):
         ("n_slots", C.c_int64),
         ("slots_per_active_tile", C.c_double),
         ("fused", C.c_int32),
+        ("pitch", C.c_int32),
+        ("vec", C.c_int32),
     ]
 
 
@@ -69,6 +71,7 @@ class PvConfig(C.Structure):
         ("panel", C.c_double * 16),
         ("output", C.c_int32),
         ("thermal", C.c_double * 3),
+        ("pitch", C.c_int32),
     ]
 
 
@@ -100,6 +103,7 @@ class WindConfig(C.Structure):
         ("n_knots", C.c_int32),
         ("V", C.c_void_p),
         ("POW_norm", C.c_void_p),
+        ("pitch", C.c_int32),
     ]
 
 
@@ -115,6 +119,7 @@ class HeatConfig(C.Structure):
         ("a", C.c_double),
         ("constant", C.c_double),
         ("cooling", C.c_int32),
+        ("pitch", C.c_int32),
     ]
 
 
@@ -130,6 +135,7 @@ class PointwiseConfig(C.Structure):
         ("c1", C.c_double),
         ("c2", C.c_double),
         ("cell_scale", C.c_void_p),
+        ("pitch", C.c_int32),
     ]
 
 
@@ -151,6 +157,7 @@ class CspConfig(C.Structure):
         ("altitude_rad", C.c_void_p),
         ("azimuth_rad", C.c_void_p),
         ("efficiency", C.c_void_p),
+        ("pitch", C.c_int32),
     ]
 
 
@@ -167,6 +174,7 @@ _SIGNATURES = {
     "atl_launch_count": (C.c_int64, []),
     "atl_set_deterministic": (C.c_int, [C.c_int]),
     "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
+    "atl_plan_create_pitched": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "atl_plan_tiling_host": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(PlanInfo), _P, _P, _P, C.c_int64]),
     "atl_plan_destroy": (None, [_P]),

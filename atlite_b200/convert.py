@@ -191,11 +191,12 @@ class _PvSpec(_Spec):
             names += ["solar_altitude", "solar_azimuth"]
         self.fields = {n: _raw(ds, n) for n in names}
         self.fields.setdefault("temperature", self.fields["influx_toa"])  # unused placeholder
+        self.pitch = engine.pitch_of(self.fields.values(), nx)
         self.op = engine.PvOp(
             ny=ny, nx=nx, time=self.time_labels, lon=lon, lat=lat, slope=slope, azimuth=azimuth,
             tracking=tracking, trigon_model=trigon, clearsky_model=clearsky,
             irr_branch=irr_branch, albedo_src=albedo_src, solar_src=solar_src, panel=panel,
-            output=output, thermal=thermal,
+            output=output, thermal=thermal, pitch=self.pitch,
         )
 
     def reduce(self, plan):
@@ -237,8 +238,9 @@ class _PointwiseSpec(_Spec):
         self.field = _raw(ds, var)
         self.time_labels = pd.DatetimeIndex(_coord(ds, "time"))
         self.name = name
+        self.pitch = engine.pitch_of([self.field], nx)
         self.op = engine.PointwiseOp(ny=ny, nx=nx, shift=shift, nan_to_zero=nan_to_zero, poly=poly,
-                                     cell_scale=cell_scale)
+                                     cell_scale=cell_scale, pitch=self.pitch)
 
     def reduce(self, plan):
         return self.op.reduce(plan, self.field)
@@ -279,6 +281,7 @@ def _runoff_spec(ds, weight_with_height=True):
         scale = _to_host(h)
         if scale.ndim == 3:
             scale = scale[0]
+        scale = np.ascontiguousarray(scale[:, : _grid_shape(ds)[1]])  # drop row padding
     return _PointwiseSpec(ds, "runoff", cell_scale=scale, name="runoff")
 
 
@@ -304,11 +307,12 @@ class _CspSpec(_Spec):
             solar_src = _lib.SOLAR_COMPUTED
         eff = EfficiencyTable.from_any(installation["efficiency"])
         self.fields = {n: _raw(ds, n) for n in names}
+        self.pitch = engine.pitch_of(self.fields.values(), nx)
         self.op = engine.CspOp(
             ny=ny, nx=nx, time=self.time_labels, lon=_coord(ds, "lon").astype(np.float64),
             lat=_coord(ds, "lat").astype(np.float64), solar_src=solar_src,
             technology=_lib.CSP_TECH[tech], r_irradiance=installation["r_irradiance"],
-            altitude=eff.altitude, azimuth=eff.azimuth, efficiency=eff.values,
+            altitude=eff.altitude, azimuth=eff.azimuth, efficiency=eff.values, pitch=self.pitch,
         )
 
     def reduce(self, plan):
@@ -358,9 +362,10 @@ class _WindSpec(_Spec):
                     f"Interpolation method must be 'logarithmic' or 'power',  but is: {interpolation_method}"
                 )
         self.wnd, self.aux = wnd, aux
+        self.pitch = engine.pitch_of([wnd, aux], nx)
         self.op = engine.WindOp(
             ny=ny, nx=nx, V=np.asarray(V, float), POW_norm=np.asarray(POW, float) / P,
-            method=method, from_height=from_height, to_height=hub_height,
+            method=method, from_height=from_height, to_height=hub_height, pitch=self.pitch,
         )
 
     def reduce(self, plan):
@@ -394,8 +399,9 @@ class _HeatSpec(_Spec):
         ny, nx = _grid_shape(ds)
         self.temp = _raw(ds, "temperature")
         self.time_labels, self.day_start = day_bins(_coord(ds, "time"), hour_shift)
+        self.pitch = engine.pitch_of([self.temp], nx)
         self.op = engine.HeatOp(ny=ny, nx=nx, threshold=threshold, a=a, constant=constant,
-                                cooling=self.cooling)
+                                cooling=self.cooling, pitch=self.pitch)
 
     def reduce(self, plan):
         return self.op.reduce(plan, self.temp, self.day_start)
@@ -693,7 +699,7 @@ def convert_and_aggregate(
     assert isinstance(matrix, sp.csr_matrix)
     dim, idx = _ensure_index(index, matrix.shape[0])
 
-    plan = engine.get_plan(matrix, ny, nx)
+    plan = engine.get_plan(matrix, ny, nx, pitch=getattr(spec, "pitch", None))
     if spec is not None:
         res = spec.reduce(plan)  # (time, bus) float32
         time_labels, name = spec.time_labels, spec.name

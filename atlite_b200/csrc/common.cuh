@@ -42,17 +42,25 @@ constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 
 struct GridDev {
   int nx, ny;
+  int pitch;       // elements per stored row of the INPUT fields (>= nx).  Device-resident
+                   // cutouts with nx % 4 != 0 are stored row-padded to a multiple of 4 so
+                   // that the 128-bit VEC kernels apply (Cutout.to_device()).
   int n_tx, n_ty;  // tiles per row / column
-  int64_t S;       // ny * nx
+  int64_t S;       // ny * pitch: elements per input time slab
+  int64_t S_out;   // ny * nx:    elements per OUTPUT plane (per-cell results are never padded)
+  int out_vec;     // per-cell outputs may use 128-bit stores (nx % 4 == 0, aligned base)
 };
 
-inline GridDev make_grid(int ny, int nx) {
+inline GridDev make_grid(int ny, int nx, int pitch = 0) {
   GridDev g;
   g.nx = nx;
   g.ny = ny;
+  g.pitch = pitch > 0 ? pitch : nx;
   g.n_tx = (nx + TILE_X - 1) / TILE_X;
   g.n_ty = (ny + TILE_Y - 1) / TILE_Y;
-  g.S = (int64_t)ny * nx;
+  g.S = (int64_t)ny * g.pitch;
+  g.S_out = (int64_t)ny * nx;
+  g.out_vec = 0;
   return g;
 }
 
@@ -69,7 +77,7 @@ struct PlanDev {
 // Two lane layouts over the same 32 x 4 tile:
 //  * SCALAR (any nx): lane l owns column 32*tx + l and rows 4*ty .. 4*ty+3; four
 //    scalar loads per field, each a coalesced 128-byte row segment.
-//  * VEC (nx % 4 == 0, 16-byte aligned fields): lane l owns row 4*ty + l/8 and the
+//  * VEC (pitch % 4 == 0, 16-byte aligned fields): lane l owns row 4*ty + l/8 and the
 //    four consecutive columns 32*tx + 4*(l%8) ..+3: ONE 16-byte load per field
 //    (a warp still touches four full 128-byte lines), a quarter of the address
 //    arithmetic.
@@ -122,7 +130,7 @@ __device__ __forceinline__ TileGeomT<false> make_geom<false>(int tile, int lane,
   const int xc = min(g.x, gd.nx - 1);
 #pragma unroll
   for (int r = 0; r < TILE_Y; ++r)
-    g.boff[r] = 4 * (int64_t)(min(g.y0 + r, gd.ny - 1) * gd.nx + xc);
+    g.boff[r] = 4 * (int64_t)(min(g.y0 + r, gd.ny - 1) * gd.pitch + xc);
   return g;
 }
 template <>
@@ -131,8 +139,14 @@ __device__ __forceinline__ TileGeomT<true> make_geom<true>(int tile, int lane, c
   const int tx = tile % gd.n_tx, ty = tile / gd.n_tx;
   g.x0 = tx * TILE_X + 4 * (lane & 7);
   g.y = ty * TILE_Y + (lane >> 3);
-  g.valid = (g.x0 < gd.nx && g.y < gd.ny) ? 0xFu : 0u;  // nx % 4 == 0: all 4 or none
-  g.boff = 4 * (int64_t)(min(g.y, gd.ny - 1) * gd.nx + min(g.x0, gd.nx - 4));
+  unsigned v = 0;  // with a padded pitch a chunk may straddle the logical width nx
+  if (g.y < gd.ny) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (g.x0 + i < gd.nx) v |= 1u << i;
+  }
+  g.valid = v;
+  g.boff = 4 * (int64_t)(min(g.y, gd.ny - 1) * gd.pitch + min(g.x0, gd.pitch - 4));
   return g;
 }
 
@@ -204,7 +218,14 @@ __device__ __forceinline__ void store4(float* __restrict__ plane, const GridDev&
 }
 __device__ __forceinline__ void store4(float* __restrict__ plane, const GridDev& gd,
                                        const TileGeomT<true>& g, const float (&v)[4]) {
-  if (g.valid) *reinterpret_cast<float4*>(plane + g.y * gd.nx + g.x0) = make_float4(v[0], v[1], v[2], v[3]);
+  float* o = plane + g.y * gd.nx + g.x0;
+  if (gd.out_vec) {
+    if (g.valid) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if ((g.valid >> r) & 1u) o[r] = v[r];
+  }
 }
 __device__ __forceinline__ void atomic_add4(float* __restrict__ plane, const GridDev& gd,
                                             const TileGeomT<false>& g, const float (&v)[4]) {
@@ -214,9 +235,19 @@ __device__ __forceinline__ void atomic_add4(float* __restrict__ plane, const Gri
 }
 __device__ __forceinline__ void atomic_add4(float* __restrict__ plane, const GridDev& gd,
                                             const TileGeomT<true>& g, const float (&v)[4]) {
-  if (g.valid) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) atomicAdd(plane + g.y * gd.nx + g.x0 + r, v[r]);
+  for (int r = 0; r < 4; ++r)
+    if ((g.valid >> r) & 1u) atomicAdd(plane + g.y * gd.nx + g.x0 + r, v[r]);
+}
+
+// Values of out-of-grid cells (row padding / tile overhang) are unspecified; zero
+// them so that padding contents can never send a tile down the NaN path.
+template <class Geom>
+__device__ __forceinline__ void zero_invalid(const Geom& g, float (&v)[4]) {
+  if (g.valid != 0xFu) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (!((g.valid >> i) & 1u)) v[i] = 0.f;
   }
 }
 
@@ -305,7 +336,7 @@ struct AtlPlan {
   int32_t n_tiles, n_active;
   int64_t n_slots;
   bool fused;
-  bool vec;  // weight layout / kernels: VEC lane layout (nx % 4 == 0)
+  bool vec;  // weight layout / kernels: VEC lane layout (grid.pitch % 4 == 0)
   // device arrays
   int32_t* d_tile_slot_ptr = nullptr;
   int32_t* d_slot_row = nullptr;

@@ -202,7 +202,8 @@ int atl_csp_create(int device, const AtlCspConfig* cfg, AtlCspOp** op_out) {
   const double D2R = 3.14159265358979323846 / 180.0;
   AtlCspOp* op = new AtlCspOp();
   op->device = device;
-  op->grid = make_grid(cfg->ny, cfg->nx);
+  ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
+  op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   op->nt = cfg->nt;
   op->solar_src = cfg->solar_src;
   op->tower = cfg->technology;
@@ -266,8 +267,9 @@ int atl_csp_reduce(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* 
   int rc = csp_check(op, f, t0, nt);
   if (rc) return rc;
   ATL_REQUIRE(plan && out_dev, "NULL argument");
-  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
-              "plan / operator grid mismatch");
+  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny &&
+                  plan->grid.pitch == op->grid.pitch,
+              "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f, t0); };
   return dispatch_reduce(make, plan, csp_aligned(f), out_dev, nt, (cudaStream_t)stream);

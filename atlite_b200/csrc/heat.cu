@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(CTA_THREADS)
   for (int d = d0; d < d1; ++d) {
     heat_day(hp, g, d, v);
     if (MODE == 0) {
+      zero_invalid(g, v);
       reduce_slots(v, s_beg, s_end, plan, out + (size_t)d * plan.n_bus, lane);
     } else if (MODE == 1) {
-      store4(out + (int64_t)d * gd.S, gd, g, v);
+      store4(out + (int64_t)d * gd.S_out, gd, g, v);
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
@@ -153,8 +154,9 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   float* det_acc = nullptr;
   if (mode == 0) {
     ATL_REQUIRE(plan, "NULL plan");
-    ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
-                "plan / operator grid mismatch");
+    ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny &&
+                    plan->grid.pitch == op->grid.pitch,
+                "plan / operator grid (or pitch) mismatch");
     ATL_CUDA(cudaMemsetAsync(out, 0, (size_t)n_days * plan->n_bus * sizeof(float), st));
     if (plan->fused) {
       if (plan->n_active == 0) return ATL_OK;
@@ -169,14 +171,14 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
       // two-pass fallback: per-cell daily values, then CSR gather
       ATL_REQUIRE(day_start_host, "two-pass fallback needs the host day table");
       float* scratch = nullptr;
-      const int64_t S = op->grid.S;
+      const int64_t S = op->grid.S_out;  // unpadded scratch cube
       int64_t blk = (256LL << 20) / (S * 4);
       blk = blk < 1 ? 1 : (blk > n_days ? n_days : blk);
       ATL_CUDA(cudaMallocAsync((void**)&scratch, (size_t)blk * S * 4, st));
       int rc = ATL_OK;
       for (int64_t d = 0; d < n_days && rc == ATL_OK; d += blk) {
         const int64_t n = n_days - d < blk ? n_days - d : blk;
-        rc = heat_launch_core(1, op, nullptr, temp + (day_start_host[d] - base) * S, d_days + d,
+        rc = heat_launch_core(1, op, nullptr, temp + (day_start_host[d] - base) * op->grid.S, d_days + d,
                               (int32_t)day_start_host[d], nullptr, n, scratch, st);
         if (rc == ATL_OK)
           rc = launch_csr_spmm(plan, scratch, n, out + (size_t)d * plan->n_bus, st);
@@ -201,27 +203,29 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   db = db < 1 ? 1 : (db > 8 ? 8 : db);
   dim3 grid(gx, (unsigned)((n_days + db - 1) / db));
   // lane layout: the plan's for the fused reduce, else by grid width / alignment
-  const bool al = aligned16(temp) && (mode != 1 || aligned16(out));
-  bool vec = op->grid.nx % 4 == 0 && al;
+  const bool al = aligned16(temp);
+  GridDev gdo = op->grid;
+  gdo.out_vec = (mode == 1 && gdo.nx % 4 == 0 && aligned16(out)) ? 1 : 0;
+  bool vec = op->grid.pitch % 4 == 0 && al;
   if (mode == 0) {
     vec = plan->vec;
     ATL_REQUIRE(!vec || al,
-                "field pointers must be 16-byte aligned (nx % 4 == 0 uses 128-bit loads)");
+                "field pointers must be 16-byte aligned (pitch % 4 == 0 uses 128-bit loads)");
   }
   if (vec) {
     if (mode == 0)
-      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, det_acc ? det_acc : out, (int)n_days, db);
+      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, (int)n_days, db);
     else if (mode == 1)
-      k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
     else
-      k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
   } else {
     if (mode == 0)
-      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, det_acc ? det_acc : out, (int)n_days, db);
+      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, (int)n_days, db);
     else if (mode == 1)
-      k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
     else
-      k_heat<2, false><<<grid, CTA_THREADS, 0, st>>>(hp, op->grid, pd, out, (int)n_days, db);
+      k_heat<2, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
   }
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
@@ -260,7 +264,8 @@ int atl_heat_create(int device, const AtlHeatConfig* cfg, AtlHeatOp** op_out) {
   ATL_REQUIRE(cfg->ny > 0 && cfg->nx > 0, "bad grid");
   AtlHeatOp* op = new AtlHeatOp();
   op->device = device;
-  op->grid = make_grid(cfg->ny, cfg->nx);
+  ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
+  op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   // the reference adds 273.15 in float64 and then meets the float32 field
   // (weak python scalar -> float32): convert.py:413-414
   op->thr_k = (float)(cfg->threshold_c + 273.15);

@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 #pragma unroll 1
     for (int k = 0; k < nfull; ++k, t += B) {
 #pragma unroll
-      for (int j = 0; j < B; ++j) phys.compute(c, g, t + j, r[j], v[j], smem);
+      for (int j = 0; j < B; ++j) {
+        phys.compute(c, g, t + j, r[j], v[j], smem);
+        zero_invalid(g, v[j]);
+      }
       if (k + 1 < nfull) {
 #pragma unroll
         for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   for (; t < t1; ++t, sb += S4) {
     phys.load(c, g, sb, r[0]);
     phys.compute(c, g, t, r[0], v[0], smem);
+    zero_invalid(g, v[0]);
     reduce_slots(v[0], s_beg, s_end, plan, out + (size_t)t * nb, lane);
   }
 }
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4)
     phys.load(c, g, sb, ra);
     phys.compute(c, g, t, ra, v, smem);
     if (MODE == 0) {
-      store4(out + (int64_t)(t - t_begin) * gd.S, gd, g, v);
+      store4(out + (int64_t)(t - t_begin) * gd.S_out, gd, g, v);
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
@@ -126,6 +130,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 4)
   }
   if (MODE == 1) atomic_add4(out, gd, g, acc);
 }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Deterministic reduce mode (atl_set_deterministic): bitwise-repeatable results.
 bool deterministic();
@@ -164,8 +170,6 @@ inline int pick_tb(int n_cta_x, int64_t nt) {
   return (int)tb;
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 template <class Phys>
 int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begin,
                  int64_t t_end, bool timesum, cudaStream_t st) {
@@ -177,10 +181,12 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
   const int gy = (int)((t_end - t_begin + tb - 1) / tb);
   dim3 grid(gx, gy);
   const size_t smem = Phys::kSmemFloats * sizeof(float);
+  GridDev go = gd;
+  go.out_vec = (gd.nx % 4 == 0 && aligned16(out)) ? 1 : 0;
   if (timesum)
-    k_cells<Phys, 1><<<grid, CTA_THREADS, smem, st>>>(phys, gd, out, (int)t_begin, (int)t_end, tb);
+    k_cells<Phys, 1><<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
   else
-    k_cells<Phys, 0><<<grid, CTA_THREADS, smem, st>>>(phys, gd, out, (int)t_begin, (int)t_end, tb);
+    k_cells<Phys, 0><<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   return ATL_OK;
@@ -236,7 +242,7 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
 template <class Phys>
 int launch_two_pass(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt,
                     cudaStream_t st) {
-  const int64_t S = plan->grid.S;
+  const int64_t S = plan->grid.S_out;  // the scratch cube is unpadded
   int64_t blk = (256LL << 20) / (S * 4);  // <= 256 MiB scratch
   if (blk < 1) blk = 1;
   if (blk > nt) blk = nt;
@@ -266,7 +272,7 @@ int dispatch_reduce(Make make, const AtlPlan* plan, bool ptrs_aligned, float* ou
   if (plan->fused) {
     if (plan->vec) {
       ATL_REQUIRE(ptrs_aligned,
-                  "field pointers must be 16-byte aligned (nx % 4 == 0 uses 128-bit loads)");
+                  "field pointers must be 16-byte aligned (pitch % 4 == 0 uses 128-bit loads)");
       return launch_fused(make(std::true_type{}), plan, out, nt, st);
     }
     return launch_fused(make(std::false_type{}), plan, out, nt, st);
@@ -278,7 +284,7 @@ int dispatch_reduce(Make make, const AtlPlan* plan, bool ptrs_aligned, float* ou
 template <class Make>
 int dispatch_cells(Make make, const GridDev& gd, bool ptrs_aligned, float* out, int64_t nt,
                    bool timesum, cudaStream_t st) {
-  if (gd.nx % 4 == 0 && ptrs_aligned && (timesum || aligned16(out)))
+  if (gd.pitch % 4 == 0 && ptrs_aligned)
     return launch_cells(make(std::true_type{}), gd, out, 0, nt, timesum, st);
   return launch_cells(make(std::false_type{}), gd, out, 0, nt, timesum, st);
 }

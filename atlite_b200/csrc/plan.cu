@@ -97,7 +97,7 @@ int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* 
     const int64_t n = std::min<int64_t>(nt - t, 65535LL * wpb);
     dim3 grid(plan->n_bus, (unsigned)((n + wpb - 1) / wpb));
     k_csr_spmm<<<grid, 32 * wpb, 0, st>>>(plan->d_indptr, plan->d_indices, plan->d_vals,
-                                          dense + t * plan->grid.S, plan->grid.S,
+                                          dense + t * plan->grid.S_out, plan->grid.S_out,
                                           out + (size_t)t * plan->n_bus, plan->n_bus, (int)n);
     ++g_launches;
     ATL_CUDA(cudaGetLastError());
@@ -166,15 +166,17 @@ struct Tiling {
   std::vector<float> w;  // n_slots * 128 weights in lane order (only if fused)
 };
 
-static int build_tiling(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr,
+static int build_tiling(int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus, const int64_t* indptr,
                         const int32_t* indices, const double* data, bool force_arrays,
                         Tiling& T) {
   ATL_REQUIRE(ny > 0 && nx > 0 && n_bus >= 0, "bad plan shape");
-  ATL_REQUIRE((int64_t)ny * nx < (1LL << 29), "grid too large (ny*nx must be < 2^29)");
+  if (pitch <= 0) pitch = nx;
+  ATL_REQUIRE(pitch >= nx, "pitch must be >= nx");
+  ATL_REQUIRE((int64_t)ny * pitch < (1LL << 29), "grid too large (ny*pitch must be < 2^29)");
   ATL_REQUIRE(indptr && (n_bus == 0 || indptr[n_bus] == 0 || (indices && data)),
               "CSR arrays missing");
-  const GridDev gd = make_grid(ny, nx);
-  const bool vec = (nx % 4 == 0);  // lane layout of the weight vectors / kernels
+  const GridDev gd = make_grid(ny, nx, pitch);
+  const bool vec = (pitch % 4 == 0);  // lane layout of the weight vectors / kernels
   const int64_t nnz_in = n_bus ? indptr[n_bus] : 0;
   const int64_t n_tiles = (int64_t)gd.n_tx * gd.n_ty;
 
@@ -189,7 +191,7 @@ static int build_tiling(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* in
     ATL_REQUIRE(indptr[r + 1] >= indptr[r], "indptr not monotone");
     for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k) {
       const int32_t c = indices[k];
-      ATL_REQUIRE(c >= 0 && c < gd.S, "column index out of range");
+      ATL_REQUIRE(c >= 0 && c < gd.S_out, "column index out of range");
       const int iy = c / nx, ix = c - iy * nx;
       const int64_t tile = (int64_t)(iy / TILE_Y) * gd.n_tx + ix / TILE_X;
       Ent e;
@@ -264,7 +266,7 @@ int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* i
   ATL_REQUIRE(info, "info is NULL");
   Tiling T;
   const bool want = tile_slot_ptr_out || slot_row_out || slot_w_out;
-  int rc = build_tiling(ny, nx, n_bus, indptr, indices, data, want, T);
+  int rc = build_tiling(ny, nx, 0, n_bus, indptr, indices, data, want, T);
   if (rc) return rc;
   info->ny = ny;
   info->nx = nx;
@@ -275,6 +277,8 @@ int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* i
   info->n_slots = T.n_slots;
   info->slots_per_active_tile = T.n_active ? (double)T.n_slots / T.n_active : 0.0;
   info->fused = T.fused ? 1 : 0;
+  info->pitch = nx;
+  info->vec = T.vec ? 1 : 0;
   if (!want) return ATL_OK;
   ATL_REQUIRE(tile_slot_ptr_out && slot_row_out && slot_w_out, "all three output arrays are needed");
   ATL_REQUIRE(slot_capacity >= T.n_slots, "slot_capacity too small");
@@ -287,10 +291,16 @@ int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* i
 int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
                     const int64_t* indptr, const int32_t* indices, const double* data,
                     AtlPlan** plan_out) {
+  return atl_plan_create_pitched(device, ny, nx, 0, n_bus, indptr, indices, data, plan_out);
+}
+
+int atl_plan_create_pitched(int device, int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus,
+                            const int64_t* indptr, const int32_t* indices, const double* data,
+                            AtlPlan** plan_out) {
   ATL_REQUIRE(plan_out, "plan_out is NULL");
   *plan_out = nullptr;
   Tiling T;
-  int rc0 = build_tiling(ny, nx, n_bus, indptr, indices, data, false, T);
+  int rc0 = build_tiling(ny, nx, pitch, n_bus, indptr, indices, data, false, T);
   if (rc0) return rc0;
   const int64_t nnz_in = T.nnz;
 
@@ -377,6 +387,8 @@ int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info) {
   info->n_slots = plan->n_slots;
   info->slots_per_active_tile = plan->n_active ? (double)plan->n_slots / plan->n_active : 0.0;
   info->fused = plan->fused ? 1 : 0;
+  info->pitch = plan->grid.pitch;
+  info->vec = plan->vec ? 1 : 0;
   return ATL_OK;
 }
 
@@ -401,7 +413,10 @@ int atl_spmm(const AtlPlan* plan, const float* dense_dev, int64_t nt, float* out
   ATL_REQUIRE(plan && dense_dev && out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(plan->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!plan->fused) return launch_csr_spmm(plan, dense_dev, nt, out_dev, st);
+  if (!plan->fused) {
+    ATL_REQUIRE(plan->grid.pitch == plan->grid.nx, "atl_spmm on a non-tiling plan needs an unpadded field");
+    return launch_csr_spmm(plan, dense_dev, nt, out_dev, st);
+  }
   auto make = [&](auto vec) {
     IdentityPhys<decltype(vec)::value> ph;
     ph.f = dense_dev;

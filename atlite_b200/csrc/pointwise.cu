@@ -89,7 +89,8 @@ int atl_pointwise_create(int device, const AtlPointwiseConfig* cfg, AtlPointwise
   ATL_REQUIRE(cfg->ny > 0 && cfg->nx > 0, "bad grid");
   AtlPointwiseOp* op = new AtlPointwiseOp();
   op->device = device;
-  op->grid = make_grid(cfg->ny, cfg->nx);
+  ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
+  op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   op->shift = (float)cfg->shift;
   op->sink = (float)cfg->sink;
   op->c0 = (float)cfg->c0;
@@ -98,7 +99,7 @@ int atl_pointwise_create(int device, const AtlPointwiseConfig* cfg, AtlPointwise
   op->nan_to_zero = cfg->nan_to_zero;
   op->poly = cfg->poly;
   if (cfg->cell_scale) {
-    const size_t bytes = (size_t)op->grid.S * sizeof(float);
+    const size_t bytes = (size_t)op->grid.S_out * sizeof(float);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_scale, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(op->d_scale, cfg->cell_scale, bytes, cudaMemcpyHostToDevice);
@@ -131,8 +132,9 @@ int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny
 int atl_pointwise_reduce(const AtlPointwiseOp* op, const AtlPlan* plan, const float* field_dev,
                          int64_t nt, float* out_dev, void* stream) {
   ATL_REQUIRE(op && plan && field_dev && out_dev, "NULL argument");
-  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
-              "plan / operator grid mismatch");
+  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny &&
+                  plan->grid.pitch == op->grid.pitch,
+              "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, field_dev); };
   return dispatch_reduce(make, plan, aligned16(field_dev), out_dev, nt, (cudaStream_t)stream);

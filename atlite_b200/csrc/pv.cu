@@ -403,13 +403,14 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   ATL_REQUIRE(cfg->albedo_src >= 0 && cfg->albedo_src <= 1, "bad albedo source");
   ATL_REQUIRE(cfg->solar_src >= 0 && cfg->solar_src <= 2, "bad solar source");
   ATL_REQUIRE(cfg->panel_model >= 0 && cfg->panel_model <= 1, "Unknown panel model");
+  ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
   ATL_REQUIRE(cfg->output >= ATL_OUT_PANEL && cfg->output <= ATL_OUT_SOLAR_THERMAL, "bad output kind");
 
   const double PI = 3.14159265358979323846;
   const double D2R = PI / 180.0;
   AtlPvOp* op = new AtlPvOp();
   op->device = device;
-  op->grid = make_grid(cfg->ny, cfg->nx);
+  op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   op->nt = cfg->nt;
   op->tracking = cfg->tracking;
   op->trigon = cfg->trigon_model;
@@ -517,8 +518,9 @@ int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f, 
   int rc = check(op, f, t0, nt);
   if (rc) return rc;
   ATL_REQUIRE(plan && out_dev, "NULL argument");
-  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
-              "plan / operator grid mismatch");
+  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny &&
+                  plan->grid.pitch == op->grid.pitch,
+              "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = fields_aligned(f);
   if (op->fast) {

@@ -257,7 +257,8 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
 
   AtlWindOp* op = new AtlWindOp();
   op->device = device;
-  op->grid = make_grid(cfg->ny, cfg->nx);
+  ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
+  op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   op->method = cfg->method;
   op->n_knots = n;
   op->NK = NK;
@@ -304,8 +305,9 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
   int rc = check_fields(op, f);
   if (rc) return rc;
   ATL_REQUIRE(plan && out_dev, "NULL argument");
-  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny,
-              "plan / operator grid mismatch");
+  ATL_REQUIRE(plan->grid.nx == op->grid.nx && plan->grid.ny == op->grid.ny &&
+                  plan->grid.pitch == op->grid.pitch,
+              "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
   return dispatch_reduce(make, plan, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt,

@@ -110,9 +110,12 @@ class Cutout:
         return compute_indicatormatrix(cells, shapes, 4326, shapes_crs)
 
     # ---- device residency
-    def to_device(self, device=None, variables=None):
+    def to_device(self, device=None, variables=None, pad=True):
         """Return a Cutout whose (time, y, x) variables live in GPU memory as
-        float32 torch tensors (solar position variables keep float64)."""
+        float32 torch tensors (solar position variables keep float64).  With
+        ``pad`` (default) rows are zero-padded to a multiple of 4 elements when
+        the width is not one already, so that the 128-bit kernels apply (the
+        padding is invisible: coordinates and results keep the logical width)."""
         import torch
 
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -128,6 +131,9 @@ class Cutout:
                 if not (n.startswith("solar_") and a.dtype == np.float64):
                     a = np.ascontiguousarray(a, dtype=np.float32)
                 arr = torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+            nx = len(out.coords["x"])
+            if pad and arr.shape[-1] == nx and nx % 4:
+                arr = torch.nn.functional.pad(arr, (0, 4 - nx % 4))
             dims = ("time", "y", "x")[-arr.ndim:]
             out[n] = (dims, arr.contiguous())
         return Cutout(data=out, time_shard=self.time_shard)

@@ -66,6 +66,26 @@ def host_f32(a):
     return a
 
 
+def pitch_of(arrays, nx):
+    """Row pitch (elements) of a set of (time, y, x) fields: the last dimension of
+    device tensors (``Cutout.to_device`` pads rows to a multiple of 4), ``nx`` for
+    host arrays."""
+    p = None
+    for a in arrays:
+        if a is None or getattr(a, "ndim", 0) != 3:
+            continue
+        w = int(a.shape[-1])
+        if p is not None and w != p:
+            raise ValueError("fields of one call must share the same row pitch")
+        p = w
+    p = nx if p is None else p
+    if p < nx:
+        raise ValueError(f"fields are narrower ({p}) than the grid ({nx})")
+    if p != nx and not any(_is_torch(a) for a in arrays if a is not None):
+        raise ValueError("host arrays must be unpadded (last dimension == nx)")
+    return p
+
+
 def time_ns(time):
     """datetime-like sequence -> contiguous int64 nanoseconds since the epoch (UTC)."""
     idx = pd.DatetimeIndex(np.asarray(time))
@@ -75,7 +95,7 @@ def time_ns(time):
 class Plan:
     """Device-side aggregation plan built from an (n_bus, S) CSR matrix."""
 
-    def __init__(self, matrix, ny, nx, device=None):
+    def __init__(self, matrix, ny, nx, device=None, pitch=None):
         lib = _lib.load()
         m = sp.csr_matrix(matrix)
         m.sum_duplicates()
@@ -89,9 +109,10 @@ class Plan:
         self._indices = np.ascontiguousarray(m.indices, dtype=np.int32)
         self._data = np.ascontiguousarray(m.data, dtype=np.float64)
         h = C.c_void_p()
+        self.pitch = nx if pitch is None else int(pitch)
         _lib.check(
-            lib.atl_plan_create(
-                self.device, ny, nx, m.shape[0],
+            lib.atl_plan_create_pitched(
+                self.device, ny, nx, self.pitch, m.shape[0],
                 _lib.ptr(self._indptr), _lib.ptr(self._indices), _lib.ptr(self._data),
                 C.byref(h),
             )
@@ -128,20 +149,21 @@ class Plan:
 _PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
 
 
-def get_plan(matrix, ny, nx, device=None):
+def get_plan(matrix, ny, nx, device=None, pitch=None):
     """Plans are cached (LRU, 4 entries): the typical workflow evaluates many
     technologies against the same shapes."""
     m = sp.csr_matrix(matrix)
     device = current_device() if device is None else device
+    pitch = nx if pitch is None else int(pitch)
     key = (
-        device, ny, nx, m.shape, m.nnz,
+        device, ny, nx, pitch, m.shape, m.nnz,
         zlib.crc32(np.ascontiguousarray(m.indptr).view(np.uint8)),
         zlib.crc32(np.ascontiguousarray(m.indices).view(np.uint8)),
         zlib.crc32(np.ascontiguousarray(m.data).view(np.uint8)),
     )
     plan = _PLAN_CACHE.get(key)
     if plan is None:
-        plan = Plan(m, ny, nx, device)
+        plan = Plan(m, ny, nx, device, pitch)
         _PLAN_CACHE[key] = plan
         while len(_PLAN_CACHE) > 4:
             _PLAN_CACHE.popitem(last=False)
@@ -173,6 +195,29 @@ class _Op:
         torch = _torch()
         return torch.empty(shape, dtype=torch.float32, device=like.device)
 
+    def _dev(self, a, f64_ok=False):
+        """Device field -> contiguous tensor, after checking what the kernels assume
+        about it: (time, ny, pitch) layout on this operator's GPU, float32 (float64
+        for stored solar position).  The C ABI takes raw pointers, so this is the
+        only place a wrong shape can be caught."""
+        torch = _torch()
+        pitch = getattr(self, "pitch", 0) or self.nx
+        if a.ndim != 3 or tuple(a.shape[1:]) != (self.ny, pitch):
+            raise ValueError(f"field has shape {tuple(a.shape)}, expected (time, {self.ny}, {pitch})")
+        if a.dtype != torch.float32 and not (f64_ok and a.dtype == torch.float64):
+            raise TypeError(f"device fields must be float32, got {a.dtype}")
+        if a.device.type != "cuda" or a.device.index != self.device:
+            raise ValueError(f"field lives on {a.device}, operator on cuda:{self.device}")
+        return a.contiguous()
+
+    def _host(self, a, f64_ok=False):
+        a = np.asarray(a)
+        if a.ndim != 3 or a.shape[1:] != (self.ny, self.nx):
+            raise ValueError(f"field has shape {a.shape}, expected (time, {self.ny}, {self.nx})")
+        if f64_ok and a.dtype == np.float64:
+            return np.ascontiguousarray(a)
+        return host_f32(a)
+
     @staticmethod
     def _empty_like(first, shape):
         """Result for an empty time axis (e.g. a rank whose time shard is empty): no
@@ -191,10 +236,11 @@ class PvOp(_Op):
 
     def __init__(self, *, ny, nx, time, lon, lat, slope, azimuth, tracking, trigon_model,
                  clearsky_model, irr_branch, albedo_src, solar_src, panel=None, time_shift="0h",
-                 altitude_threshold=1.0, output="panel", thermal=(0.0, 0.0, 0.0), device=None):
+                 altitude_threshold=1.0, output="panel", thermal=(0.0, 0.0, 0.0), device=None, pitch=0):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
+        self.pitch = int(pitch) or nx
         self._time = time_ns(time)
         self.nt = len(self._time)
         self._lon, self._lat = _lib.as_f64(lon), _lib.as_f64(lat)
@@ -210,6 +256,7 @@ class PvOp(_Op):
         cfg.trigon_model = trigon_model
         cfg.clearsky_model = clearsky_model
         cfg.irr_branch, cfg.albedo_src, cfg.solar_src = irr_branch, albedo_src, solar_src
+        cfg.pitch = int(pitch)
         cfg.output = _lib.OUTPUT[output]
         for i, v in enumerate(thermal):
             cfg.thermal[i] = float(v)
@@ -242,14 +289,11 @@ class PvOp(_Op):
                 setattr(f, n, None)
                 continue
             if host:
-                if n.startswith("solar_") and np.asarray(a).dtype == np.float64:
-                    a = np.ascontiguousarray(a)
-                else:
-                    a = host_f32(a)
+                a = self._host(a, f64_ok=n.startswith("solar_"))
                 keep.append(a)
                 setattr(f, n, a.ctypes.data)
             else:
-                a = a.contiguous()
+                a = self._dev(a, f64_ok=n.startswith("solar_"))
                 keep.append(a)
                 setattr(f, n, a.data_ptr())
         return f, keep
@@ -294,14 +338,16 @@ class WindOp(_Op):
 
     _destroy = "atl_wind_destroy"
 
-    def __init__(self, *, ny, nx, V, POW_norm, method, from_height, to_height, device=None):
+    def __init__(self, *, ny, nx, V, POW_norm, method, from_height, to_height, device=None, pitch=0):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
+        self.pitch = int(pitch) or nx
         self._V, self._P = _lib.as_f64(V), _lib.as_f64(POW_norm)
         cfg = _lib.WindConfig()
         cfg.ny, cfg.nx, cfg.method = ny, nx, method
         cfg.from_height, cfg.to_height = float(from_height), float(to_height)
+        cfg.pitch = int(pitch)
         cfg.n_knots = len(self._V)
         cfg.V, cfg.POW_norm = _lib.ptr(self._V).value, _lib.ptr(self._P).value
         h = C.c_void_p()
@@ -315,11 +361,11 @@ class WindOp(_Op):
             if a is None:
                 setattr(f, n, None)
             elif host:
-                a = host_f32(a)
+                a = self._host(a)
                 keep.append(a)
                 setattr(f, n, a.ctypes.data)
             else:
-                a = a.contiguous()
+                a = self._dev(a)
                 keep.append(a)
                 setattr(f, n, a.data_ptr())
         return f, keep
@@ -360,14 +406,16 @@ class HeatOp(_Op):
 
     _destroy = "atl_heat_destroy"
 
-    def __init__(self, *, ny, nx, threshold, a, constant, cooling=False, device=None):
+    def __init__(self, *, ny, nx, threshold, a, constant, cooling=False, device=None, pitch=0):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
+        self.pitch = int(pitch) or nx
         cfg = _lib.HeatConfig()
         cfg.ny, cfg.nx = ny, nx
         cfg.threshold_c, cfg.a, cfg.constant = float(threshold), float(a), float(constant)
         cfg.cooling = 1 if cooling else 0
+        cfg.pitch = int(pitch)
         h = C.c_void_p()
         _lib.check(lib.atl_heat_create(self.device, C.byref(cfg), C.byref(h)))
         self.handle = h
@@ -379,11 +427,11 @@ class HeatOp(_Op):
         if nd == 0 or temperature.shape[0] == 0:
             return self._empty_like(temperature, (nd, plan.n_bus))
         if _is_torch(temperature):
-            t = temperature.contiguous()
+            t = self._dev(temperature)
             out = self._out((nd, plan.n_bus), t)
             _lib.check(lib.atl_heat_reduce(self.handle, plan.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
             return out
-        t = host_f32(temperature)
+        t = self._host(temperature)
         out = np.empty((nd, plan.n_bus), dtype=np.float32)
         _lib.check(lib.atl_heat_reduce_host(self.handle, plan.handle, _hptr(t), _lib.ptr(ds), nd, _hptr(out), chunk_days))
         return out
@@ -394,7 +442,7 @@ class HeatOp(_Op):
         nd = len(ds) - 1
         if nd == 0 or temperature.shape[0] == 0:
             return self._empty_like(temperature, (self.ny, self.nx) if timesum else (nd, self.ny, self.nx))
-        t = temperature.contiguous()
+        t = self._dev(temperature)
         torch = _torch()
         if timesum:
             out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=t.device)
@@ -411,13 +459,15 @@ class PointwiseOp(_Op):
 
     _destroy = "atl_pointwise_destroy"
 
-    def __init__(self, *, ny, nx, shift=0.0, nan_to_zero=False, poly=None, cell_scale=None, device=None):
+    def __init__(self, *, ny, nx, shift=0.0, nan_to_zero=False, poly=None, cell_scale=None, device=None, pitch=0):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
+        self.pitch = int(pitch) or nx
         cfg = _lib.PointwiseConfig()
         cfg.ny, cfg.nx = ny, nx
         cfg.shift = float(shift)
+        cfg.pitch = int(pitch)
         cfg.nan_to_zero = 1 if nan_to_zero else 0
         cfg.poly = 0 if poly is None else 1
         if poly is not None:
@@ -438,21 +488,21 @@ class PointwiseOp(_Op):
         if nt == 0:
             return self._empty_like(field, (0, plan.n_bus))
         if _is_torch(field):
-            f = field.contiguous()
+            f = self._dev(field)
             out = self._out((nt, plan.n_bus), f)
             _lib.check(lib.atl_pointwise_reduce(self.handle, plan.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
             return out
-        f = host_f32(field)
+        f = self._host(field)
         out = np.empty((nt, plan.n_bus), dtype=np.float32)
         _lib.check(lib.atl_pointwise_reduce_host(self.handle, plan.handle, _hptr(f), nt, _hptr(out), chunk_steps))
         return out
 
     def cells(self, field, timesum=False):
         lib = _lib.load()
-        f = field.contiguous()
-        nt = f.shape[0]
+        nt = field.shape[0]
         if nt == 0:
-            return self._empty_like(f, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+            return self._empty_like(field, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+        f = self._dev(field)
         torch = _torch()
         if timesum:
             out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=f.device)
@@ -469,10 +519,11 @@ class CspOp(_Op):
     _destroy = "atl_csp_destroy"
 
     def __init__(self, *, ny, nx, time, lon, lat, solar_src, technology, r_irradiance, altitude, azimuth,
-                 efficiency, time_shift="0h", dni_altitude_threshold=3.75, device=None):
+                 efficiency, time_shift="0h", dni_altitude_threshold=3.75, device=None, pitch=0):
         lib = _lib.load()
         self.device = current_device() if device is None else device
         self.ny, self.nx = ny, nx
+        self.pitch = int(pitch) or nx
         self._time = time_ns(time)
         self._lon, self._lat = _lib.as_f64(lon), _lib.as_f64(lat)
         self._alt, self._az, self._eff = _lib.as_f64(altitude), _lib.as_f64(azimuth), _lib.as_f64(efficiency)
@@ -482,6 +533,7 @@ class CspOp(_Op):
         cfg.time_shift_ns = int(pd.to_timedelta(time_shift).value)
         cfg.lon_deg, cfg.lat_deg = _lib.ptr(self._lon).value, _lib.ptr(self._lat).value
         cfg.solar_src = solar_src
+        cfg.pitch = int(pitch)
         cfg.technology = technology
         cfg.r_irradiance = float(r_irradiance)
         cfg.dni_altitude_threshold_deg = float(dni_altitude_threshold)
@@ -500,11 +552,11 @@ class CspOp(_Op):
             if a is None:
                 setattr(f, n, None)
             elif host:
-                a = np.ascontiguousarray(a) if (n != "influx_direct" and np.asarray(a).dtype == np.float64) else host_f32(a)
+                a = self._host(a, f64_ok=n != "influx_direct")
                 keep.append(a)
                 setattr(f, n, a.ctypes.data)
             else:
-                a = a.contiguous()
+                a = self._dev(a, f64_ok=n != "influx_direct")
                 keep.append(a)
                 setattr(f, n, a.data_ptr())
         return f, keep

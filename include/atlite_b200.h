@@ -28,6 +28,12 @@
  *     (the cutout's NetCDF layout).  A "slab" covers time
  *     steps [t0, t0+nt) of the operator's time axis and its pointers address
  *     the slab's first step.
+ *   - `pitch` (0 = nx): elements per stored row of the DEVICE input fields.  A
+ *     device-resident cutout whose width is not a multiple of 4 may be stored
+ *     row-padded (pitch = round_up(nx, 4), padding contents arbitrary) so that
+ *     the 128-bit kernels apply; operator and plan must be created with the same
+ *     pitch.  Host entry points (*_reduce_host) always take unpadded arrays
+ *     (pitch = nx operators); per-cell OUTPUTS are never padded.
  *   - Pointers named *_dev are device pointers on the operator's device, those
  *     named *_host are host pointers.  Small tables (coordinates, time axis,
  *     power curve) are always host pointers and are copied at create time.
@@ -55,7 +61,7 @@ extern "C" {
 #define ATL_ERR_CUDA (-2)    /* CUDA runtime error (see atl_last_error) */
 #define ATL_ERR_NOMEM (-3)
 
-#define ATL_ABI_VERSION 2
+#define ATL_ABI_VERSION 3
 
 int atl_abi_version(void);
 const char* atl_last_error(void);
@@ -80,6 +86,8 @@ typedef struct {
   int64_t n_slots;        /* distinct (tile, bus) pairs                 */
   double slots_per_active_tile;
   int32_t fused;          /* 1: fused tile path, 0: two-pass CSR fallback */
+  int32_t pitch;          /* row pitch of the input fields (elements), >= nx */
+  int32_t vec;            /* 1: 128-bit lane layout (pitch % 4 == 0), 0: scalar */
 } AtlPlanInfo;
 
 /* indptr/indices/data: host CSR arrays (scipy layout), column index
@@ -87,6 +95,9 @@ typedef struct {
 int atl_plan_create(int device, int32_t ny, int32_t nx, int32_t n_bus,
                     const int64_t* indptr_host, const int32_t* indices_host,
                     const double* data_host, AtlPlan** plan_out);
+int atl_plan_create_pitched(int device, int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus,
+                            const int64_t* indptr_host, const int32_t* indices_host,
+                            const double* data_host, AtlPlan** plan_out);
 int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info_out);
 /* Host-only view of the tiling (no CUDA needed; used by the CPU tests and for
  * inspection): fills *info_out; when the three output arrays are given
@@ -140,6 +151,7 @@ typedef struct {
   double panel[16];
   int32_t output;             /* ATL_OUT_*; panel[] is ignored unless ATL_OUT_PANEL */
   double thermal[3];          /* ATL_OUT_SOLAR_THERMAL: c0, c1, t_store in deg C  */
+  int32_t pitch;              /* row pitch of the device fields, 0 = nx            */
 } AtlPvConfig;
 
 typedef struct { /* device pointers to (nt_slab, ny, nx) slabs; unused = NULL */
@@ -182,6 +194,7 @@ typedef struct {
   int32_t n_knots;         /* <= 255 */
   const double* V;         /* host, n_knots, non-decreasing (resource.py:346-355) */
   const double* POW_norm;  /* host, n_knots: POW / P  (convert.py:649)            */
+  int32_t pitch;           /* row pitch of the device fields, 0 = nx              */
 } AtlWindConfig;
 
 typedef struct {
@@ -207,6 +220,7 @@ typedef struct {
   int32_t ny, nx;
   double threshold_c, a, constant; /* convert.py:413-418 (threshold in deg C) */
   int32_t cooling;                 /* 1: a * (Tmean - threshold), convert.py:475-491 */
+  int32_t pitch;                   /* row pitch of the device field, 0 = nx            */
 } AtlHeatConfig;
 
 typedef struct AtlHeatOp AtlHeatOp;
@@ -239,7 +253,8 @@ typedef struct {
   int32_t nan_to_zero;
   int32_t poly;
   double sink, c0, c1, c2;
-  const float* cell_scale; /* host, ny*nx, or NULL */
+  const float* cell_scale; /* host, ny*nx (unpadded), or NULL */
+  int32_t pitch;           /* row pitch of the device field, 0 = nx */
 } AtlPointwiseConfig;
 
 typedef struct AtlPointwiseOp AtlPointwiseOp;
@@ -275,6 +290,7 @@ typedef struct {
   const double* altitude_rad;  /* host, n_alt, increasing */
   const double* azimuth_rad;   /* host, n_az, increasing */
   const double* efficiency;    /* host, n_alt * n_az row-major, p.u. */
+  int32_t pitch;               /* row pitch of the device fields, 0 = nx */
 } AtlCspConfig;
 
 typedef struct {

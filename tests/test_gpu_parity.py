@@ -510,10 +510,59 @@ def test_time_slab_offsets(ds_full, shapes):
 
     dev = ab.Cutout(data=ds_full).to_device()
     spec = _PvSpec(dev.data, ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
-    plan = engine.get_plan(shapes, 45, 70)
+    assert spec.pitch == 72  # to_device() pads 70-wide rows to the next multiple of 4
+    plan = engine.get_plan(shapes, 45, 70, pitch=spec.pitch)
     whole = spec.op.reduce(plan, spec.fields).cpu().numpy()
     part = spec.op.reduce(plan, {k: v[30:61] for k, v in spec.fields.items()}, t0=30, nt=31).cpu().numpy()
     np.testing.assert_allclose(part, whole[30:61], rtol=2e-5, atol=1e-6)
+
+
+def test_padded_rows_equal_unpadded_and_padding_is_never_read_into_results(ds_full, shapes):
+    """Device layout with a row pitch (to_device pads 70 -> 72 so the 128-bit lane
+    layout applies) against the unpadded layout (scalar lane layout): same values
+    for bus reductions, per-cell cubes and time sums, for every operator family;
+    NaN written into the padding columns must not reach any result."""
+    import torch
+
+    host = ab.Cutout(data=ds_full)
+    flat, padded = host.to_device(pad=False), host.to_device()
+    assert flat.data.raw("temperature").shape[-1] == 70 and padded.data.raw("temperature").shape[-1] == 72
+    for n in padded.data.data_vars:
+        padded.data.raw(n)[..., 70:] = float("nan")
+    calls = [
+        ("pv", dict(panel="CSi", orientation="latitude_optimal")),
+        ("pv", dict(panel="CdTe", orientation={"slope": 30.0, "azimuth": 180.0}, tracking="vertical")),
+        ("wind", dict(turbine="Vestas_V112_3MW")),
+        ("heat_demand", dict(hour_shift=2.0)),
+        ("temperature", {}),
+        ("irradiation", dict(orientation="latitude_optimal")),
+        ("csp", dict(installation="SAM_solar_tower")),
+    ]
+    for name, kw in calls:
+        for extra in (dict(matrix=shapes, aggregate_time=None), dict(aggregate_time=None), dict(aggregate_time="sum")):
+            a = np.asarray(getattr(flat, name)(**kw, **extra).values)
+            b = np.asarray(getattr(padded, name)(**kw, **extra).values)
+            assert a.shape == b.shape and not np.isnan(b).any(), (name, extra)
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-5 * max(1.0, np.abs(a).max()), err_msg=name)
+    # the tiling really differs: vec plan for the padded layout, scalar for the flat one
+    assert engine.get_plan(shapes, 45, 70, pitch=72).info["vec"] == 1
+    assert engine.get_plan(shapes, 45, 70).info["vec"] == 0
+    torch.cuda.synchronize()
+
+
+def test_field_shape_and_dtype_are_checked_before_the_raw_pointer_call(ds_full, shapes):
+    import torch
+    from atlite_b200.convert import _WindSpec
+
+    dev = ab.Cutout(data=ds_full).to_device()
+    spec = _WindSpec(dev.data, ab.get_windturbineconfig("Vestas_V112_3MW"))
+    plan = engine.get_plan(shapes, 45, 70, pitch=spec.pitch)
+    with pytest.raises(ValueError, match="expected"):
+        spec.op.reduce(plan, spec.wnd[:, :, :70], spec.aux[:, :, :70] if spec.aux is not None else None)
+    with pytest.raises(TypeError, match="float32"):
+        spec.op.reduce(plan, spec.wnd.double(), spec.aux.double() if spec.aux is not None else None)
+    with pytest.raises(RuntimeError):  # plan built for another pitch
+        spec.op.reduce(engine.get_plan(shapes, 45, 70), spec.wnd, spec.aux)
 
 
 # ------------------------------------------------------------------ size-independent properties

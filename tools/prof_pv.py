@@ -3,7 +3,8 @@
 
     ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat] [small|big] [reps]
 
-small = 200x200x8760 -> 100 shapes (bench workload); big = 1440x720x438 -> 3000 shapes.
+small = 200x200x8760 -> 100 shapes (bench workload); big = 1440x720x438 -> 3000 shapes;
+odd = 201x199x8760 unpadded (scalar lanes); oddpad = the same with rows padded to 204.
 Prints one JSON line with the median CUDA-event time and achieved GB/s.
 """
 import json
@@ -27,14 +28,18 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
 dev = torch.device("cuda", 0)
 if size == "small":
     nx, ny, nt, nbus, x0, y0 = 200, 200, 8760, 100, 0.0, 30.0
-elif size == "odd":  # nx % 4 != 0 -> SCALAR lane layout
+elif size in ("odd", "oddpad"):  # nx % 4 != 0: SCALAR lane layout / rows padded to pitch 204 (VEC)
     nx, ny, nt, nbus, x0, y0 = 201, 199, 8760, 100, 0.0, 30.0
 else:
     nx, ny, nt, nbus, x0, y0 = 1440, 720, 432, 3000, -180.0, -90.0
 x, y = syn.make_coords(nx, ny, x0, y0)
 tm = syn.make_time(nt + 24 * 170)[24 * 170:] if size == "big" else syn.make_time(nt)
-plan = engine.get_plan(syn.make_shapes(nx, ny, nbus), ny, nx)
 f = syn.make_pv_fields_device(tm, x, y, dev, seed=7)
+pitch = nx
+if size == "oddpad":  # what Cutout.to_device() does
+    pitch = nx + (-nx) % 4
+    f = {k: torch.nn.functional.pad(v, (0, pitch - nx)).contiguous() for k, v in f.items()}
+plan = engine.get_plan(syn.make_shapes(nx, ny, nbus), ny, nx, pitch=pitch)
 coords = dict(time=tm, x=x, y=y, lon=x, lat=y)
 if kind == "pv":
     spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
