@@ -187,6 +187,7 @@ _SIGNATURES = {
     "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
     "atl_wind_create": (C.c_int, [C.c_int, C.POINTER(WindConfig), C.POINTER(_P)]),
+    "atl_wind_curve_eval_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
     "atl_wind_destroy": (None, [_P]),
     "atl_wind_reduce": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, _P]),
     "atl_wind_cells": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),

@@ -323,6 +323,69 @@ __device__ __forceinline__ void reduce_slots2(const float (&v0)[4], const float 
     if ((lane & 15) == 0) atomicAdd(my_row + __ldg(rp), keep);
   }
 }
+
+// Four slots x two time steps in ONE transposed butterfly: 9 shuffles for 8 sums
+// instead of 20, and one atomic instruction (8 active lanes) instead of four.
+// Lane L ends up holding the sum of step (L >> 4) for slot f = (L >> 2) & 3 of the
+// group.  It evaluates the group's slots in the order f, f^1, f^2, f^3, so at the
+// xor-8 stage it keeps positions 0,1 and receives its partner's positions 2,3 (the
+// partner's f differs in bit 1: those ARE slots f, f^1), at xor-4 it keeps
+// position 0 and receives the partner's position 1 -- no selects anywhere.  The
+// step split (xor 16) is folded into which of v0/v1 a lane treats as "keep".
+// A group may run past the tile's last slot (2 or 3 left): those weight vectors
+// belong to the next tile (or the zero padding of the array); their sums live in
+// separate accumulators and are dropped.  A single left-over slot takes the
+// pairwise path.
+__device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float (&v1)[4],
+                                               int s_beg, int s_end, const PlanDev& plan,
+                                               float* __restrict__ out_row0, int lane) {
+  const float chk = ((v0[0] + v0[1]) + (v0[2] + v0[3])) + ((v1[0] + v1[1]) + (v1[2] + v1[3]));
+  const bool bad = !(fabsf(chk) <= 3.0e38f);
+  if (__any_sync(0xffffffffu, bad)) {
+    reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s_beg, s_end, plan, out_row0, lane);
+    reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s_beg, s_end, plan, out_row0 + plan.n_bus,
+                       lane);
+    return;
+  }
+  const bool hi = lane >= 16;
+  float* const my_row = out_row0 + (hi ? plan.n_bus : 0);
+  float vk[4], vs[4];  // the step this half-warp keeps / sends
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    vk[i] = hi ? v1[i] : v0[i];
+    vs[i] = hi ? v0[i] : v1[i];
+  }
+  const int f = (lane >> 2) & 3;
+  int s = s_beg;
+#pragma unroll 1
+  for (; s_end - s >= 2; s += 4) {
+    const float4* wp = plan.slot_w4 + (size_t)s * 32 + lane;
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 w = __ldg(wp + (f ^ i) * 32);
+      a[i] = fmaf(w.x, vk[0], fmaf(w.y, vk[1], fmaf(w.z, vk[2], w.w * vk[3])));
+      b[i] = fmaf(w.x, vs[0], fmaf(w.y, vs[1], fmaf(w.z, vs[2], w.w * vs[3])));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] += __shfl_xor_sync(0xffffffffu, b[i], 16);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[2], 8);
+    a[1] += __shfl_xor_sync(0xffffffffu, a[3], 8);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[1], 4);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(plan.slot_row + s + f), a[0]);
+  }
+  if (s < s_end) {  // one slot left
+    const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
+    float keep = fmaf(w.x, vk[0], fmaf(w.y, vk[1], fmaf(w.z, vk[2], w.w * vk[3])));
+    const float send = fmaf(w.x, vs[0], fmaf(w.y, vs[1], fmaf(w.z, vs[2], w.w * vs[3])));
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((lane & 15) == 0) atomicAdd(my_row + __ldg(plan.slot_row + s), keep);
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace atl

@@ -38,7 +38,7 @@ namespace atl {
 // physics so that B x (#fields) 16-byte loads per lane cover the HBM latency
 // (PV: 2 x 5, wind: 4 x 2, SpMM: 4 x 1).  MINB = CTAs/SM the register allocator
 // must allow.
-template <class Phys, int B, int MINB>
+template <class Phys, int B, int MINB, int G = 0>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
     k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
                    float* __restrict__ out, int nt, int tb) {
@@ -80,8 +80,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
         sb += B * S4;
       }
 #pragma unroll
-      for (int j = 0; j + 1 < B; j += 2)
-        reduce_slots2(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+      for (int j = 0; j + 1 < B; j += 2) {
+        if (G)  // slots in groups of four (transposed butterfly)
+          reduce_slots2g(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+        else
+          reduce_slots2(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+      }
       if (B & 1) reduce_slots(v[B - 1], s_beg, s_end, plan, out + (size_t)(t + B - 1) * nb, lane);
     }
   }
@@ -216,14 +220,17 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
   dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
   const size_t smem = Phys::kSmemFloats * sizeof(float);
   const GridDev gd = plan->grid;
-#define ATL_LAUNCH_FUSED(B, MINB) \
-  k_fused_reduce<Phys, B, MINB><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb)
+#define ATL_LAUNCH_FUSED(B, MINB, ...) \
+  k_fused_reduce<Phys, B, MINB, ##__VA_ARGS__><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb)
   switch (tuning().variant) {  // experiments; 0 = the functor's own choice
     case 1: ATL_LAUNCH_FUSED(1, 8); break;
     case 2: ATL_LAUNCH_FUSED(2, 6); break;
     case 3: ATL_LAUNCH_FUSED(4, 6); break;
     case 4: ATL_LAUNCH_FUSED(4, 8); break;
     case 5: ATL_LAUNCH_FUSED(2, 4); break;
+    case 6: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 1); break;
+    case 7: ATL_LAUNCH_FUSED(2, 5, 1); break;
+    case 8: ATL_LAUNCH_FUSED(4, 6, 1); break;
     default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks); break;
   }
 #undef ATL_LAUNCH_FUSED

@@ -335,7 +335,10 @@ int atl_plan_create_pitched(int device, int32_t ny, int32_t nx, int32_t pitch, i
     PLAN_CUDA(cudaMalloc((void**)&p->d_slot_row, std::max<size_t>(T.slot_row.size(), 1) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_slot_row, T.slot_row.data(), T.slot_row.size() * 4,
                          cudaMemcpyHostToDevice));
-    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, std::max<size_t>(T.w.size(), 4) * 4));
+    // + 3 zero slots: the grouped reduce (reduce_slots2g) reads up to 3 weight
+    // vectors past a tile's last slot (their sums are discarded)
+    PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, (T.w.size() + 3 * 128) * 4));
+    PLAN_CUDA(cudaMemset(p->d_slot_w4, 0, (T.w.size() + 3 * 128) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_slot_w4, T.w.data(), T.w.size() * 4, cudaMemcpyHostToDevice));
     PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(T.active.size(), 1) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_active, T.active.data(), T.active.size() * 4,

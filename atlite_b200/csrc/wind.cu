@@ -12,74 +12,112 @@
 
 namespace atl {
 
-// Power curve in shared memory (NK = power of two > n_knots):
-//   xcmp[NK]   knot abscissae rounded UP to float -> `xcmp[j] <= x` is exactly the
-//              float64 comparison `V[j] <= x` of numpy's binary search for a float
-//              x; padded with +inf so a branch-free binary search counts the
-//              knots <= x
+// Power curve in shared memory.
+//
+// LUT mode (every shipped turbine; the host decides): a uniform grid of NB buckets on
+// [V0, Vn-1], shifted by half a bucket, in which every bucket holds at most ONE
+// distinct knot value, none within 1e-3 of a bucket edge.  One float4 per bucket,
+//   {k, y(k), slope below k, slope from k on}
+// k = the bucket's knot rounded UP to float (so `x >= k` is exactly the float64
+// comparison `x >= V[j]` numpy's search does for a float x), or the bucket centre
+// when it has no knot (both slopes equal).  The curve stored is the CONTINUOUS
+// one: np.interp's jumps at duplicate knots (cut-in step, the appended cut-out) are
+// taken out on the host and put back by two selects -- at most one interior jump
+// plus the one at the last knot, else the fallback.  So a cell costs one 16-byte
+// shared-memory load.  For NB <= 128 the table is replicated 8x, entry (b, lane%8),
+// which makes the 128-bit loads bank-conflict free for arbitrary bucket patterns
+// (a quarter-warp's 8 lanes hit 8 different 16-byte bank groups).
+//
+// Fallback (NK = power of two > n_knots):
+//   xcmp[NK]   knot abscissae rounded UP to float, padded with +inf so a
+//              branch-free binary search counts the knots <= x
 //   seg[NK+1]  float4 {x0, f0, slope, -} indexed by that COUNT c: c = 0 -> left
 //              clamp f[0]; 1 <= c < n -> segment [V[c-1], V[c]) with x0 = V[c-1]
 //              (nearest float), slope = 0 on zero-width (duplicate-knot)
 //              segments; c >= n -> right clamp f[n-1]      (np.interp semantics)
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
+// One LUT lookup; the SAME function evaluates on the host for the CPU tests
+// (atl_wind_curve_eval_host), with the PTX clamp / floor spelled out.
+__host__ __device__ __forceinline__ float lut_interp(float x, const char* lut, int stride,
+                                                     float x_lo, float x_hi, float inv_w, float c0,
+                                                     float k_jump, float jump, float k_end,
+                                                     float y_end) {
+#ifdef __CUDA_ARCH__
+  // NaN-propagating clamp: a NaN speed picks bucket 0 and comes out NaN
+  const float xc = fmin_nan(fmax_nan(x, x_lo), x_hi);
+  const int b = __float2int_rd(fmaf(xc, inv_w, c0));
+#else
+  const float xc = (x != x) ? x : std::fmin(std::fmax(x, x_lo), x_hi);
+  const int b = (x != x) ? 0 : (int)std::floor(std::fmaf(xc, inv_w, c0));
+#endif
+  const float4 e = *reinterpret_cast<const float4*>(lut + b * stride);
+  const float sl = (x >= e.x) ? e.w : e.z;
+  float y = fmaf(sl, xc - e.x, e.y);
+  y = (x >= k_jump) ? y + jump : y;
+  return (x >= k_end) ? y_end : y;
+}
+
 template <bool VEC>
 struct WindPhys {
   static constexpr bool kVec = VEC;
   using Geom = TileGeomT<VEC>;
   const float* wnd;
   const float* aux;
-  const float* curve;  // device, 4 * NK floats
+  const float* curve;  // device: the LUT, or xcmp | seg for the fallback
   int64_t S;
   int method;
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
-  int use_lut, n_stage;  // LUT mode: the bucket table follows xcmp | seg in `curve`
-  float inv_w;
+  int use_lut, n_stage;
+  float inv_w, c0;        // bucket = floor(x * inv_w + c0)
+  int lut_stride, rep_mask;  // bytes between buckets; lane & rep_mask picks the replica
+  float k_jump, jump;     // interior jump: y += jump for x >= k_jump (+inf: none)
+  float k_end, y_end;     // x >= k_end -> y_end (right clamp, incl. the cut-out step)
 
-  struct Cell {};
+  struct Cell {
+    int rep_off;  // byte offset of this lane's replica inside a bucket's entries
+  };
   struct Raw {
     float w[4], a[4];
   };
-  static constexpr int kSmemFloats = 256 + 4 * 257 + 2 * 1025 + 2;  // xcmp | seg | LUT (<= 1025 x 8 B)
+  // LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; fallback: 256 + 4*257
+  static constexpr int kSmemFloats = 4 * 129 * 8;
   static constexpr int kBatch = 2, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
     for (int i = threadIdx.x; i < n_stage; i += blockDim.x) smem[i] = curve[i];
     __syncthreads();
   }
-  __device__ void init(Cell&, const Geom&, const float*) const {}
+  __device__ void init(Cell& c, const Geom&, const float*) const {
+    c.rep_off = ((threadIdx.x & 31) & rep_mask) * 16;
+  }
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
     load4(wnd, tb, g, r.w);
     if (method != ATL_WIND_NONE) load4(aux, tb, g, r.a);
   }
-  // np.interp for the lane's 4 values at once: find cnt = #knots <= x, then
-  // evaluate segment seg[cnt].  `xcmp[j] <= x` with xcmp rounded UP to float is
-  // exactly NumPy's float64 comparison, so the same segment is selected --
-  // including duplicate knots (cut-out) and the clamped ends.
-  //  LUT mode (the normal case): a uniform grid on [V0, Vn-1], shifted by half a
-  //  bucket, in which every bucket holds at most ONE distinct knot value, none
-  //  within 1e-3 of a bucket edge (host-checked; else the fallback).  A bucket
-  //  stores that knot (rounded up) and the segment offsets for x below / from it
-  //  on: one 8-byte load, one compare, one 16-byte load.
-  //  Fallback: branch-free binary search, the four searches in lock step.
-  __device__ __forceinline__ void interp4(const float (&x)[4], float (&r)[4], const float* sm) const {
-    const float* xcmp = sm;
-    const float4* seg = reinterpret_cast<const float4*>(sm + NK);
+  // np.interp for the lane's 4 values at once.
+  __device__ __forceinline__ void interp4(const Cell& c, const float (&x)[4], float (&r)[4],
+                                          const float* sm) const {
     if (use_lut) {
-      const float2* lut = reinterpret_cast<const float2*>(sm + NK + 4 * (NK + 1));
+      const char* lut = reinterpret_cast<const char*>(sm) + c.rep_off;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
-        const int b = __float2int_rd(fmaf(xc - x_lo, inv_w, 0.5f));
-        const float2 e = lut[b];  // {knot inside the bucket (+inf if none), packed seg offsets}
-        const unsigned pk = __float_as_uint(e.y);
-        const unsigned off = (x[i] >= e.x) ? (pk >> 16) : (pk & 0xffffu);  // bytes into seg[]
-        const float4 s = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(seg) + off);
-        const float y = fmaf(s.z, xc - s.x, s.y);
-        r[i] = (x[i] != x[i]) ? x[i] : y;
-      }
+      for (int i = 0; i < 4; ++i)
+        r[i] = lut_interp(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
       return;
     }
+    const float* xcmp = sm;
+    const float4* seg = reinterpret_cast<const float4*>(sm + NK);
     int cnt[4] = {0, 0, 0, 0};  // number of knots <= x  (NaN compares false -> 0)
 #pragma unroll 1
     for (int step = NK >> 1; step >= 1; step >>= 1) {
@@ -93,10 +131,10 @@ struct WindPhys {
       // clamp keeps inf * 0 out of the clamped ends; NaN is restored below
       const float xc = fminf(fmaxf(x[i], x_lo), x_hi);
       const float y = fmaf(s.z, xc - s.x, s.y);
-      r[i] = (x[i] != x[i]) ? x[i] : y;
+      r[i] = (x[i] != x[i] && n_knots > 1) ? x[i] : y;  // np.interp: one knot -> constant, even for NaN
     }
   }
-  __device__ void compute(const Cell&, const Geom&, int, const Raw& r, float (&v)[4],
+  __device__ void compute(const Cell& c, const Geom&, int, const Raw& r, float (&v)[4],
                           const float* sm) const {
     float x[4];
 #pragma unroll
@@ -104,13 +142,14 @@ struct WindPhys {
       x[i] = r.w[i];
       if (method == ATL_WIND_LOG) {
         // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
+        // (not rewritten as v + v*c/(..): z0 = 0 must give NaN = inf/inf like the reference)
         const float L = __log2f(r.a[i]);
         x[i] = x[i] * __fdividef(lg2_to - L, lg2_from - L);
       } else if (method == ATL_WIND_POWER) {
         x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
     }
-    interp4(x, v, sm);
+    interp4(c, x, v, sm);
   }
 };
 
@@ -126,7 +165,9 @@ struct AtlWindOp {
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
   int use_lut, n_stage;
-  float inv_w;
+  float inv_w, c0;
+  int lut_stride, rep_mask;
+  float k_jump, jump, k_end, y_end;
   float* d_curve = nullptr;
 };
 
@@ -148,6 +189,13 @@ static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
   p.use_lut = op->use_lut;
   p.n_stage = op->n_stage;
   p.inv_w = op->inv_w;
+  p.c0 = op->c0;
+  p.lut_stride = op->lut_stride;
+  p.rep_mask = op->rep_mask;
+  p.k_jump = op->k_jump;
+  p.jump = op->jump;
+  p.k_end = op->k_end;
+  p.y_end = op->y_end;
   return p;
 }
 
@@ -158,30 +206,30 @@ static int check_fields(const AtlWindOp* op, const AtlWindFields* f) {
   return ATL_OK;
 }
 
-extern "C" {
+// Host-side tables of a power curve (shared by atl_wind_create and the host
+// evaluator atl_wind_curve_eval_host the CPU tests use).
+struct CurveTables {
+  std::vector<float> curve;
+  int n_knots = 0, NK = 0, use_lut = 0, lut_stride = 16, rep_mask = 0;
+  float x_lo = 0.f, x_hi = 0.f, inv_w = 0.f, c0 = 0.f;
+  float k_jump = INFINITY, jump = 0.f, k_end = 0.f, y_end = 0.f;
+};
 
-int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
-  ATL_REQUIRE(cfg && op_out, "NULL argument");
-  *op_out = nullptr;
-  ATL_REQUIRE(cfg->ny > 0 && cfg->nx > 0, "bad grid");
-  ATL_REQUIRE(cfg->n_knots >= 1 && cfg->n_knots <= 255, "n_knots must be in [1, 255]");
-  ATL_REQUIRE(cfg->V && cfg->POW_norm, "power curve missing");
-  ATL_REQUIRE(cfg->method >= ATL_WIND_NONE && cfg->method <= ATL_WIND_POWER, "bad method");
-  for (int i = 1; i < cfg->n_knots; ++i)
-    ATL_REQUIRE(cfg->V[i] >= cfg->V[i - 1], "wind speed knots must be non-decreasing");
-  if (cfg->method != ATL_WIND_NONE)
-    ATL_REQUIRE(cfg->from_height > 0 && cfg->to_height > 0, "heights must be positive");
-
+static int build_curve(const double* V, const double* POW, int n, CurveTables& T,
+                       bool force_fallback = false) {
+  ATL_REQUIRE(n >= 1 && n <= 255, "n_knots must be in [1, 255]");
+  ATL_REQUIRE(V && POW, "power curve missing");
+  for (int i = 1; i < n; ++i)
+    ATL_REQUIRE(V[i] >= V[i - 1], "wind speed knots must be non-decreasing");
   int NK = 2;  // strictly more slots than knots: the search counts up to NK-1
-  while (NK <= cfg->n_knots) NK <<= 1;
+  while (NK <= n) NK <<= 1;
   // xcmp[NK] followed by seg[NK + 1] (float4), see WindPhys; NK * 4 bytes keeps
   // the float4 part 16-byte aligned (NK >= 4)
   if (NK < 4) NK = 4;
   std::vector<float> curve((size_t)NK + 4 * ((size_t)NK + 1), 0.f);
-  const int n = cfg->n_knots;
   for (int j = 0; j < NK; ++j) {
     if (j < n) {
-      const double x = cfg->V[j];
+      const double x = V[j];
       float xc = (float)x;
       if ((double)xc < x) xc = nextafterf(xc, INFINITY);  // round up
       curve[j] = xc;
@@ -193,90 +241,171 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
   for (int c = 0; c <= NK; ++c) {
     float x0 = 0.f, f0 = 0.f, sl = 0.f;
     if (c == 0) {
-      x0 = (float)cfg->V[0];
-      f0 = (float)cfg->POW_norm[0];
+      x0 = (float)V[0];
+      f0 = (float)POW[0];
     } else if (c >= n) {
-      x0 = (float)cfg->V[n - 1];
-      f0 = (float)cfg->POW_norm[n - 1];
+      x0 = (float)V[n - 1];
+      f0 = (float)POW[n - 1];
     } else {
       const int j = c - 1;
-      x0 = (float)cfg->V[j];
-      f0 = (float)cfg->POW_norm[j];
-      if (cfg->V[j + 1] > cfg->V[j])
-        sl = (float)((cfg->POW_norm[j + 1] - cfg->POW_norm[j]) / (cfg->V[j + 1] - cfg->V[j]));
+      x0 = (float)V[j];
+      f0 = (float)POW[j];
+      if (V[j + 1] > V[j])
+        sl = (float)((POW[j + 1] - POW[j]) / (V[j + 1] - V[j]));
     }
     seg[4 * c + 0] = x0;
     seg[4 * c + 1] = f0;
     seg[4 * c + 2] = sl;
     seg[4 * c + 3] = 0.f;
   }
-  // ---- uniform-bucket LUT (see interp4)
-  int use_lut = 0;
-  float inv_w = 0.f;
+  // ---- uniform-bucket LUT (see the comment above WindPhys)
+  auto ceil_f = [](double v) {
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+  };
+  int use_lut = 0, lut_stride = 16, rep_mask = 0;
+  float inv_w = 0.f, c0 = 0.f;
+  float k_jump = INFINITY, jump = 0.f;
+  const float k_end = ceil_f(V[n - 1]), y_end = (float)POW[n - 1];
   {
-    const double lo = cfg->V[0], hi = cfg->V[n - 1];
-    for (int NB = 32; NB <= 1024 && !use_lut && hi > lo; NB *= 2) {
+    const double lo = V[0], hi = V[n - 1];
+    // jumps of np.interp: a run of equal knots a..z with POW[a] != POW[z]
+    int n_interior = 0, jump_first = n;  // knots with index > jump_first sit above the jump
+    double Kj = 0.0, J = 0.0;
+    for (int a = 0; a < n;) {
+      int z = a;
+      while (z + 1 < n && V[z + 1] == V[a]) ++z;
+      if (POW[z] != POW[a] && V[a] != hi) {
+        ++n_interior;
+        Kj = V[a];
+        J = POW[z] - POW[a];
+        jump_first = a;
+      }
+      a = z + 1;
+    }
+    auto adj = [&](int j) { return POW[j] - (j > jump_first ? J : 0.0); };
+    auto slope = [&](int j) {  // of segment [V[j], V[j+1]); 0 on zero-width segments
+      return (j + 1 < n && V[j + 1] > V[j])
+                 ? (POW[j + 1] - POW[j]) / (V[j + 1] - V[j])
+                 : 0.0;
+    };
+    for (int NB = 32; NB <= 1024 && !use_lut && hi > lo && n_interior <= 1 && !force_fallback;
+         NB *= 2) {
       const double wdt = (hi - lo) / NB;
       std::vector<int> bucket_of(n);
       std::vector<double> knot_in((size_t)NB + 1, std::nan(""));
       bool ok = true;
       for (int j = 0; j < n && ok; ++j) {
-        const double pos = (cfg->V[j] - lo) / wdt + 0.5;
+        const double pos = (V[j] - lo) / wdt + 0.5;
         const int b = (int)std::floor(pos);
         const double frac = pos - b;
         if (b < 0 || b > NB || frac < 1e-3 || frac > 1.0 - 1e-3) ok = false;
-        else if (!std::isnan(knot_in[b]) && knot_in[b] != cfg->V[j]) ok = false;  // 2 distinct knots
+        else if (!std::isnan(knot_in[b]) && knot_in[b] != V[j]) ok = false;  // 2 distinct knots
         else {
-          knot_in[b] = cfg->V[j];
+          knot_in[b] = V[j];
           bucket_of[j] = b;
         }
       }
       if (!ok) continue;
-      const size_t base = curve.size();  // NK + 4 (NK + 1): even, so the float2 table is 8-byte aligned
-      curve.resize(base + 2 * ((size_t)NB + 1), 0.f);
-      int c_lo = 0;  // knots in buckets < b
+      const int R = NB <= 128 ? 8 : 1;
+      std::vector<float> lut((size_t)(NB + 1) * R * 4);
+      int c_lo = 0;  // knots in buckets < b  ==  the segment index left of this bucket's knot
       for (int b = 0; b <= NB; ++b) {
         int c_hi = c_lo;
         while (c_hi < n && bucket_of[c_hi] == b) ++c_hi;
-        float thr = INFINITY;
-        if (!std::isnan(knot_in[b])) {
-          thr = (float)knot_in[b];
-          if ((double)thr < knot_in[b]) thr = nextafterf(thr, INFINITY);  // round up
+        float e[4];
+        if (c_hi > c_lo) {  // bucket with a knot K = V[c_lo] = ... = V[c_hi-1]
+          const double K = V[c_lo];
+          const double sA = c_lo == 0 ? 0.0 : slope(c_lo - 1);
+          const double sB = c_hi >= n ? 0.0 : slope(c_hi - 1);
+          e[0] = ceil_f(K);
+          e[1] = (float)(adj(c_lo) + sA * ((double)e[0] - K));
+          e[2] = (float)sA;
+          e[3] = (float)sB;
+        } else {  // inside segment c_lo - 1 (1 <= c_lo <= n-1): expand about the bucket centre
+          const int j = c_lo - 1;
+          const double sl = slope(j);
+          const float kc = (float)(lo + (b * wdt));
+          e[0] = kc;
+          e[1] = (float)(adj(j) + sl * ((double)kc - V[j]));
+          e[2] = e[3] = (float)sl;
         }
-        const uint32_t pk = ((uint32_t)(c_hi * 16) << 16) | (uint32_t)(c_lo * 16);
-        float pkf;
-        std::memcpy(&pkf, &pk, 4);
-        curve[base + 2 * (size_t)b] = thr;
-        curve[base + 2 * (size_t)b + 1] = pkf;
+        for (int r = 0; r < R; ++r) std::memcpy(&lut[((size_t)b * R + r) * 4], e, 16);
         c_lo = c_hi;
       }
       use_lut = 1;
+      lut_stride = 16 * R;
+      rep_mask = R - 1;
       inv_w = (float)(1.0 / wdt);
+      c0 = (float)(0.5 - lo / wdt);
+      if (n_interior) {
+        k_jump = ceil_f(Kj);
+        jump = (float)J;
+      }
+      curve.swap(lut);  // LUT mode stages the table only
     }
   }
 
+  T.curve.swap(curve);
+  T.n_knots = n;
+  T.NK = NK;
+  T.use_lut = use_lut;
+  T.lut_stride = lut_stride;
+  T.rep_mask = rep_mask;
+  T.x_lo = (float)V[0];
+  T.x_hi = (float)V[n - 1];
+  T.inv_w = inv_w;
+  T.c0 = c0;
+  T.k_jump = k_jump;
+  T.jump = jump;
+  T.k_end = k_end;
+  T.y_end = y_end;
+  return ATL_OK;
+}
+
+extern "C" {
+
+int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
+  ATL_REQUIRE(cfg && op_out, "NULL argument");
+  *op_out = nullptr;
+  ATL_REQUIRE(cfg->ny > 0 && cfg->nx > 0, "bad grid");
+  ATL_REQUIRE(cfg->method >= ATL_WIND_NONE && cfg->method <= ATL_WIND_POWER, "bad method");
+  if (cfg->method != ATL_WIND_NONE)
+    ATL_REQUIRE(cfg->from_height > 0 && cfg->to_height > 0, "heights must be positive");
+
+  CurveTables T;
+  if (int rc = build_curve(cfg->V, cfg->POW_norm, cfg->n_knots, T)) return rc;
+  const int n = T.n_knots;
   AtlWindOp* op = new AtlWindOp();
   op->device = device;
   ATL_REQUIRE(cfg->pitch == 0 || cfg->pitch >= cfg->nx, "pitch must be >= nx");
   op->grid = make_grid(cfg->ny, cfg->nx, cfg->pitch);
   op->method = cfg->method;
   op->n_knots = n;
-  op->NK = NK;
+  op->NK = T.NK;
   op->lg2_to = op->lg2_from = op->lg2_ratio = 0.f;
-  op->x_lo = (float)cfg->V[0];
-  op->x_hi = (float)cfg->V[n - 1];
-  op->use_lut = use_lut;
-  op->n_stage = (int)curve.size();
-  op->inv_w = inv_w;
+  op->x_lo = T.x_lo;
+  op->x_hi = T.x_hi;
+  op->use_lut = T.use_lut;
+  op->n_stage = (int)T.curve.size();
+  op->inv_w = T.inv_w;
+  op->c0 = T.c0;
+  op->lut_stride = T.lut_stride;
+  op->rep_mask = T.rep_mask;
+  op->k_jump = T.k_jump;
+  op->jump = T.jump;
+  op->k_end = T.k_end;
+  op->y_end = T.y_end;
   if (cfg->method != ATL_WIND_NONE) {
     op->lg2_to = (float)std::log2(cfg->to_height);
     op->lg2_from = (float)std::log2(cfg->from_height);
     op->lg2_ratio = (float)std::log2(cfg->to_height / cfg->from_height);
   }
   cudaError_t e = cudaSetDevice(device);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_curve, curve.size() * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_curve, T.curve.size() * 4);
   if (e == cudaSuccess)
-    e = cudaMemcpy(op->d_curve, curve.data(), curve.size() * 4, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(op->d_curve, T.curve.data(), T.curve.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     atl_wind_destroy(op);
     return cuda_fail(e, "atl_wind_create");
@@ -290,6 +419,33 @@ void atl_wind_destroy(AtlWindOp* op) {
   cudaSetDevice(op->device);
   cudaFree(op->d_curve);
   delete op;
+}
+
+int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_knots,
+                             int32_t force_fallback, const float* x, int64_t n, float* y_out,
+                             int32_t* used_lut_out) {
+  ATL_REQUIRE(x && y_out && n >= 0, "bad arguments");
+  CurveTables T;
+  if (int rc = build_curve(V, POW_norm, n_knots, T, force_fallback != 0)) return rc;
+  if (used_lut_out) *used_lut_out = T.use_lut;
+  // replicas must be identical copies; evaluate through a different one per element
+  for (int64_t i = 0; i < n; ++i) {
+    if (T.use_lut) {
+      const char* lut = reinterpret_cast<const char*>(T.curve.data()) + ((int)i & T.rep_mask) * 16;
+      y_out[i] = lut_interp(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0, T.k_jump,
+                            T.jump, T.k_end, T.y_end);
+      continue;
+    }
+    const float* xcmp = T.curve.data();
+    const float* seg = T.curve.data() + T.NK;
+    int cnt = 0;
+    for (int step = T.NK >> 1; step >= 1; step >>= 1)
+      if (xcmp[cnt + step - 1] <= x[i]) cnt += step;
+    const float* sg = seg + 4 * (cnt < T.n_knots ? cnt : T.n_knots);
+    const float xc = std::fmin(std::fmax(x[i], T.x_lo), T.x_hi);
+    y_out[i] = (x[i] != x[i] && T.n_knots > 1) ? x[i] : std::fmaf(sg[2], xc - sg[0], sg[1]);
+  }
+  return ATL_OK;
 }
 
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx) {

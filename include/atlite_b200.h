@@ -330,6 +330,13 @@ int atl_heat_reduce_host(const AtlHeatOp* op, const AtlPlan* plan,
 /* Introspection of operator handles (device, grid). */
 int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
                    int32_t* solar_src);
+/* Host-only: evaluates the power-curve interpolation exactly as the kernels do
+ * (same tables, same fp32 formula), no CUDA needed; the CPU tests compare it with
+ * np.interp.  force_fallback != 0 takes the binary-search tables; *used_lut_out
+ * (optional) tells which path the curve qualifies for. */
+int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_knots,
+                             int32_t force_fallback, const float* x, int64_t n, float* y_out,
+                             int32_t* used_lut_out);
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny, int32_t* nx);

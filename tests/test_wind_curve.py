@@ -1,0 +1,109 @@
+"""Power-curve interpolation tables (LUT and binary-search fallback) against np.interp.
+
+atl_wind_curve_eval_host builds the very tables atl_wind_create uploads and evaluates
+them with the same fp32 formula the kernels use (one shared __host__ __device__
+function), so the np.interp semantics the reference relies on (convert.py:648-649:
+clamped ends, duplicate knots = steps, NaN propagation) are pinned without a GPU.
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from atlite_b200 import _lib, resource
+
+
+def eval_host(V, P, x, force_fallback=False):
+    lib = _lib.load()
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    used = C.c_int32(-1)
+    _lib.check(lib.atl_wind_curve_eval_host(_lib.ptr(V), _lib.ptr(P), len(V), int(force_fallback),
+                                            x.ctypes.data, len(x), y.ctypes.data, C.byref(used)))
+    return y, used.value
+
+
+def probe_points(V, rng, n=20000):
+    v32 = V.astype(np.float32)
+    return np.concatenate([
+        rng.uniform(V[0] - 3.0, V[-1] + 10.0, n),
+        V, np.nextafter(v32, np.float32(np.inf)), np.nextafter(v32, np.float32(-np.inf)),
+        [np.nan, np.inf, -np.inf, 0.0, -0.0],
+    ]).astype(np.float32)
+
+
+def check(V, P, x, y, slope_scale):
+    want = np.interp(x.astype(np.float64), V, P)
+    assert np.array_equal(np.isnan(y), np.isnan(want))
+    ok = ~np.isnan(want)
+    # fp32 evaluation: a few ulp of the value plus ulp(x) * steepest slope
+    tol = 4e-7 * max(1.0, np.abs(P).max()) + 4e-6 * slope_scale
+    np.testing.assert_allclose(y[ok], want[ok], rtol=0, atol=tol)
+
+
+def steepest(V, P):
+    dv = np.diff(V)
+    return float(np.max(np.abs(np.diff(P)[dv > 0] / dv[dv > 0]))) if (dv > 0).any() else 0.0
+
+
+@pytest.mark.parametrize("name", sorted(resource.windturbines))
+def test_shipped_turbines_use_the_lut_and_match_np_interp(name):
+    t = resource.get_windturbineconfig(name)
+    V, P = t["V"], t["POW"] / t["P"]
+    x = probe_points(V, np.random.default_rng(1))
+    y, used = eval_host(V, P, x)
+    assert used == 1, "every shipped power curve should qualify for the single-load LUT"
+    check(V, P, x, y, steepest(V, P))
+    yf, used_f = eval_host(V, P, x, force_fallback=True)
+    assert used_f == 0
+    check(V, P, x, yf, steepest(V, P))
+    # exactly at float-representable knots: np.interp's value to one ulp of fp32 (a
+    # curve with a cut-in step is stored without the step and gets it added back)
+    yk, _ = eval_host(V, P, V.astype(np.float32))
+    if np.array_equal(V.astype(np.float32).astype(np.float64), V):
+        np.testing.assert_allclose(yk, np.interp(V, V, P), rtol=0, atol=1.2e-7 * np.abs(P).max())
+
+
+def test_smoothed_curve_and_steps():
+    t = resource.windturbine_smooth(resource.get_windturbineconfig("Vestas_V112_3MW"))
+    V, P = t["V"], t["POW"] / t["P"]
+    x = probe_points(V, np.random.default_rng(2))
+    y, used = eval_host(V, P, x)
+    check(V, P, x, y, steepest(V, P))
+    # cut-in step AND cut-out step AND a step at the very first knot
+    for V, P, lut in [
+        ([3, 3, 5, 12, 25, 25], [0, 0.1, 0.3, 1, 1, 0], 1),
+        ([0, 3, 3, 12, 25, 25], [0, 0, 0.2, 1, 1, 0], 1),
+        ([0, 3, 3, 12, 12, 25], [0, 0, 0.2, 0.9, 1, 1], 0),   # two interior steps -> fallback
+        ([2, 2, 2, 10, 25], [0, 0.5, 0.1, 1, 0.2], 1),         # triple knot, no cut-out step
+        ([4.0], [0.7], 0),                                     # single knot: constant
+    ]:
+        V, P = np.array(V, float), np.array(P, float)
+        x = probe_points(V, np.random.default_rng(3), 5000)
+        y, used = eval_host(V, P, x)
+        assert used == lut, (V, P)
+        check(V, P, x, y, steepest(V, P))
+
+
+@settings(max_examples=150, deadline=None)
+@given(
+    st.lists(st.floats(0.05, 3.0), min_size=1, max_size=40),
+    st.lists(st.floats(0.0, 1.0), min_size=41, max_size=41),
+    st.lists(st.integers(0, 39), max_size=3),
+    st.integers(0, 2**31 - 1),
+)
+def test_random_curves(steps, pows, dup_at, seed):
+    V = np.concatenate([[1.0], 1.0 + np.cumsum(steps)])
+    for d in dup_at:  # duplicate some knots (zero-width segments = steps)
+        if d + 1 < len(V):
+            V[d + 1] = V[d]
+    V = np.sort(V)
+    P = np.array(pows[: len(V)])
+    x = probe_points(V, np.random.default_rng(seed), 2000)
+    for ff in (False, True):
+        y, used = eval_host(V, P, x, force_fallback=ff)
+        check(V, P, x, y, steepest(V, P))
