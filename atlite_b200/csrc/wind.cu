@@ -320,7 +320,9 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
           const double sA = c_lo == 0 ? 0.0 : slope(c_lo - 1);
           const double sB = c_hi >= n ? 0.0 : slope(c_hi - 1);
           e[0] = ceil_f(K);
-          e[1] = (float)(adj(c_lo) + sA * ((double)e[0] - K));
+          // the reference point is e[0], not K (up to one ulp apart when K is not a
+          // float): split the difference between the two sides
+          e[1] = (float)(adj(c_lo) + 0.5 * (sA + sB) * ((double)e[0] - K));
           e[2] = (float)sA;
           e[3] = (float)sB;
         } else {  // inside segment c_lo - 1 (1 <= c_lo <= n-1): expand about the bucket centre
