@@ -34,7 +34,8 @@ namespace atl {
 // loads of the NEXT batch are issued into the now-dead raw registers, and only
 // then the shuffle-reduce + atomics of the current batch execute -- so B steps of
 // loads are in flight across the whole reduce phase at no extra register cost.
-// Steps are reduced pairwise with one butterfly (reduce_slots2).  B is chosen per
+// Steps are reduced two at a time, slots four at a time, in one transposed
+// butterfly (reduce_slots2g; G = 0 selects the older pairwise reduce_slots2).  B is chosen per
 // physics so that B x (#fields) 16-byte loads per lane cover the HBM latency
 // (PV: 2 x 5, wind: 4 x 2, SpMM: 4 x 1).  MINB = CTAs/SM the register allocator
 // must allow.
@@ -222,16 +223,10 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
   const GridDev gd = plan->grid;
 #define ATL_LAUNCH_FUSED(B, MINB, ...) \
   k_fused_reduce<Phys, B, MINB, ##__VA_ARGS__><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb)
-  switch (tuning().variant) {  // experiments; 0 = the functor's own choice
-    case 1: ATL_LAUNCH_FUSED(1, 8); break;
-    case 2: ATL_LAUNCH_FUSED(2, 6); break;
-    case 3: ATL_LAUNCH_FUSED(4, 6); break;
-    case 4: ATL_LAUNCH_FUSED(4, 8); break;
-    case 5: ATL_LAUNCH_FUSED(2, 4); break;
-    case 6: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 1); break;
-    case 7: ATL_LAUNCH_FUSED(2, 5, 1); break;
-    case 8: ATL_LAUNCH_FUSED(4, 6, 1); break;
-    default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks); break;
+  switch (tuning().variant) {  // A/B experiments (ATL_VARIANT); 0 = the functor's own choice
+    case 1: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 0); break;  // pairwise reduce
+    case 2: ATL_LAUNCH_FUSED(4, 6, 1); break;                            // deeper batch
+    default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 1); break;
   }
 #undef ATL_LAUNCH_FUSED
   ++g_launches;

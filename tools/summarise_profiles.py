@@ -51,9 +51,14 @@ def full(rep):
             "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size"]
     s = {k: [d.get(k), units.get(k)] for k in keys}
     stalls = sorted(((float(v), k) for k, v in d.items()
-                     if "issue_stalled" in k and k.endswith("per_warp_active.pct") and v not in (None, "")), reverse=True)
-    s["top_stalls_pct_of_warp_active"] = {k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_warp_active.pct", ""): v
-                                          for v, k in stalls[:6]}
+                     if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k
+                     and v not in (None, "")), reverse=True)
+    s["top_stalls_warps_per_issue"] = {
+        k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): round(v, 3)
+        for v, k in stalls[:7]}
+    for k in ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+              "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"):
+        s[k] = [d.get(k), units.get(k)]
     return s
 
 
@@ -61,10 +66,11 @@ if __name__ == "__main__":
     for ln in launches("gpurun_out/launches_bench.csv", f"profiles/{TAG}_launches_bench.csv")[:10]:
         print(ln)
     summ = {}
-    for tag, rep in (("pv_200x200x8760_100shapes", "gpurun_out/prof_pv_small_r1.ncu-rep"),
-                     ("pv_1440x720x432_3000shapes", "gpurun_out/prof_pv_big_r1.ncu-rep"),
-                     ("wind_200x200x8760_100shapes", "gpurun_out/prof_wind_small_r1.ncu-rep"),
-                     ("heat_200x200x8760_100shapes", "gpurun_out/prof_heat_small_r1.ncu-rep")):
+    SUF = sys.argv[2] if len(sys.argv) > 2 else "r1"
+    for tag, rep in (("pv_200x200x8760_100shapes", f"gpurun_out/prof_pv_small_{SUF}.ncu-rep"),
+                     ("pv_1440x720x432_3000shapes", f"gpurun_out/prof_pv_big_{SUF}.ncu-rep"),
+                     ("wind_200x200x8760_100shapes", f"gpurun_out/prof_wind_small_{SUF}.ncu-rep"),
+                     ("heat_200x200x8760_100shapes", f"gpurun_out/prof_heat_small_{SUF}.ncu-rep")):
         try:
             summ[tag] = full(rep)
         except Exception as e:  # noqa: BLE001
@@ -76,4 +82,4 @@ if __name__ == "__main__":
                   "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
                   "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):
             print("  ", k, s[k])
-        print("   stalls", s["top_stalls_pct_of_warp_active"])
+        print("   stalls", s["top_stalls_warps_per_issue"])
