@@ -186,6 +186,11 @@ _SIGNATURES = {
     "atl_pv_timesum": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
     "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
+    "atl_indicator_compute": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_int32, _P, _P, _P, _P, C.POINTER(_P)]),
+    "atl_indicator_nnz": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "atl_indicator_export": (C.c_int, [_P, _P, _P, _P]),
+    "atl_indicator_destroy": (None, [_P]),
     "atl_wind_create": (C.c_int, [C.c_int, C.POINTER(WindConfig), C.POINTER(_P)]),
     "atl_wind_curve_eval_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
     "atl_wind_destroy": (None, [_P]),

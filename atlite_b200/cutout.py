@@ -73,6 +73,10 @@ class Cutout:
         return float(np.round(y[1] - y[0], 8)) if len(y) > 1 else 0.0
 
     @property
+    def crs(self):
+        return getattr(self.data, "attrs", {}).get("crs", "EPSG:4326")
+
+    @property
     def extent(self):
         x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
         return np.array([x.min() - self.dx / 2, x.max() + self.dx / 2,
@@ -93,21 +97,19 @@ class Cutout:
         )
 
     def indicatormatrix(self, shapes, shapes_crs=4326):
-        """Cell x shape overlap matrix (gis.py:104-145).  GIS preprocessing is
-        outside the hot path: delegate to atlite when it
-        and its GIS stack are importable, otherwise ask for ``matrix=``."""
-        try:
-            from atlite.gis import compute_indicatormatrix  # type: ignore
-            from shapely.geometry import box  # type: ignore
-        except Exception as e:  # noqa: BLE001
+        """Cell x shape overlap matrix (cutout.py:492-515 -> gis.py:104-145): entry
+        [i, j] is the fraction of grid cell j (``cutout.grid`` order) inside shape i.
+        Computed on the GPU from the polygon edges (csrc/indicator.cu); shapes may be
+        shapely / geopandas objects, GeoJSON dicts or coordinate arrays (see gis.py).
+        Shapes must be in the cutout's CRS (no reprojection here)."""
+        from . import gis
+
+        if str(shapes_crs).upper().replace("EPSG:", "") != str(self.crs).upper().replace("EPSG:", ""):
             raise NotImplementedError(
-                "building an indicator matrix from shapes needs shapely/atlite; "
-                "pass a precomputed `matrix=` (n_bus x n_cells, cutout.grid order)"
-            ) from e
-        g = self.grid
-        dx, dy = self.dx, self.dy
-        cells = [box(x - dx / 2, y - dy / 2, x + dx / 2, y + dy / 2) for x, y in zip(g.x, g.y)]
-        return compute_indicatormatrix(cells, shapes, 4326, shapes_crs)
+                f"shapes_crs={shapes_crs!r}: reprojection is outside this package; "
+                f"pass shapes in the cutout's CRS ({self.crs})"
+            )
+        return gis.compute_indicatormatrix(self.coords["x"], self.coords["y"], shapes)
 
     # ---- device residency
     def to_device(self, device=None, variables=None, pad=True):

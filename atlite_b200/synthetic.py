@@ -253,3 +253,36 @@ def make_pv_fields_device(time, x, y, device, seed=0):
     f["albedo"] = u(0.05, 0.4)
     f["temperature"] = u(255.0, 305.0)
     return f
+
+
+def make_voronoi_shapes(x, y, n_shapes, seed=8, margin=0.0):
+    """``n_shapes`` convex polygons that PARTITION the cutout extent (cell boxes
+    included) -- NUTS-like regions for the indicator-matrix tests and benchmarks.
+    Voronoi cells of random seeds, bounded by mirroring the seeds across the four
+    sides of the extent.  Returns a list of (N, 2) float64 rings (counter-clockwise,
+    not closed); ``margin`` > 0 shrinks the partitioned box inside the extent."""
+    from scipy.spatial import Voronoi
+
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    dx, dy = (x[-1] - x[0]) / (len(x) - 1), (y[-1] - y[0]) / (len(y) - 1)
+    xlo, xhi = x[0] - dx / 2 + margin, x[-1] + dx / 2 - margin
+    ylo, yhi = y[0] - dy / 2 + margin, y[-1] + dy / 2 - margin
+    rng = np.random.default_rng(seed)
+    pts = np.c_[rng.uniform(xlo, xhi, n_shapes), rng.uniform(ylo, yhi, n_shapes)]
+    mirrored = [pts]
+    for axis, bound in ((0, xlo), (0, xhi), (1, ylo), (1, yhi)):
+        m = pts.copy()
+        m[:, axis] = 2 * bound - m[:, axis]
+        mirrored.append(m)
+    vor = Voronoi(np.concatenate(mirrored))
+    rings = []
+    for k in range(n_shapes):
+        region = vor.regions[vor.point_region[k]]
+        assert -1 not in region and len(region) >= 3
+        ring = vor.vertices[region]
+        ring[:, 0] = np.clip(ring[:, 0], xlo, xhi)  # snap round-off on the box sides
+        ring[:, 1] = np.clip(ring[:, 1], ylo, yhi)
+        c = ring.mean(0)
+        order = np.argsort(np.arctan2(ring[:, 1] - c[1], ring[:, 0] - c[0]))
+        rings.append(np.ascontiguousarray(ring[order]))
+    return rings

@@ -347,6 +347,30 @@ int atl_csp_op_info(const AtlCspOp* op, int32_t* device, int32_t* ny, int32_t* n
  * "gpu_launches" evidence). */
 int64_t atl_launch_count(void);
 
+/* ------------------------------------------------------------------ */
+/* Indicator matrix: shapes -> CSR (n_shapes, ny*nx) of covered cell   */
+/* fractions (cutout.py:492-515 -> gis.py:104-145 on the regular grid  */
+/* of cutout.py:355-376).  SURVEY section 8 f1.                        */
+/* ------------------------------------------------------------------ */
+typedef struct AtlIndicator AtlIndicator;
+/* Grid: cell (iy, ix) is the box of half-width (dx/2, dy/2) about (x0 + ix*dx,
+ * y0 + iy*dy); dx, dy > 0.  Shapes: shape s owns rings
+ * shape_ring_ptr[s] .. shape_ring_ptr[s+1]-1; ring r owns the vertices
+ * ring_ptr[r] .. ring_ptr[r+1]-1 of xy (x, y interleaved, float64, same CRS as the
+ * grid; the closing vertex may be repeated or not); ring_is_hole[r] != 0 marks an
+ * interior ring.  Ring orientation is free.  All pointers are HOST pointers; the
+ * areas are computed on `device`.  Entries are kept when the covered fraction
+ * exceeds 1e-10; columns are sorted (iy*nx + ix). */
+int atl_indicator_compute(int device, int32_t ny, int32_t nx, double x0, double dx, double y0,
+                          double dy, int32_t n_shapes, const int64_t* shape_ring_ptr,
+                          const int64_t* ring_ptr, const int8_t* ring_is_hole, const double* xy,
+                          AtlIndicator** out);
+int atl_indicator_nnz(const AtlIndicator* ind, int64_t* nnz_out);
+/* indptr_out[n_shapes+1], indices_out[nnz], data_out[nnz] (host, caller-owned) */
+int atl_indicator_export(const AtlIndicator* ind, int64_t* indptr_out, int32_t* indices_out,
+                         double* data_out);
+void atl_indicator_destroy(AtlIndicator* ind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,218 @@
+"""Indicator matrix: shapes -> covered cell fractions.
+
+CPU part: the Sutherland-Hodgman oracle against known answers -- the reference's own
+known-answer test (test/test_gis.py:322-332: a shape equal to one grid cell) and
+analytic areas -- plus the host-side shape packing.  GPU part: the CUDA
+edge-accumulation kernels (csrc/indicator.cu, through the C ABI) against that oracle
+and through size-independent properties at scale.
+"""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import indicator_oracle as IO
+import atlite_b200 as ab
+from atlite_b200 import gis, synthetic as syn
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def box(x0, y0, x1, y1):
+    return np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], dtype=float)
+
+
+def oracle(x, y, shapes):
+    return IO.indicatormatrix(x, y, [gis.geometry_rings(s) for s in shapes])
+
+
+def shoelace(ring):
+    r = np.asarray(ring, float)
+    return 0.5 * abs(np.sum(r[:, 0] * np.roll(r[:, 1], -1) - np.roll(r[:, 0], -1) * r[:, 1]))
+
+
+X, Y = syn.make_coords(12, 9, 5.0, 40.0)  # 0.25 degree cells
+
+
+# ------------------------------------------------------------------ oracle known answers (CPU)
+
+
+def test_oracle_reference_kat_cell_shape_gives_exactly_one():
+    """test/test_gis.py:322-332: indicatormatrix([cell]) has a single 1.0."""
+    for iy, ix in ((0, 0), (8, 10)):  # lower-left cell; the reference's `iloc[-2]`
+        cell = box(X[ix] - 0.125, Y[iy] - 0.125, X[ix] + 0.125, Y[iy] + 0.125)
+        m = oracle(X, Y, [cell])
+        assert m[0, iy * 12 + ix] == 1.0
+        assert m.sum() == 1
+
+
+def test_oracle_analytic_areas():
+    # a box covering 2.5 x 1.5 cells, offset by half a cell
+    b = box(X[2], Y[3], X[2] + 2.5 * 0.25, Y[3] + 1.5 * 0.25)
+    m = oracle(X, Y, [b]).toarray().reshape(9, 12)
+    assert np.isclose(m.sum(), 2.5 * 1.5)
+    np.testing.assert_allclose(m[3, 2:5], [0.25, 0.5, 0.5])
+    # triangle with legs of 2 cells: area 2 cells, the hypotenuse halves the diagonal cells
+    x, y = np.arange(4.0), np.arange(3.0)
+    t = np.array([[-0.5, -0.5], [1.5, -0.5], [-0.5, 1.5]])
+    m = oracle(x, y, [t]).toarray().reshape(3, 4)
+    np.testing.assert_allclose(m, [[1, 0.5, 0, 0], [0.5, 0, 0, 0], [0, 0, 0, 0]])
+    # polygon with a hole, both orientations of both rings: same answer
+    outer, hole = box(-0.5, -0.5, 2.5, 1.5), box(0.5, -0.25, 1.5, 0.75)
+    for o in (outer, outer[::-1]):
+        for h in (hole, hole[::-1]):
+            m = oracle(x, y, [[o, h]]).toarray().reshape(3, 4)
+            assert np.isclose(m.sum(), 6 - 1)
+            assert np.isclose(m[0, 1], 1 - 0.75) and np.isclose(m[1, 1], 1 - 0.25)
+    # concave (L-shaped) polygon: area 3 cells
+    L = np.array([[-0.5, -0.5], [1.5, -0.5], [1.5, 0.5], [0.5, 0.5], [0.5, 1.5], [-0.5, 1.5]])
+    m = oracle(x, y, [L]).toarray().reshape(3, 4)
+    np.testing.assert_allclose(m, [[1, 1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 0]])
+
+
+def test_shape_packing_accepts_geojson_geo_interface_and_arrays():
+    ring, hole = box(0, 0, 4, 4), box(1, 1, 2, 2)
+
+    class Geo:  # what shapely / geopandas objects expose
+        def __init__(self, gi):
+            self.__geo_interface__ = gi
+
+    closed = np.vstack([ring, ring[:1]])
+    poly = {"type": "Polygon", "coordinates": [closed.tolist(), np.vstack([hole, hole[:1]]).tolist()]}
+    multi = {"type": "MultiPolygon", "coordinates": [[closed.tolist()], [box(5, 5, 6, 6).tolist()]]}
+    feature = {"type": "Feature", "geometry": poly, "properties": {}}
+    srp, rp, holes, xy = gis.pack_shapes([ring, [ring, hole], poly, Geo(multi), feature, None])
+    assert srp.tolist() == [0, 1, 3, 5, 7, 9, 9]
+    assert holes.tolist() == [0, 0, 1, 0, 1, 0, 0, 0, 1]
+    assert rp[-1] == len(xy) and xy.dtype == np.float64 and xy.shape[1] == 2
+    # collections: dict and pandas Series keep their order
+    import pandas as pd
+
+    a = gis.pack_shapes({"a": ring, "b": [ring, hole]})
+    b = gis.pack_shapes(pd.Series([ring, [ring, hole]], index=["a", "b"]))
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    with pytest.raises(ValueError, match="unsupported geometry"):
+        gis.pack_shapes([{"type": "Point", "coordinates": [0, 0]}])
+    with pytest.raises(TypeError):
+        gis.pack_shapes(["not a polygon"])
+
+
+def test_grid_axis_validation():
+    assert gis.regular_axis([1.0, 1.25, 1.5], "x") == (1.0, 0.25)
+    for bad in ([1.0], [3.0, 2.0, 1.0], [0.0, 1.0, 3.0]):
+        with pytest.raises(ValueError):
+            gis.regular_axis(bad, "x")
+    c = ab.Cutout(data=syn.make_dataset(12, 9, 2, kinds=("temperature",)))
+    with pytest.raises(NotImplementedError, match="reprojection"):
+        c.indicatormatrix([box(0, 0, 1, 1)], shapes_crs=3035)
+
+
+def test_product_does_not_import_the_oracle():
+    code = ("import sys, atlite_b200, atlite_b200.gis; "
+            "assert 'indicator_oracle' not in sys.modules and 'atlite_oracle' not in sys.modules")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=REPO)
+
+
+# ------------------------------------------------------------------ CUDA kernels (GPU)
+
+
+def random_shapes(rng, n, x, y):
+    shapes = []
+    for t in range(n):
+        k = rng.integers(3, 12)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(0.05, 1.2, k)
+        c = np.array([rng.uniform(x[0] - 0.5, x[-1] + 0.5), rng.uniform(y[0] - 0.5, y[-1] + 0.5)])
+        ring = np.c_[c[0] + rad * np.cos(ang), c[1] + 0.6 * rad * np.sin(ang)]  # star-shaped, maybe concave
+        if t % 2:
+            ring = ring[::-1]
+        rings = [ring]
+        if t % 3 == 0:  # a hole strictly inside
+            rings.append(np.c_[c[0] + 0.02 * np.cos(ang), c[1] + 0.012 * np.sin(ang)])
+        if t % 5 == 0:  # second part: MultiPolygon as GeoJSON
+            far = box(x[0] + 0.3, y[0] + 0.1, x[0] + 0.9, y[0] + 0.45)
+            shapes.append({"type": "MultiPolygon",
+                           "coordinates": [[np.vstack([r, r[:1]]).tolist() for r in rings],
+                                           [np.vstack([far, far[:1]]).tolist()]]})
+        else:
+            shapes.append(rings)
+    return shapes
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_on_random_polygons():
+    rng = np.random.default_rng(11)
+    shapes = random_shapes(rng, 40, X, Y)
+    shapes += [box(X[0] - 0.125, Y[0] - 0.125, X[0] + 0.125, Y[0] + 0.125),   # the reference KAT
+               box(-50, -50, 80, 80),                                      # covers everything
+               box(100, 100, 101, 101),                                    # entirely outside
+               box(X[3], Y[0] - 3, X[5], Y[0] + 0.01),                      # sticks out below
+               np.array([[6.0, 41.0], [6.0, 41.0], [6.0, 41.0]]),           # degenerate
+               np.array([[6.0, 41.0], [7.0, 41.0]])]                        # two points
+    got = gis.compute_indicatormatrix(X, Y, shapes)
+    want = oracle(X, Y, shapes)
+    assert got.shape == want.shape == (len(shapes), 9 * 12)
+    assert got.has_sorted_indices and got.indices.dtype == np.int32
+    np.testing.assert_allclose(got.toarray(), want.toarray(), rtol=0, atol=2e-12)
+    assert got[40, 0] == 1.0 and got[40].sum() == 1           # exactly, like test_gis.py:322-332
+    assert got[41].nnz == 108 and (got[41].data == 1.0).all()
+    assert got[42].nnz == got[44].nnz == got[45].nnz == 0
+    # same sparsity pattern as the oracle wherever the value is not at the keep threshold
+    w = want.toarray()
+    assert ((got.toarray() > 0) == (w > 0))[np.abs(w - 1e-10) > 1e-11].all()
+
+
+@pytest.mark.gpu
+def test_gpu_partition_of_unity_and_areas_at_scale():
+    """Voronoi regions partition the extent: every cell's column sums to 1, every
+    row sums to the polygon's area in cells; bit-identical run to run; batching."""
+    nx, ny, n = 400, 300, 500
+    x, y = syn.make_coords(nx, ny, -12.0, 33.0)
+    rings = syn.make_voronoi_shapes(x, y, n)
+    m = gis.compute_indicatormatrix(x, y, rings)
+    np.testing.assert_allclose(np.asarray(m.sum(0)).ravel(), 1.0, rtol=0, atol=1e-9)
+    area = np.array([shoelace(r) for r in rings]) / 0.25**2
+    np.testing.assert_allclose(np.asarray(m.sum(1)).ravel(), area, rtol=1e-10, atol=1e-8)
+    assert m.data.min() > 1e-10 and m.data.max() <= 1.0
+    m2 = gis.compute_indicatormatrix(x, y, rings)
+    assert (m.indptr == m2.indptr).all() and (m.indices == m2.indices).all() and (m.data == m2.data).all()
+    # many small batches (scratch budget of 2000 box cells) give the identical matrix
+    code = ("import numpy as np, pickle, sys; sys.path.insert(0, %r); "
+            "from atlite_b200 import gis, synthetic as syn; "
+            "x, y = syn.make_coords(400, 300, -12.0, 33.0); "
+            "m = gis.compute_indicatormatrix(x, y, syn.make_voronoi_shapes(x, y, 500)); "
+            "sys.stdout.buffer.write(pickle.dumps((m.indptr, m.indices, m.data)))" % REPO)
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True,
+                         env={**os.environ, "ATL_INDICATOR_BUDGET": "2000"}).stdout
+    import pickle
+
+    ip, ix, dat = pickle.loads(out)
+    assert (ip == m.indptr).all() and (ix == m.indices).all() and (dat == m.data).all()
+
+
+@pytest.mark.gpu
+def test_gpu_shapes_argument_end_to_end():
+    """convert_and_aggregate(shapes=...) (convert.py:235-240): the indicator matrix is
+    built on the GPU and fed to the fused kernels; same result as passing it as matrix=."""
+    import pandas as pd
+
+    ds = syn.make_dataset(70, 45, 48, x0=-10.0, y0=-20.0, dx=0.5, dy=1.0)
+    c = ab.Cutout(data=ds)
+    x, y = np.asarray(c.coords["x"]), np.asarray(c.coords["y"])
+    rings = syn.make_voronoi_shapes(x, y, 9)
+    shapes = pd.Series(rings, index=[f"region{k}" for k in range(9)])
+    ind = c.indicatormatrix(shapes)
+    assert sp.issparse(ind) and ind.shape == (9, 45 * 70)
+    a = c.wind("Vestas_V112_3MW", shapes=shapes, aggregate_time=None)
+    b = c.wind("Vestas_V112_3MW", matrix=ind, index=shapes.index, aggregate_time=None)
+    assert list(a.coords[a.dims[0]]) == list(shapes.index)
+    np.testing.assert_array_equal(a.values, b.values)
+    want = oracle(x, y, rings)
+    np.testing.assert_allclose(ind.toarray(), want.toarray(), rtol=0, atol=2e-12)
+    pu = c.pv("CSi", "latitude_optimal", shapes=shapes, per_unit=True, aggregate_time="mean")
+    assert pu.shape == (9,) and (pu.values > 0).all() and (pu.values < 1).all()
