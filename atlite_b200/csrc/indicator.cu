@@ -19,7 +19,7 @@
 //
 //   k_edges   one thread per edge: walks the rows / cells it crosses, adds the
 //             differences into the shape's bounding-box buffer.  Sums are kept
-//             as 2^-40 fixed point in 64-bit integer atomics: associative, so the
+//             as 2^-52 fixed point in 64-bit integer atomics: associative, so the
 //             result (and with it the sparsity pattern) is identical run to run.
 //   k_scan    one warp per buffer row: prefix sum -> coverage in [0, 1], counts
 //             the entries above the keep threshold.
@@ -38,7 +38,8 @@
 
 namespace atl {
 
-constexpr double kFix = 1099511627776.0;  // 2^40
+constexpr double kFix = 4503599627370496.0;  // 2^52: one ulp of a coverage fraction; sums wrap
+                                              // harmlessly (mod 2^64) as long as the final coverage is < 2048
 constexpr double kKeep = 1e-10;           // coverage fractions at or below this are dropped
 
 struct EdgeDev {

@@ -67,6 +67,29 @@ __host__ __device__ __forceinline__ float lut_interp(float x, const char* lut, i
   return (x >= k_end) ? y_end : y;
 }
 
+// Lattice mode: all knots lie on lo + m*w, so every bucket [lo + b*w, lo + (b+1)*w)
+// sits inside ONE segment of the (jump-free, hence continuous) curve and holds just
+// {slope, intercept}: which bucket a speed within rounding of a knot lands in does
+// not matter.  The steps come back through `nj` exact compares.  `lut` points one
+// entry past a guard copy of bucket 0 (floor may give -1 at x_lo).
+__host__ __device__ __forceinline__ float lattice_interp(float x, const char* lut, int stride,
+                                                         float x_lo, float x_hi, float inv_w,
+                                                         float c0, int nj, float k1, float j1,
+                                                         float k2, float j2) {
+#ifdef __CUDA_ARCH__
+  const float xc = fmin_nan(fmax_nan(x, x_lo), x_hi);
+  const int b = __float2int_rd(fmaf(xc, inv_w, c0));
+#else
+  const float xc = (x != x) ? x : std::fmin(std::fmax(x, x_lo), x_hi);
+  const int b = (x != x) ? 0 : (int)std::floor(std::fmaf(xc, inv_w, c0));
+#endif
+  const float2 e = *reinterpret_cast<const float2*>(lut + b * stride);
+  float y = fmaf(e.x, xc, e.y);
+  if (nj > 0) y = (x >= k1) ? y + j1 : y;
+  if (nj > 1) y = (x >= k2) ? y + j2 : y;
+  return y;
+}
+
 template <bool VEC>
 struct WindPhys {
   static constexpr bool kVec = VEC;
@@ -79,11 +102,14 @@ struct WindPhys {
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
   float x_lo, x_hi;
-  int use_lut, n_stage;
+  int use_lut, n_stage;   // use_lut: 0 binary search, 1 general LUT, 2 lattice LUT
   float inv_w, c0;        // bucket = floor(x * inv_w + c0)
   int lut_stride, rep_mask;  // bytes between buckets; lane & rep_mask picks the replica
-  float k_jump, jump;     // interior jump: y += jump for x >= k_jump (+inf: none)
-  float k_end, y_end;     // x >= k_end -> y_end (right clamp, incl. the cut-out step)
+  int lut_entry;          // bytes per entry (16 general, 8 lattice)
+  int nj;                 // lattice: number of steps (0..2), at k_jump / k_end
+  float k_jump, jump;     // general: interior jump, y += jump for x >= k_jump (+inf: none)
+  float k_end, y_end;     // general: x >= k_end -> y_end (right clamp incl. cut-out step);
+                          // lattice: second step, y += y_end for x >= k_end
 
   struct Cell {
     int rep_off;  // byte offset of this lane's replica inside a bucket's entries
@@ -91,8 +117,9 @@ struct WindPhys {
   struct Raw {
     float w[4], a[4];
   };
-  // LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; fallback: 256 + 4*257
-  static constexpr int kSmemFloats = 4 * 129 * 8;
+  // general LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; lattice:
+  // <= 130 x 16 or <= 258 x 4 replicas, 2 floats each; fallback: 256 + 4*257
+  static constexpr int kSmemFloats = 2 * 130 * 16;
   static constexpr int kBatch = 2, kMinBlocks = 6;
 
   __device__ void stage(float* smem) const {
@@ -100,7 +127,7 @@ struct WindPhys {
     __syncthreads();
   }
   __device__ void init(Cell& c, const Geom&, const float*) const {
-    c.rep_off = ((threadIdx.x & 31) & rep_mask) * 16;
+    c.rep_off = ((threadIdx.x & 31) & rep_mask) * lut_entry;
   }
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
     load4(wnd, tb, g, r.w);
@@ -109,6 +136,13 @@ struct WindPhys {
   // np.interp for the lane's 4 values at once.
   __device__ __forceinline__ void interp4(const Cell& c, const float (&x)[4], float (&r)[4],
                                           const float* sm) const {
+    if (use_lut == 2) {
+      const char* lut = reinterpret_cast<const char*>(sm) + lut_stride + c.rep_off;  // skip the guard
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        r[i] = lattice_interp(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, nj, k_jump, jump, k_end, y_end);
+      return;
+    }
     if (use_lut) {
       const char* lut = reinterpret_cast<const char*>(sm) + c.rep_off;
 #pragma unroll
@@ -166,7 +200,7 @@ struct AtlWindOp {
   float x_lo, x_hi;
   int use_lut, n_stage;
   float inv_w, c0;
-  int lut_stride, rep_mask;
+  int lut_stride, rep_mask, lut_entry, nj;
   float k_jump, jump, k_end, y_end;
   float* d_curve = nullptr;
 };
@@ -192,6 +226,8 @@ static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
   p.c0 = op->c0;
   p.lut_stride = op->lut_stride;
   p.rep_mask = op->rep_mask;
+  p.lut_entry = op->lut_entry;
+  p.nj = op->nj;
   p.k_jump = op->k_jump;
   p.jump = op->jump;
   p.k_end = op->k_end;
@@ -210,13 +246,15 @@ static int check_fields(const AtlWindOp* op, const AtlWindFields* f) {
 // evaluator atl_wind_curve_eval_host the CPU tests use).
 struct CurveTables {
   std::vector<float> curve;
-  int n_knots = 0, NK = 0, use_lut = 0, lut_stride = 16, rep_mask = 0;
+  int n_knots = 0, NK = 0, use_lut = 0, lut_stride = 16, rep_mask = 0, lut_entry = 16, nj = 0;
   float x_lo = 0.f, x_hi = 0.f, inv_w = 0.f, c0 = 0.f;
   float k_jump = INFINITY, jump = 0.f, k_end = 0.f, y_end = 0.f;
 };
 
+// force_mode: -1 best available, 0 binary search, 1 general LUT, 2 lattice LUT
 static int build_curve(const double* V, const double* POW, int n, CurveTables& T,
-                       bool force_fallback = false) {
+                       int force_mode = -1) {
+  const bool force_fallback = force_mode == 0;
   ATL_REQUIRE(n >= 1 && n <= 255, "n_knots must be in [1, 255]");
   ATL_REQUIRE(V && POW, "power curve missing");
   for (int i = 1; i < n; ++i)
@@ -264,11 +302,86 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
     if ((double)f < v) f = nextafterf(f, INFINITY);
     return f;
   };
-  int use_lut = 0, lut_stride = 16, rep_mask = 0;
+  int use_lut = 0, lut_stride = 16, rep_mask = 0, lut_entry = 16, nj = 0;
   float inv_w = 0.f, c0 = 0.f;
   float k_jump = INFINITY, jump = 0.f;
-  const float k_end = ceil_f(V[n - 1]), y_end = (float)POW[n - 1];
-  {
+  float k_end = ceil_f(V[n - 1]), y_end = (float)POW[n - 1];
+  // ---- lattice LUT: knots on lo + m*w, at most two steps
+  if (n >= 2 && V[n - 1] > V[0] && (force_mode == -1 || force_mode == 2)) {
+    const double lo = V[0], hi = V[n - 1];
+    struct Jump { double K, J; };
+    std::vector<Jump> jumps;
+    std::vector<int> last;  // last index of every run of equal knots
+    for (int a = 0; a < n;) {
+      int z = a;
+      while (z + 1 < n && V[z + 1] == V[a]) ++z;
+      if (POW[z] != POW[a]) jumps.push_back({V[a], POW[z] - POW[a]});
+      last.push_back(z);
+      a = z + 1;
+    }
+    double dmin = hi - lo;
+    for (size_t k = 1; k < last.size(); ++k) dmin = std::min(dmin, V[last[k]] - V[last[k - 1]]);
+    int NB = 0;
+    double wdt = 0.0;
+    for (int q = 1; q <= 8 && !NB && jumps.size() <= 2; ++q) {
+      const double w = dmin / q;
+      const double nb = (hi - lo) / w;
+      if (nb > 256.5) break;
+      bool ok = std::fabs(nb - std::round(nb)) < 1e-6;
+      for (size_t k = 0; k < last.size() && ok; ++k) {
+        const double m = (V[last[k]] - lo) / w;
+        ok = std::fabs(m - std::round(m)) < 1e-6;
+      }
+      if (ok) {
+        NB = (int)std::round(nb);
+        wdt = (hi - lo) / NB;
+      }
+    }
+    if (NB) {
+      const int R = NB <= 128 ? 16 : 4;
+      std::vector<float> lut((size_t)(NB + 2) * R * 2);
+      auto put = [&](int slot, double sl, double icpt) {
+        const float e[2] = {(float)sl, (float)icpt};
+        for (int r = 0; r < R; ++r) std::memcpy(&lut[((size_t)slot * R + r) * 2], e, 8);
+      };
+      // value of the continuous (steps removed) curve at the last knot of run k
+      auto cont = [&](size_t k) {
+        double y = POW[last[k]];
+        for (const Jump& j : jumps)
+          if (j.K <= V[last[k]]) y -= j.J;
+        return y;
+      };
+      size_t k = 0;
+      for (int b = 0; b < NB; ++b) {
+        const double mid = lo + (b + 0.5) * wdt;
+        while (k + 1 < last.size() && V[last[k + 1]] <= mid) ++k;
+        const int z = last[k];  // segment [V[z], V[z+1])
+        const double sl = (POW[z + 1] - POW[z]) / (V[z + 1] - V[z]);
+        put(b + 1, sl, cont(k) - sl * V[z]);
+        if (b == 0) put(0, sl, cont(k) - sl * V[z]);  // guard for floor(..) == -1
+      }
+      put(NB + 1, 0.0, cont(last.size() - 1));  // x == x_hi: right clamp of the continuous curve
+      use_lut = 2;
+      lut_entry = 8;
+      lut_stride = 8 * R;
+      rep_mask = R - 1;
+      inv_w = (float)(1.0 / wdt);
+      c0 = (float)(-lo / wdt);
+      nj = (int)jumps.size();
+      k_jump = k_end = INFINITY;
+      jump = y_end = 0.f;
+      if (nj > 0) {
+        k_jump = ceil_f(jumps[0].K);
+        jump = (float)jumps[0].J;
+      }
+      if (nj > 1) {
+        k_end = ceil_f(jumps[1].K);
+        y_end = (float)jumps[1].J;
+      }
+      curve.swap(lut);
+    }
+  }
+  if (!use_lut && force_mode != 2) {
     const double lo = V[0], hi = V[n - 1];
     // jumps of np.interp: a run of equal knots a..z with POW[a] != POW[z]
     int n_interior = 0, jump_first = n;  // knots with index > jump_first sit above the jump
@@ -291,7 +404,7 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
                  : 0.0;
     };
     for (int NB = 32; NB <= 1024 && !use_lut && hi > lo && n_interior <= 1 && !force_fallback;
-         NB *= 2) {
+         NB *= 2) {  // general LUT
       const double wdt = (hi - lo) / NB;
       std::vector<int> bucket_of(n);
       std::vector<double> knot_in((size_t)NB + 1, std::nan(""));
@@ -355,6 +468,8 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
   T.use_lut = use_lut;
   T.lut_stride = lut_stride;
   T.rep_mask = rep_mask;
+  T.lut_entry = lut_entry;
+  T.nj = nj;
   T.x_lo = (float)V[0];
   T.x_hi = (float)V[n - 1];
   T.inv_w = inv_w;
@@ -395,6 +510,8 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
   op->c0 = T.c0;
   op->lut_stride = T.lut_stride;
   op->rep_mask = T.rep_mask;
+  op->lut_entry = T.lut_entry;
+  op->nj = T.nj;
   op->k_jump = T.k_jump;
   op->jump = T.jump;
   op->k_end = T.k_end;
@@ -424,14 +541,21 @@ void atl_wind_destroy(AtlWindOp* op) {
 }
 
 int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_knots,
-                             int32_t force_fallback, const float* x, int64_t n, float* y_out,
+                             int32_t force_mode, const float* x, int64_t n, float* y_out,
                              int32_t* used_lut_out) {
   ATL_REQUIRE(x && y_out && n >= 0, "bad arguments");
   CurveTables T;
-  if (int rc = build_curve(V, POW_norm, n_knots, T, force_fallback != 0)) return rc;
+  ATL_REQUIRE(force_mode >= -1 && force_mode <= 2, "force_mode must be -1, 0, 1 or 2");
+  if (int rc = build_curve(V, POW_norm, n_knots, T, force_mode)) return rc;
   if (used_lut_out) *used_lut_out = T.use_lut;
   // replicas must be identical copies; evaluate through a different one per element
   for (int64_t i = 0; i < n; ++i) {
+    if (T.use_lut == 2) {
+      const char* lut = reinterpret_cast<const char*>(T.curve.data()) + T.lut_stride + ((int)i & T.rep_mask) * 8;
+      y_out[i] = lattice_interp(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0, T.nj, T.k_jump,
+                                T.jump, T.k_end, T.y_end);
+      continue;
+    }
     if (T.use_lut) {
       const char* lut = reinterpret_cast<const char*>(T.curve.data()) + ((int)i & T.rep_mask) * 16;
       y_out[i] = lut_interp(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0, T.k_jump,

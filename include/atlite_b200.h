@@ -332,11 +332,13 @@ int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
                    int32_t* solar_src);
 /* Host-only: evaluates the power-curve interpolation exactly as the kernels do
  * (same tables, same fp32 formula), no CUDA needed; the CPU tests compare it with
- * np.interp.  force_fallback != 0 takes the binary-search tables; *used_lut_out
- * (optional) tells which path the curve qualifies for. */
+ * np.interp.  force_mode: -1 = the table atl_wind_create would pick, 0 = binary
+ * search, 1 = general bucket LUT, 2 = lattice LUT (knots on a uniform lattice);
+ * *mode_out (optional) = the table actually built (a forced LUT mode the curve does
+ * not qualify for falls back to 0). */
 int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_knots,
-                             int32_t force_fallback, const float* x, int64_t n, float* y_out,
-                             int32_t* used_lut_out);
+                             int32_t force_mode, const float* x, int64_t n, float* y_out,
+                             int32_t* mode_out);
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny, int32_t* nx);

@@ -15,14 +15,15 @@ from hypothesis import given, settings, strategies as st
 from atlite_b200 import _lib, resource
 
 
-def eval_host(V, P, x, force_fallback=False):
+def eval_host(V, P, x, mode=-1):
+    """mode: -1 what atl_wind_create picks, 0 binary search, 1 general LUT, 2 lattice LUT"""
     lib = _lib.load()
     V = np.ascontiguousarray(V, dtype=np.float64)
     P = np.ascontiguousarray(P, dtype=np.float64)
     x = np.ascontiguousarray(x, dtype=np.float32)
     y = np.empty_like(x)
     used = C.c_int32(-1)
-    _lib.check(lib.atl_wind_curve_eval_host(_lib.ptr(V), _lib.ptr(P), len(V), int(force_fallback),
+    _lib.check(lib.atl_wind_curve_eval_host(_lib.ptr(V), _lib.ptr(P), len(V), int(mode),
                                             x.ctypes.data, len(x), y.ctypes.data, C.byref(used)))
     return y, used.value
 
@@ -53,21 +54,34 @@ def steepest(V, P):
 
 
 @pytest.mark.parametrize("name", sorted(resource.windturbines))
-def test_shipped_turbines_use_the_lut_and_match_np_interp(name):
+def test_shipped_turbines_use_a_lut_and_match_np_interp(name):
     t = resource.get_windturbineconfig(name)
     V, P = t["V"], t["POW"] / t["P"]
     x = probe_points(V, np.random.default_rng(1))
     y, used = eval_host(V, P, x)
-    assert used == 1, "every shipped power curve should qualify for the single-load LUT"
+    assert used in (1, 2), "every shipped power curve should qualify for a single-load LUT"
     check(V, P, x, y, steepest(V, P))
-    yf, used_f = eval_host(V, P, x, force_fallback=True)
-    assert used_f == 0
-    check(V, P, x, yf, steepest(V, P))
-    # exactly at float-representable knots: np.interp's value to one ulp of fp32 (a
-    # curve with a cut-in step is stored without the step and gets it added back)
-    yk, _ = eval_host(V, P, V.astype(np.float32))
+    for mode in (0, 1, 2):  # every table the curve qualifies for
+        ym, used_m = eval_host(V, P, x, mode)
+        assert used_m in (0, mode)
+        check(V, P, x, ym, steepest(V, P))
+    assert eval_host(V, P, x, 1)[1] == 1  # the general LUT takes every shipped curve
+    # exactly at float-representable knots: np.interp's value to one ulp of fp32 (steps are
+    # stored separately and added back; the lattice table evaluates slope * x + intercept)
     if np.array_equal(V.astype(np.float32).astype(np.float64), V):
-        np.testing.assert_allclose(yk, np.interp(V, V, P), rtol=0, atol=1.2e-7 * np.abs(P).max())
+        for mode in (1, 2):
+            yk, _ = eval_host(V, P, V.astype(np.float32), mode)
+            np.testing.assert_allclose(yk, np.interp(V, V, P), rtol=0,
+                                       atol=(1.2e-7 if mode == 1 else 5e-7) * np.abs(P).max())
+
+
+def test_lattice_mode_is_chosen_for_lattice_curves():
+    names = {n: eval_host(*(lambda t: (t["V"], t["POW"] / t["P"]))(resource.get_windturbineconfig(n)),
+                          np.zeros(1, np.float32))[1] for n in resource.windturbines}
+    assert names["Vestas_V112_3MW"] == 2 and names["Enercon_E126_7500kW"] == 2
+    assert sum(v == 2 for v in names.values()) >= 20, names
+    t = resource.windturbine_smooth(resource.get_windturbineconfig("Vestas_V112_3MW"))
+    assert eval_host(t["V"], t["POW"] / t["P"], np.zeros(1, np.float32))[1] == 2  # linspace(0, 35, 72)
 
 
 def test_smoothed_curve_and_steps():
@@ -77,17 +91,22 @@ def test_smoothed_curve_and_steps():
     y, used = eval_host(V, P, x)
     check(V, P, x, y, steepest(V, P))
     # cut-in step AND cut-out step AND a step at the very first knot
-    for V, P, lut in [
-        ([3, 3, 5, 12, 25, 25], [0, 0.1, 0.3, 1, 1, 0], 1),
-        ([0, 3, 3, 12, 25, 25], [0, 0, 0.2, 1, 1, 0], 1),
-        ([0, 3, 3, 12, 12, 25], [0, 0, 0.2, 0.9, 1, 1], 0),   # two interior steps -> fallback
-        ([2, 2, 2, 10, 25], [0, 0.5, 0.1, 1, 0.2], 1),         # triple knot, no cut-out step
-        ([4.0], [0.7], 0),                                     # single knot: constant
+    for V, P, auto, general in [
+        ([3, 3, 5, 12, 25, 25], [0, 0.1, 0.3, 1, 1, 0], 2, 1),
+        ([0, 3, 3, 12, 25, 25], [0, 0, 0.2, 1, 1, 0], 2, 1),
+        ([0, 3, 3, 12, 12, 25], [0, 0, 0.2, 0.9, 1, 1], 2, 0),      # two interior steps
+        ([0, 3, 3, 12, 12, 25, 25], [0, 0, 0.2, 0.9, 1, 1, 0], 0, 0),  # three steps -> search
+        ([2, 2, 2, 10, 25], [0, 0.5, 0.1, 1, 0.2], 2, 1),             # triple knot, no cut-out step
+        ([0, 2.37, 9.1, 25.003], [0, 0.1, 0.9, 1.0], 1, 1),           # off-lattice knots
+        ([4.0], [0.7], 0, 0),                                         # single knot: constant
     ]:
         V, P = np.array(V, float), np.array(P, float)
         x = probe_points(V, np.random.default_rng(3), 5000)
         y, used = eval_host(V, P, x)
-        assert used == lut, (V, P)
+        assert used == auto, (V, P, used)
+        check(V, P, x, y, steepest(V, P))
+        y, used = eval_host(V, P, x, 1)
+        assert used == general, (V, P, used)
         check(V, P, x, y, steepest(V, P))
 
 
@@ -106,6 +125,6 @@ def test_random_curves(steps, pows, dup_at, seed):
     V = np.sort(V)
     P = np.array(pows[: len(V)])
     x = probe_points(V, np.random.default_rng(seed), 2000)
-    for ff in (False, True):
-        y, used = eval_host(V, P, x, force_fallback=ff)
+    for mode in (-1, 0, 1, 2):
+        y, used = eval_host(V, P, x, mode)
         check(V, P, x, y, steepest(V, P))
