@@ -7,7 +7,7 @@ cutout); host arrays go through the library's streaming entry points
 from __future__ import annotations
 
 import ctypes as C
-import zlib
+import hashlib
 from collections import OrderedDict
 
 import numpy as np
@@ -155,12 +155,10 @@ def get_plan(matrix, ny, nx, device=None, pitch=None):
     m = sp.csr_matrix(matrix)
     device = current_device() if device is None else device
     pitch = nx if pitch is None else int(pitch)
-    key = (
-        device, ny, nx, pitch, m.shape, m.nnz,
-        zlib.crc32(np.ascontiguousarray(m.indptr).view(np.uint8)),
-        zlib.crc32(np.ascontiguousarray(m.indices).view(np.uint8)),
-        zlib.crc32(np.ascontiguousarray(m.data).view(np.uint8)),
-    )
+    h = hashlib.blake2b(digest_size=16)  # content hash: a collision would silently reuse a wrong plan
+    for a in (m.indptr, m.indices, m.data):
+        h.update(np.ascontiguousarray(a).view(np.uint8))
+    key = (device, ny, nx, pitch, m.shape, m.nnz, str(m.indices.dtype), h.digest())
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         plan = Plan(m, ny, nx, device, pitch)

@@ -374,7 +374,36 @@ def extra_measurements(torch, dev):
     ctsh = float(nx) * ny * nth
     out["heat_1440x720_slab"] = {"steps": nth, "kernel_ms": ms, "cell_ts_per_s": ctsh / ms * 1e3,
                                  "achieved_GBs": ctsh * 4 / ms / 1e6, "frac_of_hbm_peak": ctsh * 4 / ms / 1e6 / peak}
+    del f, ds, dsw, dsh, wnd, rough
+    out["indicatormatrix_1440x720_3000"] = indicator_measurement(x, y, nbus)
     return out
+
+
+def indicator_measurement(x, y, n_shapes):
+    """The step in front of the path: shapes -> indicator matrix, 3000
+    Voronoi regions on the 1440 x 720 grid.  Wall time of the public call (host
+    packing + H2D + kernels + CSR back on the host), with the oracle's clipping
+    loop timed on a few shapes beside it."""
+    import time
+
+    from atlite_b200 import gis, synthetic as syn
+
+    rings = syn.make_voronoi_shapes(x, y, n_shapes)
+    gis.compute_indicatormatrix(x, y, rings[:8])  # warm-up (context, allocator)
+    t0 = time.perf_counter()
+    m = gis.compute_indicatormatrix(x, y, rings)
+    dt = time.perf_counter() - t0
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle"))
+    import indicator_oracle as IO  # the checker, timed as the CPU stand-in for shapely's loop
+
+    k = 6
+    t0 = time.perf_counter()
+    mo = IO.indicatormatrix(x, y, [gis.geometry_rings(r) for r in rings[:k]])
+    dto = time.perf_counter() - t0
+    err = float(abs(m[:k] - mo).max())
+    return {"shapes": n_shapes, "nnz": int(m.nnz), "edges": int(sum(len(r) for r in rings)), "gpu_call_ms": dt * 1e3,
+            "cpu_oracle_ms_per_shape": dto / k * 1e3, "cpu_oracle_extrapolated_ms": dto / k * n_shapes * 1e3,
+            "max_abs_diff_on_sample": err, "column_sum_max_dev": float(abs(np.asarray(m.sum(0)).ravel() - 1).max())}
 
 
 def main():
