@@ -102,8 +102,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 
 // MODE 0: store per-cell values out[(t - t_begin), y, x]
 // MODE 1: accumulate the (NaN-skipping) time sum into out[y, x]
-template <class Phys, int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 4)
+// Rolling software pipeline over B register sets: as soon as step t has been
+// evaluated from set j its registers are reloaded with step t + B, so B - 1 steps
+// of arithmetic (and the other warps) cover every load.  Load indices are clamped
+// to the block's last step instead of predicated (at most B - 1 redundant loads
+// and evaluations per time block, their results discarded).
+template <class Phys, int MODE, int B, int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
     k_cells(const Phys phys, const GridDev gd, float* __restrict__ out, int t_begin,
             int t_end, int tb) {
   extern __shared__ float smem[];
@@ -114,23 +119,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 4)
   const auto g = make_geom<Phys::kVec>(tile, lane, gd);
   const int t0 = t_begin + blockIdx.y * tb;
   const int t1 = min(t_end, t0 + tb);
+  if (t0 >= t1) return;
 
   typename Phys::Cell c;
   phys.init(c, g, smem);
-  typename Phys::Raw ra;
+  typename Phys::Raw r[B];
   float v[4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int64_t S4 = gd.S * 4;
-  int64_t sb = (int64_t)t0 * S4;
-#pragma unroll 1
-  for (int t = t0; t < t1; ++t, sb += S4) {
-    phys.load(c, g, sb, ra);
-    phys.compute(c, g, t, ra, v, smem);
-    if (MODE == 0) {
-      store4(out + (int64_t)(t - t_begin) * gd.S_out, gd, g, v);
-    } else {
+  const int tl = t1 - 1;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
+  for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t0 + j, tl) * S4, r[j]);
+#pragma unroll 1
+  for (int t = t0; t < t1; t += B) {
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const bool live = t + j < t1;
+      phys.compute(c, g, min(t + j, tl), r[j], v, smem);
+      phys.load(c, g, (int64_t)min(t + j + B, tl) * S4, r[j]);
+      if (MODE == 0) {
+        if (live) store4(out + (int64_t)(t + j - t_begin) * gd.S_out, gd, g, v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += (live && v[q] == v[q]) ? v[q] : 0.f;
+      }
     }
   }
   if (MODE == 1) atomic_add4(out, gd, g, acc);
@@ -189,9 +201,11 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
   GridDev go = gd;
   go.out_vec = (gd.nx % 4 == 0 && aligned16(out)) ? 1 : 0;
   if (timesum)
-    k_cells<Phys, 1><<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
+    k_cells<Phys, 1, Phys::kBatch, Phys::kMinBlocks>
+        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
   else
-    k_cells<Phys, 0><<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
+    k_cells<Phys, 0, Phys::kBatch, Phys::kMinBlocks>
+        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   return ATL_OK;

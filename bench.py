@@ -374,8 +374,27 @@ def extra_measurements(torch, dev):
     ctsh = float(nx) * ny * nth
     out["heat_1440x720_slab"] = {"steps": nth, "kernel_ms": ms, "cell_ts_per_s": ctsh / ms * 1e3,
                                  "achieved_GBs": ctsh * 4 / ms / 1e6, "frac_of_hbm_peak": ctsh * 4 / ms / 1e6 / peak}
-    del f, ds, dsw, dsh, wnd, rough
+    del f, ds, dsw, dsh, wnd, rough, spec, ws, hs
     out["indicatormatrix_1440x720_3000"] = indicator_measurement(x, y, nbus)
+    # BASELINE configs[4]: Europe-scale 1000 x 800, per-cell pv + wind capacity factors (no shapes
+    # reduction: the no-matrix branch, convert.py:200-211) -> k_cells time-sum kernels
+    nx, ny, nt = 1000, 800, 240
+    x, y = syn.make_coords(nx, ny, -12.0, 33.0, 0.05, 0.05)
+    tm = syn.make_time(nt + 24 * 170)[24 * 170:]
+    f = syn.make_pv_fields_device(tm, x, y, dev, seed=9)
+    co = dict(time=tm, x=x, y=y, lon=x, lat=y)
+    spec = _PvSpec(ab.Dataset(f, coords=co), ab.get_solarpanelconfig(PANEL), ab.get_orientation(ORIENT))
+    ws = _WindSpec(ab.Dataset({"wnd100m": (f["temperature"] - 255.0) * 0.5, "roughness": f["albedo"] * 0.5 + 1e-3}, coords=co),
+                   ab.get_windturbineconfig("Vestas_V112_3MW"))
+    cts = float(nx) * ny * nt
+    ms_pv = timeit(lambda: spec.cells(timesum=True))
+    ms_w = timeit(lambda: ws.cells(timesum=True))
+    out["percell_cf_1000x800_slab"] = {
+        "steps": nt, "pv_kernel_ms": ms_pv, "wind_kernel_ms": ms_w,
+        "cell_ts_per_s_combined": cts / (ms_pv + ms_w) * 1e3,
+        "pv_frac_of_hbm_peak": cts * 20 / ms_pv / 1e6 / peak, "wind_frac_of_hbm_peak": cts * 8 / ms_w / 1e6 / peak,
+        "combined_achieved_GBs": cts * 28 / (ms_pv + ms_w) / 1e6,
+        "combined_frac_of_hbm_peak": cts * 28 / (ms_pv + ms_w) / 1e6 / peak}
     return out
 
 

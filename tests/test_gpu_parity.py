@@ -601,11 +601,11 @@ def test_config0_wind_50x50x24_one_shape_full_parity():
     assert_parity(bt(res), want, cap_of(m), what="config 0")
 
 
-def _device_cutout(nx, ny, nt, x0, y0, t_skip=0):
+def _device_cutout(nx, ny, nt, x0, y0, t_skip=0, dx=0.25, dy=0.25):
     import torch
 
     dev = torch.device("cuda", 0)
-    x, y = syn.make_coords(nx, ny, x0, y0)
+    x, y = syn.make_coords(nx, ny, x0, y0, dx, dy)
     tm = syn.make_time(nt + t_skip)[t_skip:]
     f = syn.make_pv_fields_device(tm, x, y, dev, seed=3)
     f["wnd100m"] = (f["temperature"] - 255.0) * 0.5
@@ -667,6 +667,45 @@ def test_config2_3_wind_heat_1440x720_3000_shapes_properties():
     hh = bt(c.heat_demand(threshold=1000.0, matrix=ones, aggregate_time=None))[:, 0]
     tmean = f["temperature"].reshape(10, 24, -1).double().mean(1).sum(1).cpu().numpy()
     np.testing.assert_allclose(hh, (1273.15 * nx * ny - tmean), rtol=1e-5)
+
+
+def test_config4_percell_capacity_factors_1000x800_properties():
+    """BASELINE configs[4]: Europe-scale 1000 x 800 grid, pv + wind capacity factors per
+    cell with per-cell layout weights, no shapes reduction (the no-matrix branch,
+    convert.py:200-211, twice).  96 steps; checked through (a) the oracle on a window
+    of cells (per-cell physics is independent of the neighbours), (b) mean == mean of
+    the per-cell cube, (c) layout-weighted sum == the layout= (one bus) matrix path."""
+    nx, ny, nt = 1000, 800, 96
+    c, f = _device_cutout(nx, ny, nt, -12.0, 33.0, t_skip=24 * 150, dx=0.05, dy=0.05)
+    cf_pv = c.pv("CSi", "latitude_optimal", aggregate_time="mean")
+    cf_w = c.wind("Vestas_V112_3MW", aggregate_time="mean")
+    assert cf_pv.dims == ("y", "x") and cf_pv.shape == cf_w.shape == (ny, nx)
+    pv, w = np.asarray(cf_pv.values), np.asarray(cf_w.values)
+    assert not np.isnan(pv).any() and (pv >= 0).all() and (pv < 1.2).all() and (w >= 0).all() and (w <= 1 + 1e-6).all()
+    # (a) oracle on a window
+    ys, xs = slice(397, 403), slice(500, 512)
+    od = {k: v[:, ys, xs].cpu().numpy() for k, v in f.items()}
+    od.update(time=c.data.coords["time"], lon=c.data.coords["x"][xs], lat=c.data.coords["y"][ys])
+    want_pv = O.convert_pv(od, ab.get_solarpanelconfig("CSi"), O.get_orientation("latitude_optimal")).mean(0)
+    want_w = O.convert_wind(od, ab.get_windturbineconfig("Vestas_V112_3MW")).mean(0)
+    assert_parity(pv[ys, xs], want_pv, what="config4 pv window")
+    assert_parity(w[ys, xs], want_w, what="config4 wind window")
+    # (b) the same through the per-cell cube of the first day
+    day = ab.Cutout(data=ab.Dataset({k: v[:24] for k, v in f.items()},
+                                    coords=dict(time=c.data.coords["time"][:24], x=c.data.coords["x"], y=c.data.coords["y"],
+                                                lon=c.data.coords["x"], lat=c.data.coords["y"])))
+    cube = np.asarray(day.wind("Vestas_V112_3MW", aggregate_time=None).values)
+    assert cube.shape == (24, ny, nx)
+    np.testing.assert_allclose(cube.mean(0, dtype=np.float64), day.wind("Vestas_V112_3MW", aggregate_time="mean").values,
+                               rtol=2e-5, atol=1e-6)
+    # (c) per-cell layout weights: sum(layout * cf) == the one-bus layout= path
+    lay = syn.make_layout(nx, ny)
+    layout = ab.DataArray(lay, {"y": c.data.coords["y"], "x": c.data.coords["x"]}, ("y", "x"))
+    bus = c.pv("CSi", "latitude_optimal", layout=layout, aggregate_time="mean")
+    np.testing.assert_allclose(float(np.asarray(bus.values).ravel()[0]), float((lay * pv.astype(np.float64)).sum()), rtol=2e-5)
+    combined = float((lay * (pv.astype(np.float64) + w)).sum())
+    busw = c.wind("Vestas_V112_3MW", layout=layout, aggregate_time="mean")
+    np.testing.assert_allclose(combined, float(np.asarray(bus.values).ravel()[0] + np.asarray(busw.values).ravel()[0]), rtol=2e-5)
 
 
 def test_deterministic_mode_is_bitwise_repeatable(ds_full, shapes):

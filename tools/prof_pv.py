@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only timing / ncu target for the fused kernels on device-resident data.
 
-    ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat] [small|big] [reps]
+    ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat|pvsum|pvcube|windsum|windcube] [small|big|odd|oddpad|c5] [reps]
 
 small = 200x200x8760 -> 100 shapes (bench workload); big = 1440x720x438 -> 3000 shapes;
 odd = 201x199x8760 unpadded (scalar lanes); oddpad = the same with rows padded to 204.
@@ -28,11 +28,13 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
 dev = torch.device("cuda", 0)
 if size == "small":
     nx, ny, nt, nbus, x0, y0 = 200, 200, 8760, 100, 0.0, 30.0
+elif size == "c5":  # BASELINE configs[4]: Europe-scale 1000 x 800 at 0.05 deg, per-cell outputs
+    nx, ny, nt, nbus, x0, y0 = 1000, 800, 240, 100, -12.0, 33.0
 elif size in ("odd", "oddpad"):  # nx % 4 != 0: SCALAR lane layout / rows padded to pitch 204 (VEC)
     nx, ny, nt, nbus, x0, y0 = 201, 199, 8760, 100, 0.0, 30.0
 else:
     nx, ny, nt, nbus, x0, y0 = 1440, 720, 432, 3000, -180.0, -90.0
-x, y = syn.make_coords(nx, ny, x0, y0)
+x, y = syn.make_coords(nx, ny, x0, y0, *((0.05, 0.05) if size == "c5" else ()))
 tm = syn.make_time(nt + 24 * 170)[24 * 170:] if size == "big" else syn.make_time(nt)
 f = syn.make_pv_fields_device(tm, x, y, dev, seed=7)
 pitch = nx
@@ -41,7 +43,17 @@ if size == "oddpad":  # what Cutout.to_device() does
     f = {k: torch.nn.functional.pad(v, (0, pitch - nx)).contiguous() for k, v in f.items()}
 plan = engine.get_plan(syn.make_shapes(nx, ny, nbus), ny, nx, pitch=pitch)
 coords = dict(time=tm, x=x, y=y, lon=x, lat=y)
-if kind == "pv":
+out_b = 0.0
+if kind in ("pvsum", "pvcube"):  # no-matrix branch (convert.py:200-211): per-cell time sum / cube
+    spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
+    fn, bpc = (lambda: spec.cells(timesum=kind == "pvsum")), 20
+    out_b = 0.0 if kind == "pvsum" else 4.0
+elif kind in ("windsum", "windcube"):
+    ds = ab.Dataset({"wnd100m": (f["temperature"] - 255.0) * 0.5, "roughness": f["albedo"] * 0.5 + 1e-3}, coords=coords)
+    ws = _WindSpec(ds, ab.get_windturbineconfig("Vestas_V112_3MW"))
+    fn, bpc = (lambda: ws.cells(timesum=kind == "windsum")), 8
+    out_b = 0.0 if kind == "windsum" else 4.0
+elif kind == "pv":
     spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
     fn, bpc = (lambda: spec.op.reduce(plan, spec.fields)), 20
 elif kind == "wind":
@@ -64,5 +76,6 @@ ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
 cts = float(nx) * ny * nt
 print(json.dumps({"kind": kind, "size": size, "variant": os.environ.get("ATL_VARIANT", "0"),
                   "tb": os.environ.get("ATL_TB", "auto"), "ms": round(ms, 4),
-                  "cell_ts_per_s": cts / ms * 1e3, "GBs": round(cts * bpc / ms / 1e6, 1),
-                  "frac_6573": round(cts * bpc / ms / 1e6 / 6573.5, 4), "plan": plan.info["slots_per_active_tile"]}))
+                  "cell_ts_per_s": cts / ms * 1e3, "GBs": round(cts * (bpc + out_b) / ms / 1e6, 1),
+                  "frac_6573": round(cts * (bpc + out_b) / ms / 1e6 / 6573.5, 4),
+                  "plan": plan.info["slots_per_active_tile"]}))
