@@ -48,11 +48,14 @@ class TimeShard:
             return t if t.is_cuda else t.cuda()
         return t.cpu()
 
-    def gather_time(self, local, labels=None, counts=None):
+    def gather_time(self, local, labels=None, counts=None, async_op=False):
         """Concatenate per-rank (nt_r, ...) results along time, in rank order.
         ``labels=None`` skips the (host-side, pickled) gather of the time labels;
         ``counts`` (steps per rank, when the caller knows the shard layout) skips
-        the size exchange and its host synchronisation."""
+        the size exchange and its host synchronisation.  ``async_op`` (equal shards,
+        no labels) returns ``(out, work)`` without making the current stream wait, so
+        the next conversion overlaps the NVLink transfer; ``work.wait()`` before ``out``
+        is read."""
         import torch
         import torch.distributed as dist
 
@@ -66,6 +69,8 @@ class TimeShard:
         assert len(counts) == self.world and counts[self.rank] == t.shape[0]
         if len(set(counts)) == 1:
             out = torch.empty((self.world * counts[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            if async_op and labels is None:
+                return out, dist.all_gather_into_tensor(out, t, group=self.group, async_op=True)
             dist.all_gather_into_tensor(out, t, group=self.group)
         else:  # ragged shards: pad to the longest
             m = max(counts)

@@ -156,6 +156,15 @@ def _gloo_worker(rank, world, port, q):
             out, lab = sh.gather_time(full[lo:hi], time[lo:hi])
             assert np.array_equal(out.numpy(), full), (rank, align)
             assert list(lab) == list(time)
+        # asynchronous gather of equal shards (what bench.py overlaps with the next pass)
+        lo, hi = shard_bounds(nt, world, rank, 1)
+        works = []
+        for k in range(3):
+            out, work = TimeShard().gather_time(full[lo:hi] + k, counts=[nt // world] * world, async_op=True)
+            works.append((out, work, k))
+        for out, work, k in works:
+            work.wait()
+            assert np.array_equal(out.numpy(), full + k), (rank, k)
         plane = np.full((3, 4), float(rank + 1), dtype=np.float32)
         tot, n = TimeShard().sum_over_ranks(plane, 10 * (rank + 1))
         assert np.allclose(tot.numpy(), sum(range(1, world + 1))) and n == 10 * sum(range(1, world + 1))
