@@ -6,7 +6,7 @@ hand-written sm_100a CUDA kernels in ``libatlite_b200.so``.
 """
 
 from . import resource
-from ._lib import set_deterministic
+from ._lib import release_host_staging, set_deterministic
 from .convert import (
     coefficient_of_performance,
     convert_and_aggregate,

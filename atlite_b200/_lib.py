@@ -186,6 +186,7 @@ _SIGNATURES = {
     "atl_pv_timesum": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
     "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
+    "atl_release_host_staging": (None, []),
     "atl_indicator_compute": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.c_int32, _P, _P, _P, _P, C.POINTER(_P)]),
     "atl_indicator_nnz": (C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -256,6 +257,11 @@ def check(rc):
 def set_deterministic(on=True):
     """Bitwise-repeatable fused reductions (fixed summation order); returns the previous setting."""
     return bool(load().atl_set_deterministic(1 if on else 0))
+
+
+def release_host_staging():
+    """Free the pinned staging buffers the host-streaming calls keep between calls."""
+    load().atl_release_host_staging()
 
 
 def launch_count():

@@ -7,8 +7,11 @@
 //
 // Pinned (cudaHostAlloc / cudaHostRegister'ed) inputs are DMA'd directly;
 // pageable inputs go through a pinned staging ring (memcpy -> async H2D).
+#include <algorithm>
 #include <cstring>
 #include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -33,6 +36,75 @@ static bool is_pinned(const void* p) {
     return false;
   }
   return a.type == cudaMemoryTypeHost;
+}
+
+// Pinned staging buffers for pageable inputs are kept across calls (cudaHostAlloc
+// of a few hundred MiB costs more than the transfer it serves); a call takes
+// buffers out of the pool and puts them back when it returns.
+struct StagePool {
+  std::mutex mu;
+  std::vector<std::pair<char*, size_t>> free_list;
+  char* take(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_list.size(); ++i)
+        if (free_list[i].second >= bytes && (best < 0 || free_list[i].second < free_list[best].second))
+          best = i;
+      if (best >= 0) {
+        char* p = free_list[best].first;
+        sizes.push_back({p, free_list[best].second});
+        free_list.erase(free_list.begin() + best);
+        return p;
+      }
+    }
+    char* p = nullptr;
+    if (cudaHostAlloc((void**)&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      release();  // drop cached buffers and retry once
+      if (cudaHostAlloc((void**)&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    sizes.push_back({p, bytes});
+    return p;
+  }
+  void give(char* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t i = 0; i < sizes.size(); ++i)
+      if (sizes[i].first == p) {
+        free_list.push_back(sizes[i]);
+        sizes.erase(sizes.begin() + i);
+        return;
+      }
+  }
+  void release() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& b : free_list) cudaFreeHost(b.first);
+    free_list.clear();
+  }
+  std::vector<std::pair<char*, size_t>> sizes;  // buffers currently lent out
+};
+static StagePool g_stage;
+
+// Pageable -> pinned copy on several host threads (one thread moves ~10 GB/s, the
+// PCIe link wants 50+).
+static void par_memcpy(char* dst, const char* src, size_t bytes) {
+  static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t kMin = 8u << 20;
+  unsigned nthr = (unsigned)std::min<size_t>(std::min(8u, hw), bytes / kMin);
+  if (nthr <= 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t part = ((bytes / nthr) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (unsigned k = 1; k < nthr; ++k) {
+    const size_t off = (size_t)k * part;
+    if (off >= bytes) break;
+    th.emplace_back([=] { std::memcpy(dst + off, src + off, std::min(part, bytes - off)); });
+  }
+  std::memcpy(dst, src, std::min(part, bytes));
+  for (auto& t : th) t.join();
 }
 
 static void pool_keep_memory(int device) {
@@ -108,7 +180,14 @@ static int stream_slabs(int device, const std::vector<SlabField>& fields, int64_
     const size_t bytes = (size_t)max_steps * S * fields[i].elem;
     for (int b = 0; b < NBUF; ++b) {
       SS_CUDA(cudaMallocAsync(&dev[b][i], bytes, s_copy));
-      if (!pinned[i]) SS_CUDA(cudaHostAlloc((void**)&stage[b][i], bytes, cudaHostAllocDefault));
+      if (!pinned[i]) {
+        stage[b][i] = g_stage.take(bytes);
+        if (!stage[b][i]) {
+          set_error("out of pinned host memory for the staging ring");
+          rc = ATL_ERR_CUDA;
+          goto cleanup;
+        }
+      }
     }
   }
   SS_CUDA(cudaMallocAsync((void**)&out_dev, (size_t)n_units * n_bus * sizeof(float) + 16, s_copy));
@@ -129,7 +208,7 @@ static int stream_slabs(int device, const std::vector<SlabField>& fields, int64_
         const char* src = fields[i].host + off;
         if (!pinned[i]) {
           if (it >= NBUF) SS_CUDA(cudaEventSynchronize(ev_staged[b]));  // staging slot drained
-          std::memcpy(stage[b][i], src, bytes);
+          par_memcpy(stage[b][i], src, bytes);
           src = stage[b][i];
         }
         SS_CUDA(cudaMemcpyAsync(dev[b][i], src, bytes, cudaMemcpyHostToDevice, s_copy));
@@ -153,7 +232,7 @@ cleanup:
   for (int b = 0; b < NBUF; ++b) {
     for (size_t i = 0; i < fields.size(); ++i) {
       if (dev[b][i]) cudaFreeAsync(dev[b][i], s_copy ? s_copy : 0);
-      if (stage[b][i]) cudaFreeHost(stage[b][i]);
+      if (stage[b][i]) g_stage.give(stage[b][i]);
     }
     if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
     if (ev_done[b]) cudaEventDestroy(ev_done[b]);
@@ -181,6 +260,8 @@ int heat_upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out, 
 }
 
 extern "C" {
+
+void atl_release_host_staging(void) { g_stage.release(); }
 
 int atl_pv_reduce_host(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f,
                        int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps) {

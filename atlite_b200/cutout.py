@@ -111,6 +111,32 @@ class Cutout:
             )
         return gis.compute_indicatormatrix(self.coords["x"], self.coords["y"], shapes)
 
+    # ---- host residency
+    def pin_host(self, variables=None):
+        """Return a Cutout whose (time, y, x) variables live in page-locked host memory
+        (float32 NumPy views of pinned torch tensors).  Host-streamed conversions then DMA
+        the time slabs directly at PCIe rate instead of staging pageable memory through
+        the library's pinned ring."""
+        import torch
+
+        ds = self.data
+        names = list(ds.data_vars) if variables is None else list(variables)
+        out = Dataset(coords={k: np.asarray(getattr(v, "values", v)) for k, v in dict(ds.coords).items()
+                              if k in ("time", "x", "y", "lon", "lat")},
+                      attrs=dict(getattr(ds, "attrs", {})))
+        keep = []
+        for n in names:
+            a = _convert._to_host(_convert._raw(ds, n))
+            if not (n.startswith("solar_") and a.dtype == np.float64):
+                a = np.asarray(a, dtype=np.float32)
+            t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+            t.numpy()[...] = a
+            keep.append(t)
+            out[n] = (("time", "y", "x")[-a.ndim:], t.numpy())
+        res = Cutout(data=out, time_shard=self.time_shard)
+        res._pinned = keep  # the tensors own the page-locked memory
+        return res
+
     # ---- device residency
     def to_device(self, device=None, variables=None, pad=True):
         """Return a Cutout whose (time, y, x) variables live in GPU memory as

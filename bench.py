@@ -308,6 +308,18 @@ def run_ours(args):
     dev_res = out.float().cpu().numpy()
     api_res = np.asarray(res.values).T
     agree = float(np.max(np.abs(dev_res - api_res) / (np.abs(api_res) + 1e-3)))
+    # the same call on plain (pageable) NumPy arrays: staged through the library's pinned ring
+    pageable_value = None
+    if world == 1 and not args.no_extra:
+        ds_page = ab.Dataset({k: np.array(v.numpy()) for k, v in host.items()},
+                             coords=dict(time=time_axis, x=x, y=y, lon=x, lat=y))
+        cut_page = ab.Cutout(data=ds_page)
+        cut_page.pv(PANEL, ORIENT, matrix=shapes, aggregate_time=None)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            cut_page.pv(PANEL, ORIENT, matrix=shapes, aggregate_time=None)
+        pageable_value = cell_ts_rank * 2 / (time.perf_counter() - t0)
+        del ds_page, cut_page
 
     line = {
         "metric": "grid-cell-timesteps/s on PV convert+aggregate",
@@ -324,6 +336,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "grid-cell-timesteps/s",
                 "h2d_bytes_per_step": int(cell_ts_rank * BYTES_PER_CELL_TS),
                 "d2h_bytes_per_step": int(NT * NBUS * 4), "steps": e2e_steps,
+                **({"pageable_numpy_value": pageable_value} if pageable_value else {}),
                 "api": "atlite_b200.Cutout(data=<pinned host arrays>).pv('CSi','latitude_optimal',matrix=...,aggregate_time=None)",
                 "max_rel_diff_vs_device_path": agree},
         "gpu_launches": int(launches),

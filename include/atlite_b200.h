@@ -348,6 +348,9 @@ int atl_csp_op_info(const AtlCspOp* op, int32_t* device, int32_t* ny, int32_t* n
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" evidence). */
 int64_t atl_launch_count(void);
+/* The atl_*_reduce_host calls keep their pinned staging buffers (used for pageable
+ * inputs) for the next call; this frees them. */
+void atl_release_host_staging(void);
 
 /* ------------------------------------------------------------------ */
 /* Indicator matrix: shapes -> CSR (n_shapes, ny*nx) of covered cell   */

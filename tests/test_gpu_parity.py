@@ -504,6 +504,23 @@ def test_device_resident_matches_host_streaming(ds_full, shapes):
     np.testing.assert_allclose(hh, hd, rtol=2e-5, atol=1e-4)
 
 
+def test_pinned_and_pageable_host_paths_agree(ds_full, shapes):
+    """Pageable NumPy inputs are staged through the library's pinned ring (kept across
+    calls, multi-threaded copy); pin_host() inputs are DMA'd directly: same numbers."""
+    page = ab.Cutout(data=ds_full)
+    pinned = page.pin_host()
+    for name, kw in (("pv", dict(panel="CSi", orientation="latitude_optimal")), ("wind", dict(turbine="Vestas_V112_3MW")),
+                     ("heat_demand", {})):
+        a = getattr(page, name)(matrix=shapes, aggregate_time=None, **kw).values
+        b = getattr(pinned, name)(matrix=shapes, aggregate_time=None, **kw).values
+        c = getattr(page, name)(matrix=shapes, aggregate_time=None, **kw).values  # staging buffers reused
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-4)
+        np.testing.assert_allclose(a, c, rtol=2e-5, atol=1e-4)
+    ab.release_host_staging()
+    d = page.pv("CSi", "latitude_optimal", matrix=shapes, aggregate_time=None).values  # pool refills
+    assert d.shape == (23, 72)
+
+
 def test_time_slab_offsets(ds_full, shapes):
     """A slab [t0, t0+nt) of the operator's time axis equals the same rows of the whole."""
     from atlite_b200.convert import _PvSpec
