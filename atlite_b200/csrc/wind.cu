@@ -72,9 +72,10 @@ __host__ __device__ __forceinline__ float lut_interp(float x, const char* lut, i
 // {slope, intercept}: which bucket a speed within rounding of a knot lands in does
 // not matter.  The steps come back through `nj` exact compares.  `lut` points one
 // entry past a guard copy of bucket 0 (floor may give -1 at x_lo).
+template <int NJ>  // number of steps to add back (compile time: each costs 3 instructions per cell)
 __host__ __device__ __forceinline__ float lattice_interp(float x, const char* lut, int stride,
                                                          float x_lo, float x_hi, float inv_w,
-                                                         float c0, int nj, float k1, float j1,
+                                                         float c0, float k1, float j1,
                                                          float k2, float j2) {
 #ifdef __CUDA_ARCH__
   const float xc = fmin_nan(fmax_nan(x, x_lo), x_hi);
@@ -85,8 +86,8 @@ __host__ __device__ __forceinline__ float lattice_interp(float x, const char* lu
 #endif
   const float2 e = *reinterpret_cast<const float2*>(lut + b * stride);
   float y = fmaf(e.x, xc, e.y);
-  if (nj > 0) y = (x >= k1) ? y + j1 : y;
-  if (nj > 1) y = (x >= k2) ? y + j2 : y;
+  if (NJ > 0) y = (x >= k1) ? y + j1 : y;
+  if (NJ > 1) y = (x >= k2) ? y + j2 : y;
   return y;
 }
 
@@ -138,9 +139,19 @@ struct WindPhys {
                                           const float* sm) const {
     if (use_lut == 2) {
       const char* lut = reinterpret_cast<const char*>(sm) + lut_stride + c.rep_off;  // skip the guard
+      if (nj == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        r[i] = lattice_interp(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, nj, k_jump, jump, k_end, y_end);
+        for (int i = 0; i < 4; ++i)
+          r[i] = lattice_interp<0>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
+      } else if (nj == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          r[i] = lattice_interp<1>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          r[i] = lattice_interp<2>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
+      }
       return;
     }
     if (use_lut) {
@@ -552,8 +563,12 @@ int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_
   for (int64_t i = 0; i < n; ++i) {
     if (T.use_lut == 2) {
       const char* lut = reinterpret_cast<const char*>(T.curve.data()) + T.lut_stride + ((int)i & T.rep_mask) * 8;
-      y_out[i] = lattice_interp(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0, T.nj, T.k_jump,
-                                T.jump, T.k_end, T.y_end);
+      y_out[i] = T.nj == 0   ? lattice_interp<0>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0,
+                                                  T.k_jump, T.jump, T.k_end, T.y_end)
+                 : T.nj == 1 ? lattice_interp<1>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0,
+                                                  T.k_jump, T.jump, T.k_end, T.y_end)
+                             : lattice_interp<2>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0,
+                                                  T.k_jump, T.jump, T.k_end, T.y_end);
       continue;
     }
     if (T.use_lut) {
