@@ -63,10 +63,11 @@ def full(rep):
 
 
 if __name__ == "__main__":
-    for ln in launches("gpurun_out/launches_bench.csv", f"profiles/{TAG}_launches_bench.csv")[:10]:
+    SUF = sys.argv[2] if len(sys.argv) > 2 else "r1"
+    src = f"gpurun_out/launches_bench_{SUF}.csv" if len(sys.argv) > 2 else "gpurun_out/launches_bench.csv"
+    for ln in launches(src, f"profiles/{TAG}_launches_bench.csv")[:10]:
         print(ln)
     summ = {}
-    SUF = sys.argv[2] if len(sys.argv) > 2 else "r1"
     for tag, rep in (("pv_200x200x8760_100shapes", f"gpurun_out/prof_pv_small_{SUF}.ncu-rep"),
                      ("pv_1440x720x432_3000shapes", f"gpurun_out/prof_pv_big_{SUF}.ncu-rep"),
                      ("wind_200x200x8760_100shapes", f"gpurun_out/prof_wind_small_{SUF}.ncu-rep"),
