@@ -699,7 +699,12 @@ def convert_and_aggregate(
     assert isinstance(matrix, sp.csr_matrix)
     dim, idx = _ensure_index(index, matrix.shape[0])
 
-    plan = engine.get_plan(matrix, ny, nx, pitch=getattr(spec, "pitch", None))
+    pitch = getattr(spec, "pitch", None)
+    if spec is None:  # plugin result computed from a row-padded device cutout keeps the padding
+        vals0 = getattr(da, "values", da)
+        if engine._is_torch(vals0) and vals0.ndim == 3 and vals0.shape[-1] != nx:
+            pitch = int(vals0.shape[-1])
+    plan = engine.get_plan(matrix, ny, nx, pitch=pitch)
     if spec is not None:
         res = spec.reduce(plan)  # (time, bus) float32
         time_labels, name = spec.time_labels, spec.name

@@ -104,6 +104,7 @@ class Plan:
                 f"matrix has {m.shape[1]} columns but the cutout grid has {ny}x{nx}={ny * nx} cells"
             )
         self.shape = m.shape
+        self.grid = (ny, nx)
         self.device = current_device() if device is None else device
         self._indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
         self._indices = np.ascontiguousarray(m.indices, dtype=np.int32)
@@ -139,6 +140,14 @@ class Plan:
             dense = torch.from_numpy(host_f32(dense)).to(f"cuda:{self.device}")
         dense = dense.contiguous().to(torch.float32)
         nt = dense.shape[0]
+        ny, nx = self.grid
+        ok = (dense.ndim == 3 and tuple(dense.shape[1:]) == (ny, self.pitch)) or \
+             (dense.ndim == 2 and dense.shape[1] == ny * self.pitch)
+        if not ok:
+            raise ValueError(f"per-cell values have shape {tuple(dense.shape)}; this plan expects "
+                             f"(time, {ny}, {self.pitch}) or (time, {ny * self.pitch})")
+        if dense.device.type != "cuda" or dense.device.index != self.device:
+            raise ValueError(f"per-cell values live on {dense.device}, the plan on cuda:{self.device}")
         out = torch.zeros((nt, self.n_bus), dtype=torch.float32, device=dense.device)
         if nt == 0:
             return out

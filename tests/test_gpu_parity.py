@@ -580,6 +580,14 @@ def test_field_shape_and_dtype_are_checked_before_the_raw_pointer_call(ds_full, 
         spec.op.reduce(plan, spec.wnd.double(), spec.aux.double() if spec.aux is not None else None)
     with pytest.raises(RuntimeError):  # plan built for another pitch
         spec.op.reduce(engine.get_plan(shapes, 45, 70), spec.wnd, spec.aux)
+    # generic SpMM: the dense field must have the plan's layout
+    flat_plan = engine.get_plan(shapes, 45, 70)
+    with pytest.raises(ValueError, match="expects"):
+        flat_plan.spmm(torch.zeros(3, 45, 72, device="cuda"))
+    with pytest.raises(ValueError, match="expects"):
+        plan.spmm(torch.zeros(3, 45 * 70, device="cuda"))
+    ones = plan.spmm(torch.ones(2, 45, 72, device="cuda")).cpu().numpy()
+    np.testing.assert_allclose(ones, np.tile(cap_of(shapes), (2, 1)), rtol=1e-6)
 
 
 # ------------------------------------------------------------------ size-independent properties
