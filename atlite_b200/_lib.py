@@ -187,6 +187,9 @@ _SIGNATURES = {
     "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
     "atl_release_host_staging": (None, []),
+    "atl_era5_wind": (C.c_int, [C.c_int, C.c_int64] + [_P] * 5 + [C.c_int32] + [_P] * 4 + [_P]),
+    "atl_era5_influx": (C.c_int, [C.c_int, C.c_int64] + [_P] * 4 + [C.c_int32] + [_P] * 4 + [_P]),
+    "atl_solar_position": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "atl_indicator_compute": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.c_int32, _P, _P, _P, _P, C.POINTER(_P)]),
     "atl_indicator_nnz": (C.c_int, [_P, C.POINTER(C.c_int64)]),

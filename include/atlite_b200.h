@@ -376,6 +376,30 @@ int atl_indicator_export(const AtlIndicator* ind, int64_t* indptr_out, int32_t* 
                          double* data_out);
 void atl_indicator_destroy(AtlIndicator* ind);
 
+/* ------------------------------------------------------------------ */
+/* ERA5 prepare-time derivations (datasets/era5.py:120-201), SURVEY    */
+/* section 8 f4.  All field pointers are DEVICE pointers to n float32  */
+/* values (any shape); outputs may not alias inputs.                   */
+/* ------------------------------------------------------------------ */
+/* get_data_wind (era5.py:120-135) [+ sanitize_wind :141-146 if sanitize != 0]:
+ * wnd100m = |(u100, v100)|, wnd_shear_exp = ln(|(u10, v10)| / wnd100m) / ln(10/100),
+ * wnd_azimuth = atan2(u100, v100) mapped to [0, 2 pi), roughness = fsr (< 0 -> 2e-4). */
+int atl_era5_wind(int device, int64_t n, const float* u100, const float* v100, const float* u10,
+                  const float* v10, const float* fsr, int32_t sanitize, float* wnd100m,
+                  float* wnd_shear_exp, float* wnd_azimuth, float* roughness, void* stream);
+/* get_data_influx (era5.py:163-175) [+ sanitize_influx :195-201]: albedo =
+ * ((ssrd - ssr) / ssrd, 0 where ssrd == 0 or NaN), influx_diffuse = ssrd - fdir, and
+ * influx_{toa, direct, diffuse} converted J m-2 -> W m-2 (/ 3600) [clipped at 0]. */
+int atl_era5_influx(int device, int64_t n, const float* ssrd, const float* ssr, const float* tisr,
+                    const float* fdir, int32_t sanitize, float* influx_toa, float* influx_direct,
+                    float* influx_diffuse, float* albedo, void* stream);
+/* SolarPosition (pv/solar_position.py:69-116) materialised as the cutout variables
+ * solar_altitude / solar_azimuth (era5.py:182-188 uses time_shift = -30 min):
+ * (nt, ny, nx) float64 each, device; time / lon / lat are host arrays. */
+int atl_solar_position(int device, const int64_t* time_ns_host, int64_t nt, int64_t time_shift_ns,
+                       const double* lon_deg_host, int32_t nx, const double* lat_deg_host, int32_t ny,
+                       double* altitude_dev, double* azimuth_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
