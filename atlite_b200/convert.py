@@ -701,7 +701,7 @@ def convert_and_aggregate(
 
     pitch = getattr(spec, "pitch", None)
     if spec is None:  # plugin result computed from a row-padded device cutout keeps the padding
-        vals0 = getattr(da, "values", da)
+        vals0 = da if engine._is_torch(da) else getattr(da, "values", da)
         if engine._is_torch(vals0) and vals0.ndim == 3 and vals0.shape[-1] != nx:
             pitch = int(vals0.shape[-1])
     plan = engine.get_plan(matrix, ny, nx, pitch=pitch)
@@ -709,7 +709,7 @@ def convert_and_aggregate(
         res = spec.reduce(plan)  # (time, bus) float32
         time_labels, name = spec.time_labels, spec.name
     else:
-        vals = getattr(da, "values", da)
+        vals = da if engine._is_torch(da) else getattr(da, "values", da)
         res = plan.spmm(np.asarray(vals) if not engine._is_torch(vals) else vals)
         time_labels = pd.Index(np.asarray(da.coords["time"])) if hasattr(da, "coords") else pd.RangeIndex(len(vals))
         name = getattr(da, "name", None)

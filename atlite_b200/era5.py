@@ -41,6 +41,8 @@ def _raw(ds, name):
     if name not in ds:
         raise KeyError(f"raw ERA5 variable {name!r} missing")
     v = ds.raw(name) if hasattr(ds, "raw") else ds[name]
+    if _is_torch(v):  # (torch.Tensor.values is a method: do not unwrap tensors)
+        return v
     return getattr(v, "values", v)
 
 

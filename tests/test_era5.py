@@ -99,6 +99,14 @@ def test_gpu_raw_download_to_conversion_end_to_end():
     nx, ny, nt = 40, 12, 48
     ds, d = _raw_dataset(nx, ny, nt, seed=4)
     cut = ab.Cutout(data=era5.prepare(ds))
+    # raw fields that are already on the device take the same path
+    import torch
+
+    ds_dev = ab.Dataset({k: (("time", "y", "x"), torch.from_numpy(v).cuda()) for k, v in d.items()},
+                        coords=dict(ds.coords))
+    again = era5.prepare(ds_dev, features=("wind", "influx"))
+    for k in ("wnd100m", "wnd_azimuth", "albedo", "influx_diffuse", "solar_azimuth"):
+        assert torch.equal(again.raw(k), cut.data.raw(k)) or torch.allclose(again.raw(k), cut.data.raw(k), equal_nan=True), k
     assert {"wnd100m", "roughness", "influx_toa", "albedo", "solar_altitude", "temperature", "runoff"} <= set(cut.data.data_vars)
     m = syn.make_shapes(nx, ny, 5)
     ow = EO.get_data_wind(d["u100"], d["v100"], d["u10"], d["v10"], d["fsr"])
