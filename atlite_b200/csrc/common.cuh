@@ -357,8 +357,9 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
   }
   const int f = (lane >> 2) & 3;
   int s = s_beg;
+  const int32_t* rp = plan.slot_row + s_beg + f;  // running pointer: this lane's slot of the group
 #pragma unroll 1
-  for (; s_end - s >= 2; s += 4) {
+  for (; s_end - s >= 2; s += 4, rp += 4) {
     const float4* wp = plan.slot_w4 + (size_t)s * 32 + lane;
     float a[4], b[4];
 #pragma unroll
@@ -374,7 +375,7 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
     a[0] += __shfl_xor_sync(0xffffffffu, a[1], 4);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(plan.slot_row + s + f), a[0]);
+    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(rp), a[0]);
   }
   if (s < s_end) {  // one slot left
     const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);

@@ -91,8 +91,8 @@ __host__ __device__ __forceinline__ float lattice_interp(float x, const char* lu
   return y;
 }
 
-template <bool VEC>
-struct WindPhys {
+template <bool VEC, int METHOD>  // METHOD: ATL_WIND_NONE / _LOG / _POWER, compile time (no predicated
+struct WindPhys {                // duplicates of the loads, no uniform branches in the per-cell code)
   static constexpr bool kVec = VEC;
   using Geom = TileGeomT<VEC>;
   const float* wnd;
@@ -132,7 +132,7 @@ struct WindPhys {
   }
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
     load4(wnd, tb, g, r.w);
-    if (method != ATL_WIND_NONE) load4(aux, tb, g, r.a);
+    if (METHOD != ATL_WIND_NONE) load4(aux, tb, g, r.a);
   }
   // np.interp for the lane's 4 values at once.
   __device__ __forceinline__ void interp4(const Cell& c, const float (&x)[4], float (&r)[4],
@@ -185,12 +185,12 @@ struct WindPhys {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       x[i] = r.w[i];
-      if (method == ATL_WIND_LOG) {
+      if (METHOD == ATL_WIND_LOG) {
         // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
         // (not rewritten as v + v*c/(..): z0 = 0 must give NaN = inf/inf like the reference)
         const float L = __log2f(r.a[i]);
         x[i] = x[i] * __fdividef(lg2_to - L, lg2_from - L);
-      } else if (method == ATL_WIND_POWER) {
+      } else if (METHOD == ATL_WIND_POWER) {
         x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
     }
@@ -216,9 +216,9 @@ struct AtlWindOp {
   float* d_curve = nullptr;
 };
 
-template <bool VEC>
-static WindPhys<VEC> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
-  WindPhys<VEC> p;
+template <bool VEC, int METHOD>
+static WindPhys<VEC, METHOD> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
+  WindPhys<VEC, METHOD> p;
   p.wnd = f->wnd;
   p.aux = f->aux;
   p.curve = op->d_curve;
@@ -606,9 +606,19 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
                   plan->grid.pitch == op->grid.pitch,
               "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
-  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
-  return dispatch_reduce(make, plan, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt,
-                         (cudaStream_t)stream);
+  const bool al = aligned16(f->wnd) && aligned16(f->aux);
+#define ATL_WIND_CASE(M)                                                                  \
+  case M: {                                                                               \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+    return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);            \
+  }
+  switch (op->method) {
+    ATL_WIND_CASE(ATL_WIND_NONE)
+    ATL_WIND_CASE(ATL_WIND_LOG)
+    ATL_WIND_CASE(ATL_WIND_POWER)
+  }
+#undef ATL_WIND_CASE
+  return ATL_ERR_INVALID;
 }
 
 int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, float* out_dev,
@@ -617,9 +627,19 @@ int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, floa
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
-  return dispatch_cells(make, op->grid, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt, false,
-                        (cudaStream_t)stream);
+  const bool al = aligned16(f->wnd) && aligned16(f->aux);
+#define ATL_WIND_CASE(M)                                                                  \
+  case M: {                                                                               \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+    return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);  \
+  }
+  switch (op->method) {
+    ATL_WIND_CASE(ATL_WIND_NONE)
+    ATL_WIND_CASE(ATL_WIND_LOG)
+    ATL_WIND_CASE(ATL_WIND_POWER)
+  }
+#undef ATL_WIND_CASE
+  return ATL_ERR_INVALID;
 }
 
 int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, float* out_dev,
@@ -628,9 +648,19 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, fl
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
-  auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f); };
-  return dispatch_cells(make, op->grid, aligned16(f->wnd) && aligned16(f->aux), out_dev, nt, true,
-                        (cudaStream_t)stream);
+  const bool al = aligned16(f->wnd) && aligned16(f->aux);
+#define ATL_WIND_CASE(M)                                                                  \
+  case M: {                                                                               \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);  \
+  }
+  switch (op->method) {
+    ATL_WIND_CASE(ATL_WIND_NONE)
+    ATL_WIND_CASE(ATL_WIND_LOG)
+    ATL_WIND_CASE(ATL_WIND_POWER)
+  }
+#undef ATL_WIND_CASE
+  return ATL_ERR_INVALID;
 }
 
 }  // extern "C"
