@@ -2,12 +2,15 @@
 imported by atlite_b200).  NumPy float64 restatement of the arithmetic in
 /root/reference/atlite/datasets/era5.py, each function citing the lines it follows.
 
-PARITY PINNING: **unpinned against an executed reference** -- the reference computes
-these inside ``get_data_*`` after a CDS download (``retrieve_data``), which cannot run
-here (no network, no cdsapi / xarray); the reference's tests hold no numeric vectors
-for them.  Pinned on hand-computable known answers in tests/test_era5.py; the solar
-position is the already pinned ``atlite_oracle.solar_position`` (golden vectors of the
-reference's own pv/solar_position.py).
+PARITY PINNING: **pinned against the reference's own source.**  The reference computes
+these inside ``get_data_*`` after a CDS download; tests/golden/make_golden.py::era5_cases
+loads datasets/era5.py from /root/reference under the xarray/dask stand-in
+(tests/golden/xr_shim.py), replaces only ``retrieve_data`` (the download) and
+``_rename_and_clean_coords`` (coordinate renaming) and records the outputs of
+get_data_wind / sanitize_wind / get_data_influx / sanitize_influx (incl. the stored solar
+position) in tests/golden/reference_era5.npz.  tests/test_era5.py holds this oracle to
+them (the reference computes in float32: 6e-7; solar position 1e-12), plus
+hand-computable known answers.  Not pinned against genuine xarray/dask (absent here).
 """
 
 from __future__ import annotations

@@ -221,5 +221,55 @@ def main():
     print(f"{len(cases)} cases -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
 
 
+def era5_cases():
+    """The arithmetic of datasets/era5.py AFTER the download (get_data_wind :120-135,
+    sanitize_wind :141-146, get_data_influx :163-188, sanitize_influx :195-201) executed from
+    the reference's own source: ``retrieve_data`` (the CDS request) and
+    ``_rename_and_clean_coords`` (longitude/latitude renaming) are replaced by a stand-in that
+    hands over seeded raw fields.  -> tests/golden/reference_era5.npz"""
+    era5 = xr_shim.load_reference_era5()
+    nx, ny, nt = 11, 7, 30
+    rng = np.random.default_rng(21)
+    x, y = np.arange(nx) * 1.5 - 9.0, np.arange(ny) * 6.0 - 20.0
+    t = pd.date_range("2013-09-21 18:00", periods=nt, freq="h")
+    co = dict(time=t, x=x, y=y, lon=x, lat=y)
+
+    def f(lo, hi):
+        return rng.uniform(lo, hi, (nt, ny, nx)).astype(np.float32)
+
+    raw = dict(u100=f(-15, 15), v100=f(-15, 15), u10=f(-8, 8), v10=f(-8, 8), fsr=f(-0.05, 2.0),
+               ssrd=f(0, 3.0e6), tisr=f(-50, 4.5e6))
+    raw["ssr"] = (raw["ssrd"] * rng.uniform(0.6, 1.0, (nt, ny, nx))).astype(np.float32)
+    raw["fdir"] = (raw["ssrd"] * rng.uniform(0.0, 1.1, (nt, ny, nx))).astype(np.float32)
+    raw["ssrd"][0, 0, :4] = 0.0
+    raw["ssr"][0, 1, 2] = np.nan
+    raw["fsr"][0, 2, 2] = np.nan
+    raw["u100"][0, 0, 0], raw["v100"][0, 0, 0] = 0.0, -3.0
+    raw["u100"][0, 0, 1], raw["v100"][0, 0, 1] = -2.0, 0.0
+    units = dict(u100="m s**-1", v100="m s**-1", u10="m s**-1", v10="m s**-1", fsr="m",
+                 ssrd="J m**-2", ssr="J m**-2", tisr="J m**-2", fdir="J m**-2")
+    ds_raw = xr_shim.Dataset({k: xr_shim.DataArray(v, co, ("time", "y", "x"), attrs={"units": units[k]})
+                              for k, v in raw.items()}, coords=co)
+    era5.retrieve_data = lambda **kw: ds_raw  # noqa: E731  (every get_data_* picks its variables by name)
+    era5._rename_and_clean_coords = lambda ds, add_lon_lat=True: ds  # noqa: E731
+    out = {"x": x, "y": y, "time_ns": pd.DatetimeIndex(t).as_unit("ns").asi8}
+    out.update({f"raw|{k}": v for k, v in raw.items()})
+    wind = era5.get_data_wind({})
+    for k in ("wnd100m", "wnd_shear_exp", "wnd_azimuth", "roughness"):
+        out[f"wind|{k}"] = np.asarray(wind[k].values)
+    wind_s = era5.sanitize_wind(wind)
+    out["wind_sanitized|roughness"] = np.asarray(wind_s["roughness"].values)
+    infl = era5.get_data_influx({})
+    for k in ("influx_toa", "influx_direct", "influx_diffuse", "albedo", "solar_altitude", "solar_azimuth"):
+        out[f"influx|{k}"] = np.asarray(infl[k].values)
+    infl_s = era5.sanitize_influx(infl)
+    for k in ("influx_toa", "influx_direct", "influx_diffuse"):
+        out[f"influx_sanitized|{k}"] = np.asarray(infl_s[k].values)
+    path = os.path.join(HERE, "reference_era5.npz")
+    np.savez_compressed(path, **out)
+    print(f"era5 derivations -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     main()
+    era5_cases()

@@ -135,6 +135,14 @@ class DataArray:
     def chunk(self, *a, **k):
         return self
 
+    def assign_attrs(self, *args, **kw):
+        out = self._new(self.values)
+        out.attrs = dict(self.attrs)
+        for a in args:
+            out.attrs.update(a)
+        out.attrs.update(kw)
+        return out
+
     def copy(self):
         out = self._new(self.values.copy())
         out.attrs = dict(self.attrs)
@@ -451,8 +459,26 @@ class Dataset:
             out._vars[mapping.get(k, k)] = self._vars[k]
         return out
 
+    def drop_vars(self, names, errors="raise"):
+        names = [names] if isinstance(names, str) else list(names)
+        out = Dataset(coords={k: v for k, v in self._coords.items() if k not in names}, attrs=self.attrs)
+        for k, v in self._vars.items():
+            if k not in names:
+                out._vars[k] = v
+        return out
+
     def load(self, **kw):
         return self
+
+
+def merge(objs):
+    out = Dataset(attrs=getattr(objs[0], "attrs", {}))
+    for o in objs:
+        for ck, cv in o._coords.items():
+            out._coords.setdefault(ck, cv)
+        for k, v in o._vars.items():
+            out._vars[k] = v
+    return out
 
 
 def apply_ufunc(func, *args, input_core_dims=None, output_core_dims=None, output_dtypes=None,
@@ -481,7 +507,7 @@ def install():
     if "atlite.convert" in sys.modules and getattr(sys.modules["atlite.convert"], "_shimmed", False):
         return sys.modules["atlite.convert"]
     xr = _module("xarray", DataArray=DataArray, Dataset=Dataset, Coordinates=Coordinates,
-                 apply_ufunc=apply_ufunc, date_range=date_range)
+                 apply_ufunc=apply_ufunc, date_range=date_range, merge=merge)
     xr.testing = types.SimpleNamespace()
 
     class _DaskArray:  # isinstance(da.data, Array) is False for NumPy-backed data
@@ -493,6 +519,8 @@ def install():
     d = _module("dask", compute=lambda *a, **k: a, delayed=lambda f=None, **k: f)
     d.array = _module("dask.array", **ufuncs)
     _module("dask.array.core", Array=_DaskArray)
+    _module("dask.utils", SerializableLock=type("SerializableLock", (), {}))
+    _module("cdsapi")  # datasets/era5.py imports it at module level; never called here
 
     class ProgressBar:
         def __init__(self, *a, **k):
@@ -540,3 +568,15 @@ def install():
     conv = load("atlite.convert", "convert.py")
     conv._shimmed = True
     return conv
+
+
+def load_reference_era5():
+    """atlite/datasets/era5.py from its source file, for the arithmetic after the download
+    (get_data_wind / get_data_influx / sanitize_*).  The caller replaces ``retrieve_data``
+    and ``_rename_and_clean_coords`` (CDS request + coordinate renaming) by a stand-in."""
+    install()
+    spec = importlib.util.spec_from_file_location("atlite.datasets.era5", f"{REF}/datasets/era5.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["atlite.datasets.era5"] = mod
+    spec.loader.exec_module(mod)
+    return mod

@@ -1,6 +1,8 @@
 """ERA5 prepare-time derivations: oracle known answers on the CPU,
 CUDA kernels (csrc/era5.cu, through the C ABI) against the oracle on the GPU."""
 
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -29,6 +31,66 @@ def test_oracle_known_answers():
     np.testing.assert_allclose(i["influx_toa"], [10.0, 0.0, 0.0, 2.0])
     raw = EO.get_data_influx([3600.0], [0.0], [-3.6], [7200.0], sanitize=False)
     np.testing.assert_allclose([raw["influx_diffuse"][0], raw["influx_toa"][0]], [-1.0, -0.001])
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_era5.npz")
+
+
+def _golden():
+    g = np.load(GOLDEN)
+    raw = {k.split("|")[1]: g[k] for k in g.files if k.startswith("raw|")}
+    return g, raw
+
+
+def _close(got, want, what, tol=6e-7):
+    """fp32 reference values (the reference computes these in float32) vs the float64 oracle
+    (tol 6e-7: the reference's own rounding) or the fp32 kernels (tol 4e-6: both sides round,
+    the kernels use approximate division / sqrt): relative, plus the same absolute for the
+    difference-of-logs (shear exponent) and the angles."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    np.testing.assert_allclose(got, want, rtol=tol, atol=tol, equal_nan=True, err_msg=what)
+
+
+def test_oracle_is_pinned_to_the_reference_source():
+    """tests/golden/reference_era5.npz was produced by datasets/era5.py's own lines
+    (make_golden.py::era5_cases); the oracle must reproduce them."""
+    g, raw = _golden()
+    for sanitize, tag in ((False, ""), (True, "_sanitized")):
+        w = EO.get_data_wind(raw["u100"], raw["v100"], raw["u10"], raw["v10"], raw["fsr"], sanitize=sanitize)
+        for k in ("wnd100m", "wnd_shear_exp", "wnd_azimuth"):
+            _close(w[k], g[f"wind|{k}"], k)
+        _close(w["roughness"], g[f"wind{tag}|roughness"], "roughness" + tag)
+        i = EO.get_data_influx(raw["ssrd"], raw["ssr"], raw["tisr"], raw["fdir"], sanitize=sanitize)
+        _close(i["albedo"], g["influx|albedo"], "albedo")
+        for k in ("influx_toa", "influx_direct", "influx_diffuse"):
+            _close(i[k], g[f"influx{tag}|{k}"], k + tag)
+    t = pd.DatetimeIndex(g["time_ns"].astype("datetime64[ns]"))
+    sol = O.solar_position(dict(time=t, lon=g["x"], lat=g["y"]), time_shift="-30min")
+    np.testing.assert_allclose(sol["altitude"], g["influx|solar_altitude"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(sol["azimuth"], g["influx|solar_azimuth"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_reference_golden_vectors():
+    from atlite_b200 import era5
+
+    g, raw = _golden()
+    t = pd.DatetimeIndex(g["time_ns"].astype("datetime64[ns]"))
+    ds = ab.Dataset({k: (("time", "y", "x"), v) for k, v in raw.items()},
+                    coords=dict(time=t, x=g["x"], y=g["y"], lon=g["x"], lat=g["y"]))
+    for sanitize, tag in ((False, ""), (True, "_sanitized")):
+        w = era5.get_data_wind(ds, sanitize=sanitize)
+        for k in ("wnd100m", "wnd_shear_exp", "wnd_azimuth"):
+            _close(w.raw(k).cpu().numpy(), g[f"wind|{k}"], k, 4e-6)
+        _close(w.raw("roughness").cpu().numpy(), g[f"wind{tag}|roughness"], "roughness" + tag, 4e-6)
+        i = era5.get_data_influx(ds, sanitize=sanitize)
+        _close(i.raw("albedo").cpu().numpy(), g["influx|albedo"], "albedo", 4e-6)
+        for k in ("influx_toa", "influx_direct", "influx_diffuse"):
+            _close(i.raw(k).cpu().numpy(), g[f"influx{tag}|{k}"], k + tag, 4e-6)
+    np.testing.assert_allclose(i.raw("solar_altitude").cpu().numpy(), g["influx|solar_altitude"], rtol=0, atol=1e-10)
+    d = np.angle(np.exp(1j * (i.raw("solar_azimuth").cpu().numpy() - g["influx|solar_azimuth"])))
+    assert np.abs(d).max() < 2e-7
 
 
 def _raw_dataset(nx, ny, nt, seed=0, x0=-10.0, y0=35.0):
