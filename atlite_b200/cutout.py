@@ -16,7 +16,7 @@ import numpy as np
 import pandas as pd
 
 from . import convert as _convert
-from .labelled import HAVE_XARRAY, DataArray, Dataset, make_dataarray
+from .labelled import HAVE_XARRAY, Dataset, make_dataarray
 
 if HAVE_XARRAY:  # pragma: no cover
     import xarray as xr

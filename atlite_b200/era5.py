@@ -20,8 +20,6 @@ ready for ``Cutout(data=...)``.  Kernels: csrc/era5.cu; no CPU fallback.
 
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import pandas as pd
 

@@ -3,11 +3,9 @@ pins in test/test_aggregate_time.py and the physical properties it checks in
 test/test_preparation_and_conversion.py (night => exactly 0, no NaN, > 0,
 capacity == layout sums, tracking ordering), on synthetic data."""
 
-import warnings
 
 import numpy as np
 import pytest
-import scipy.sparse as sp
 from conftest import oracle_ds
 
 import atlite_oracle as O

@@ -6,7 +6,6 @@ duplicates, explicit zeros and empty rows."""
 import ctypes as C
 
 import numpy as np
-import pytest
 import scipy.sparse as sp
 from hypothesis import given, settings, strategies as st
 
