@@ -35,7 +35,7 @@ from .convert import (
     wind,
 )
 from .cutout import Cutout
-from .labelled import DataArray, Dataset
+from .labelled import DataArray, Dataset, LazyDataset
 from .orientation import get_orientation
 from .resource import (
     cspinstallations,
@@ -50,7 +50,7 @@ from .resource import (
 __version__ = "0.1.0"
 
 __all__ = [
-    "Cutout", "Dataset", "DataArray", "convert_and_aggregate", "convert_pv", "convert_wind",
+    "Cutout", "Dataset", "LazyDataset", "DataArray", "convert_and_aggregate", "convert_pv", "convert_wind",
     "convert_heat_demand", "pv", "wind", "heat_demand", "get_orientation",
     "get_windturbineconfig", "get_solarpanelconfig", "windturbine_smooth", "windturbines",
     "solarpanels", "resource", "set_deterministic",

@@ -46,6 +46,7 @@ class PlanInfo(C.Structure):
         ("fused", C.c_int32),
         ("pitch", C.c_int32),
         ("vec", C.c_int32),
+        ("n_pairs", C.c_int64),
     ]
 
 
@@ -72,6 +73,7 @@ class PvConfig(C.Structure):
         ("output", C.c_int32),
         ("thermal", C.c_double * 3),
         ("pitch", C.c_int32),
+        ("orientation_2d", C.c_int32),
     ]
 
 
@@ -177,13 +179,15 @@ _SIGNATURES = {
     "atl_plan_create_pitched": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "atl_plan_tiling_host": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(PlanInfo), _P, _P, _P, C.c_int64]),
+    "atl_plan_pairs_host": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int64), _P, _P, _P,
+                                      C.c_int64, C.c_int64]),
     "atl_plan_destroy": (None, [_P]),
     "atl_spmm": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "atl_pv_create": (C.c_int, [C.c_int, C.POINTER(PvConfig), C.POINTER(_P)]),
     "atl_pv_destroy": (None, [_P]),
     "atl_pv_reduce": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
     "atl_pv_cells": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
-    "atl_pv_timesum": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_pv_timesum": (C.c_int, [_P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, _P, _P]),
     "atl_pv_reduce_host": (C.c_int, [_P, _P, C.POINTER(PvFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_pv_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
     "atl_release_host_staging": (None, []),
@@ -200,28 +204,28 @@ _SIGNATURES = {
     "atl_wind_destroy": (None, [_P]),
     "atl_wind_reduce": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, _P]),
     "atl_wind_cells": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),
-    "atl_wind_timesum": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),
+    "atl_wind_timesum": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P, _P]),
     "atl_wind_reduce_host": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, C.c_int64]),
     "atl_wind_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
     "atl_heat_create": (C.c_int, [C.c_int, C.POINTER(HeatConfig), C.POINTER(_P)]),
     "atl_heat_destroy": (None, [_P]),
     "atl_heat_reduce": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
     "atl_heat_cells": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
-    "atl_heat_timesum": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "atl_heat_timesum": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "atl_heat_reduce_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int64]),
     "atl_heat_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
     "atl_pointwise_create": (C.c_int, [C.c_int, C.POINTER(PointwiseConfig), C.POINTER(_P)]),
     "atl_pointwise_destroy": (None, [_P]),
     "atl_pointwise_reduce": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "atl_pointwise_cells": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
-    "atl_pointwise_timesum": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "atl_pointwise_timesum": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "atl_pointwise_reduce_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64]),
     "atl_pointwise_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 3),
     "atl_csp_create": (C.c_int, [C.c_int, C.POINTER(CspConfig), C.POINTER(_P)]),
     "atl_csp_destroy": (None, [_P]),
     "atl_csp_reduce": (C.c_int, [_P, _P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
     "atl_csp_cells": (C.c_int, [_P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
-    "atl_csp_timesum": (C.c_int, [_P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P]),
+    "atl_csp_timesum": (C.c_int, [_P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, _P, _P]),
     "atl_csp_reduce_host": (C.c_int, [_P, _P, C.POINTER(CspFields), C.c_int64, C.c_int64, _P, C.c_int64]),
     "atl_csp_op_info": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 4),
 }

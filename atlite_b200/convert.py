@@ -76,6 +76,10 @@ def _grid_shape(ds):
 
 
 def _is_dask_backed(ds):
+    """Lazily loaded cutout: a dask-backed xarray dataset (what ``Cutout(path)`` opens,
+    cutout.py:142-154) or an ``atlite_b200.LazyDataset``."""
+    if getattr(ds, "lazy", False):
+        return True
     if not HAVE_XARRAY or hasattr(ds, "raw"):
         return False
     try:
@@ -114,6 +118,11 @@ class _Spec:
             for k, v in fields.items()
         }
 
+    def cells_timesum(self):
+        """(NaN-skipping per-cell time sum, number of valid steps per cell), each (y, x)."""
+        sc = self.cells(timesum=True)
+        return sc[0], sc[1]
+
 
 class _PvSpec(_Spec):
     name = "specific generation"
@@ -144,14 +153,28 @@ class _PvSpec(_Spec):
         lon_r = DataArray(np.radians(lon), {"x": _coord(ds, "x")}, ("x",), "lon")
         lat_r = DataArray(np.radians(lat), {"y": _coord(ds, "y")}, ("y",), "lat")
         o = orientation(lon_r, lat_r, None)
-        slope = np.asarray(getattr(o["slope"], "values", o["slope"]), dtype=np.float64)
-        azimuth = np.asarray(getattr(o["azimuth"], "values", o["azimuth"]), dtype=np.float64)
-        for nm, arr in (("slope", slope), ("azimuth", azimuth)):
-            if arr.ndim > 1 or (arr.ndim == 1 and arr.shape[0] != ny):
-                raise NotImplementedError(
-                    f"orientation {nm} must be a scalar or vary with latitude (y) only; "
-                    f"got shape {arr.shape}"
-                )
+
+        def table(v, nm):
+            """slope / azimuth of the callback (pv/orientation.py:107) -> scalar, (y,) or (y, x)."""
+            if hasattr(v, "dims") and hasattr(v, "transpose") and getattr(v, "ndim", 0) >= 1:
+                dims = tuple(v.dims)
+                if not set(dims) <= {"y", "x"}:
+                    raise NotImplementedError(
+                        f"orientation {nm} varies along {dims}; only (y, x)-dependent orientations are "
+                        "supported (the orientation may not depend on time / the solar position)")
+                v = v.transpose(*[d for d in ("y", "x") if d in dims])
+                arr = np.asarray(v.values, dtype=np.float64)
+                return arr[None, :] * np.ones((ny, 1)) if dims == ("x",) else arr
+            arr = np.asarray(getattr(v, "values", v), dtype=np.float64)
+            if arr.ndim == 0 or arr.shape == (ny,) or arr.shape == (ny, nx):
+                return arr
+            if arr.shape == (nx,):
+                return arr[None, :] * np.ones((ny, 1))
+            raise NotImplementedError(
+                f"orientation {nm} must be a scalar, vary with latitude (y), or be a (y, x) array; "
+                f"got shape {arr.shape}")
+
+        slope, azimuth = table(o["slope"], "slope"), table(o["azimuth"], "azimuth")
 
         # TiltedIrradiation inputs (pv/irradiation.py:202-213)
         if _has(ds, "influx"):
@@ -277,6 +300,12 @@ def _cop_spec(ds, source, sink_T, c0, c1, c2):
 def _runoff_spec(ds, weight_with_height=True):
     scale = None
     if weight_with_height:
+        if not _has(ds, "height"):
+            raise KeyError(
+                "runoff(weight_with_height=True) needs the static 'height' variable (datasets/era5.py:65-81: "
+                "geopotential z / g0); prepare the cutout with the 'height' feature "
+                "(atlite_b200.era5.get_data_height) or pass weight_with_height=False"
+            )
         h = _raw(ds, "height")
         scale = _to_host(h)
         if scale.ndim == 3:
@@ -512,12 +541,137 @@ _SPECS = {
 }
 
 
+# identity -> spec: this package's own convert_* objects ...
+_REGISTRY = {globals()[_n]: _s for _n, _s in _SPECS.items()}
+
+
+def _reference_registry():
+    """... plus the reference's, when the caller has imported it (``atlite.convert``
+    in sys.modules): a script written against the reference passes
+    ``atlite.convert.convert_pv`` etc. as ``convert_func``."""
+    import sys
+
+    mod = sys.modules.get("atlite.convert")
+    if mod is None:
+        return {}
+    return {getattr(mod, n): s for n, s in _SPECS.items() if callable(getattr(mod, n, None))}
+
+
 def _known_spec(convert_func):
-    name = getattr(convert_func, "__name__", "")
-    mod = getattr(convert_func, "__module__", "") or ""
-    if name in _SPECS and (mod.startswith("atlite_b200") or mod.startswith("atlite")):
-        return _SPECS[name]
-    return None
+    """Fused operator for a KNOWN converter, matched by identity (never by name: a user
+    plugin that happens to be called ``convert_pv`` keeps the plugin protocol)."""
+    try:
+        spec = _REGISTRY.get(convert_func)
+        return spec if spec is not None else _reference_registry().get(convert_func)
+    except TypeError:  # unhashable callable
+        return None
+
+
+# --------------------------------------------------------------------------
+# time-partitioned execution: several GPUs from one process, lazily loaded cutouts
+# --------------------------------------------------------------------------
+
+
+PART_BYTES = 1 << 30  # input bytes per time part of a lazily loaded cutout
+
+
+def _time_slice(ds, lo, hi):
+    """Steps [lo, hi) of a cutout dataset (views for in-memory data; for a dask-backed
+    xarray dataset still lazy: only these steps are read when the part is converted)."""
+    if hasattr(ds, "isel_time"):
+        return ds.isel_time(lo, hi)
+    return ds.isel(time=slice(lo, hi))
+
+
+def _bytes_per_step(ds):
+    ny, nx = _grid_shape(ds)
+    names = list(ds.data_vars) if hasattr(ds, "data_vars") else list(ds)
+    if hasattr(ds, "dims_of"):
+        n3 = sum(1 for n in names if len(ds.dims_of(n)) == 3)
+    else:
+        n3 = sum(1 for n in names if len(ds[n].dims) == 3)  # xarray: metadata only, nothing is read
+    return max(1, n3) * ny * nx * 4
+
+
+def _is_host_resident(ds):
+    """No variable lives on a GPU (device-resident cutouts are single-device objects)."""
+    if not hasattr(ds, "raw") or getattr(ds, "lazy", False):
+        return True
+    return not any(engine._is_torch(ds.raw(n)) and ds.raw(n).is_cuda for n in ds.keys())
+
+
+def _partition(ds, n_time, devices, lazy, day_offsets=None):
+    """Contiguous time parts [(lo, hi, device)], in time order.  In-memory cutouts get one
+    part per device; lazily loaded ones (dask-backed) parts of ~1 GiB of input, cut on the
+    dataset's own time chunks (cutout.py:143: {"time": 100}), so a cutout that does not
+    fit the host memory streams through it.  ``day_offsets`` (heat / cooling demand):
+    part boundaries are snapped to calendar-day starts of the shifted axis."""
+    from .dist import shard_bounds
+
+    n_dev = len(devices)
+    if n_time == 0:
+        return [(0, 0, devices[0])]
+    cuts = [0]
+    if lazy:
+        unit = 100
+        try:
+            ch = ds.chunks.get("time") if hasattr(ds.chunks, "get") else None
+            if ch:
+                unit = max(1, int(ch[0]))
+        except Exception:  # noqa: BLE001
+            pass
+        k = max(1, int(round(PART_BYTES / (unit * _bytes_per_step(ds)))))
+        per_dev = [shard_bounds(n_time, n_dev, r, align=unit) for r in range(n_dev)]
+        for lo, hi in per_dev:
+            for c in range(lo + unit * k, hi, unit * k):
+                cuts.append(c)
+            if hi > cuts[-1]:
+                cuts.append(hi)
+        owner_of = lambda lo: next(devices[r] for r, (a, b) in enumerate(per_dev) if a <= lo < b)  # noqa: E731
+    else:
+        per_dev = [shard_bounds(n_time, n_dev, r) for r in range(n_dev)]
+        cuts += [hi for lo, hi in per_dev if hi > lo]
+        owner_of = lambda lo: next(devices[r] for r, (a, b) in enumerate(per_dev) if a <= lo < b)  # noqa: E731
+    if day_offsets is not None:  # snap to day starts (first step of a day of the shifted axis)
+        offs = np.asarray(day_offsets)
+        snapped = sorted({int(offs[np.argmin(np.abs(offs - c))]) for c in cuts[1:-1]} | {0, n_time})
+        cuts = snapped
+    cuts = sorted(set(cuts))
+    return [(lo, hi, owner_of(min(lo, n_time - 1))) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
+def _run_partitioned(ds, spec_cls, convert_kwds, parts, run, workers_per_device):
+    """Convert every time part on its device (one host thread per device, two for lazily
+    loaded data so that reading part i+1 overlaps the GPU work on part i) and return the
+    per-part results in time order.  ``run(spec, device) -> result`` does the per-part work."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    torch = engine._torch()
+    devices = sorted({d for _, _, d in parts})
+    pools = {d: ThreadPoolExecutor(workers_per_device, thread_name_prefix=f"atl-dev{d}") for d in devices}
+    caught = warnings.catch_warnings(record=True)
+    log = caught.__enter__()  # the worker threads' warnings are re-issued once by the caller's thread
+    warnings.simplefilter("always")
+
+    def work(lo, hi, dev):
+        torch.cuda.set_device(dev)  # per-thread current device
+        spec = spec_cls(_time_slice(ds, lo, hi), **convert_kwds)
+        return run(spec, dev), spec
+
+    try:
+        futs = [pools[d].submit(work, lo, hi, d) for lo, hi, d in parts]
+        out = [f.result() for f in futs]
+    finally:
+        for p in pools.values():
+            p.shutdown(wait=True)
+        caught.__exit__(None, None, None)
+    seen = set()
+    for w in log:
+        key = (w.category, str(w.message))
+        if key not in seen:
+            seen.add(key)
+            warnings.warn_explicit(w.message, w.category, w.filename, w.lineno)
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -628,12 +782,31 @@ def convert_and_aggregate(
     ds = cutout.data
     ny, nx = _grid_shape(ds)
     spec_cls = _known_spec(convert_func)
-    if spec_cls is not None:
+    shard = getattr(cutout, "time_shard", None)  # multi-GPU time sharding (dist.py)
+    devices = list(getattr(cutout, "devices", None) or [])
+    lazy = _is_dask_backed(ds)
+    # several GPUs from this one process, and/or a lazily loaded (dask-backed) cutout that
+    # is converted time part by time part instead of being materialised whole
+    partitioned = spec_cls is not None and (len(devices) > 1 or lazy) and _is_host_resident(ds)
+    if partitioned and shard is not None:
+        raise ValueError("a cutout is either time-sharded across processes (time_shard=) or fanned "
+                         "out to several devices by one process (devices=), not both")
+    if len(devices) == 1 and not partitioned:
+        engine._torch().cuda.set_device(devices[0])
+    if partitioned:
+        spec, da = None, None
+    elif spec_cls is not None:
         spec, da = spec_cls(ds, **convert_kwds), None
     else:  # plugin protocol: the callable produces the (time, y, x) field itself
         spec, da = None, convert_func(ds, **convert_kwds)
 
-    shard = getattr(cutout, "time_shard", None)  # multi-GPU time sharding (dist.py)
+    if partitioned:
+        n_time = len(_coord(ds, "time"))
+        day_offsets = None
+        if spec_cls in (_HeatSpec, _CoolingSpec):
+            day_offsets = day_bins(_coord(ds, "time"), convert_kwds.get("hour_shift", 0.0))[1]
+        parts = _partition(ds, n_time, devices or [engine.current_device()], lazy, day_offsets)
+        wpd = 2 if lazy else 1
     no_args = all(v is None for v in [layout, shapes, matrix])
 
     if no_args:
@@ -643,6 +816,26 @@ def convert_and_aggregate(
                 "given for `per_unit` or `return_capacity`"
             )
         agg = "sum" if aggregate_time == "legacy" else aggregate_time
+        if partitioned:
+            coords_yx = {"y": _coord(ds, "y"), "x": _coord(ds, "x")}
+            if agg is None:
+                res = _run_partitioned(ds, spec_cls, convert_kwds, parts,
+                                       lambda sp_, dev: _to_host(sp_.cells()), wpd)
+                sp0 = res[0][1]
+                attrs = {"units": sp0.units} if sp0.units else {}
+                labels = pd.Index(np.concatenate([np.asarray(sp_.time_labels) for _, sp_ in res]))
+                vals = np.concatenate([v for v, _ in res], axis=0)
+                return make_dataarray(vals, ("time", "y", "x"), {"time": labels, **coords_yx}, attrs, sp0.name)
+            res = _run_partitioned(ds, spec_cls, convert_kwds, parts,
+                                   lambda sp_, dev: tuple(_to_host(a).astype(np.float64) for a in sp_.cells_timesum()), wpd)
+            sp0 = res[0][1]
+            attrs = {"units": sp0.units} if sp0.units else {}
+            total = sum(v[0] for v, _ in res)
+            count = sum(v[1] for v, _ in res)
+            if agg == "mean":
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    total = np.where(count > 0, total / count, np.nan)
+            return make_dataarray(total, ("y", "x"), coords_yx, attrs, sp0.name)
         if spec is None:
             if agg == "sum":
                 return da.sum("time", keep_attrs=True)
@@ -657,13 +850,16 @@ def convert_and_aggregate(
             if shard is not None:
                 vals, labels = shard.gather_time(vals, labels)
             return make_dataarray(vals, ("time", "y", "x"), {"time": labels, **coords_yx}, attrs, spec.name)
-        total = spec.cells(timesum=True)
-        n_t = len(spec.time_labels)
+        # NaN-skipping time sum and the number of valid steps per cell (da.sum / da.mean
+        # over "time" skip NaN, convert.py:51-56; an all-NaN cell has mean NaN, sum 0)
+        total, count = spec.cells_timesum()
         if shard is not None:
-            total, n_t = shard.sum_over_ranks(total, n_t)
+            total, count = shard.sum_planes(total, count)
         vals = _to_host(total).astype(np.float64)
         if agg == "mean":
-            vals = vals / n_t
+            cnt = _to_host(count).astype(np.float64)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                vals = np.where(cnt > 0, vals / cnt, np.nan)
         return make_dataarray(vals, ("y", "x"), coords_yx, attrs, spec.name)
 
     if matrix is not None:
@@ -699,13 +895,29 @@ def convert_and_aggregate(
     assert isinstance(matrix, sp.csr_matrix)
     dim, idx = _ensure_index(index, matrix.shape[0])
 
+    if partitioned:
+        digest = engine.matrix_digest(matrix)
+        res = _run_partitioned(
+            ds, spec_cls, convert_kwds, parts,
+            lambda sp_, dev: _to_host(sp_.reduce(engine.get_plan(matrix, ny, nx, device=dev, pitch=sp_.pitch,
+                                                                 digest=digest))), wpd)
+        time_labels = pd.Index(np.concatenate([np.asarray(sp_.time_labels) for _, sp_ in res]))
+        if isinstance(res[0][1].time_labels, pd.DatetimeIndex):
+            time_labels = pd.DatetimeIndex(time_labels)
+        name = res[0][1].name
+        res = np.concatenate([v for v, _ in res], axis=0)
     pitch = getattr(spec, "pitch", None)
-    if spec is None:  # plugin result computed from a row-padded device cutout keeps the padding
+    if partitioned:
+        pass
+    elif spec is None:  # plugin result computed from a row-padded device cutout keeps the padding
         vals0 = da if engine._is_torch(da) else getattr(da, "values", da)
         if engine._is_torch(vals0) and vals0.ndim == 3 and vals0.shape[-1] != nx:
             pitch = int(vals0.shape[-1])
-    plan = engine.get_plan(matrix, ny, nx, pitch=pitch)
-    if spec is not None:
+    if not partitioned:
+        plan = engine.get_plan(matrix, ny, nx, pitch=pitch)
+    if partitioned:
+        pass
+    elif spec is not None:
         res = spec.reduce(plan)  # (time, bus) float32
         time_labels, name = spec.time_labels, spec.name
     else:

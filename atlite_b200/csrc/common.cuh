@@ -64,11 +64,22 @@ inline GridDev make_grid(int ny, int nx, int pitch = 0) {
   return g;
 }
 
+// One stored matrix entry of a (tile, bus) slot, as the staged reduce consumes it:
+// `off` = BYTE offset of the cell inside one row of the warp's staging area (stage
+// index * 8, see stage_index below), `w` = the weight.
+struct __align__(8) PairEnt {
+  uint32_t off;
+  float w;
+};
+
 // Device view of an aggregation plan (see plan.cu).
 struct PlanDev {
   const int32_t* tile_slot_ptr;  // [n_tiles + 1]
   const int32_t* slot_row;       // [n_slots] bus index of each (tile, bus) slot
-  const float4* slot_w4;         // [n_slots * 32] weights: lane l -> its 4 cells (layout per `vec`)
+  const float4* slot_w4;         // [n_slots * 32] dense weights: lane l -> its 4 cells (layout per `vec`)
+  const int2* slot_rec;          // [n_slots] {first entry, entry count / PAIR_PAD} into `pairs`
+  const PairEnt* pairs;          // the STORED entries of every slot (CSR semantics: nothing else is
+                                 // touched), each slot padded to a multiple of PAIR_PAD
   const int32_t* active_tiles;   // [n_active]
   int32_t n_active;
   int32_t n_bus;
@@ -104,11 +115,21 @@ struct TileGeomT<true> {
   __host__ __device__ int cell_y(int) const { return y; }
 };
 
-// position of cell (iy, ix) inside its tile's 128-entry weight vector
+// position of cell (iy, ix) inside its tile's 128-entry weight vector: 4 * lane + i
+// (i = which of the lane's 4 cells), for either lane layout
 __host__ __device__ inline int tile_local_index(bool vec, int iy, int ix) {
   const int lx = ix % TILE_X, ly = iy % TILE_Y;
   return vec ? ((ly * 8 + lx / 4) * 4 + (lx & 3)) : (lx * 4 + ly);
 }
+// position of the same cell in a row of the warp's staging area (staged reduce): value i
+// of lane l sits at 32 * i + l, so the 32 lanes of a store hit 32 consecutive slots
+__host__ __device__ inline int stage_index(int local) { return 32 * (local & 3) + (local >> 2); }
+// The entry list of a slot is sorted by stage index and padded to a multiple of
+// PAIR_PAD entries with {PAD_OFF, 0}: PAD_OFF addresses the padding bytes behind the 128
+// cells of a staging row, which the kernel keeps at 0.0f, so a pad entry adds exactly 0
+// whatever the cells hold (0 * NaN would not).
+constexpr int PAIR_PAD = 8;
+constexpr uint32_t PAD_OFF = TILE_CELLS * 8;
 
 #ifdef __CUDACC__
 template <bool VEC>
@@ -148,6 +169,19 @@ __device__ __forceinline__ TileGeomT<true> make_geom<true>(int tile, int lane, c
   g.valid = v;
   g.boff = 4 * (int64_t)(min(g.y, gd.ny - 1) * gd.pitch + min(g.x0, gd.pitch - 4));
   return g;
+}
+
+// NaN-propagating min / max (FMNMX.NAN): xarray's / numpy's clip keeps NaN, CUDA's
+// fminf / fmaxf drop it
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
 }
 
 __device__ __forceinline__ float warp_sum(float p) {
@@ -405,6 +439,9 @@ struct AtlPlan {
   int32_t* d_tile_slot_ptr = nullptr;
   int32_t* d_slot_row = nullptr;
   float4* d_slot_w4 = nullptr;
+  int2* d_slot_rec = nullptr;
+  atl::PairEnt* d_pairs = nullptr;
+  int64_t n_pairs = 0;
   int32_t* d_active = nullptr;
   // deterministic mode: identity slot index + (bus -> slots) lists
   int32_t* d_slot_ident = nullptr;
@@ -419,6 +456,8 @@ struct AtlPlan {
     p.tile_slot_ptr = d_tile_slot_ptr;
     p.slot_row = d_slot_row;
     p.slot_w4 = d_slot_w4;
+    p.slot_rec = d_slot_rec;
+    p.pairs = d_pairs;
     p.active_tiles = d_active;
     p.n_active = n_active;
     p.n_bus = n_bus;

@@ -40,6 +40,8 @@ struct CspPhys {
   };
   static constexpr int kSmemFloats = 128 + 128 + 8192;
   static constexpr int kBatch = 1, kMinBlocks = 4;
+  static constexpr bool kHasExact = false;
+  static constexpr int kStage = 8;  // the 33 KB efficiency table leaves room for 8-step stages
 
   __device__ void stage(float* smem) const {
     const int n = n_alt + n_az + n_alt * n_az;
@@ -286,13 +288,13 @@ int atl_csp_cells(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t
 }
 
 int atl_csp_timesum(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t nt,
-                    float* out_dev, void* stream) {
+                    float* out_dev, float* count_dev, void* stream) {
   int rc = csp_check(op, f, t0, nt);
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, f, t0); };
-  return dispatch_cells(make, op->grid, csp_aligned(f), out_dev, nt, true, (cudaStream_t)stream);
+  return dispatch_cells(make, op->grid, csp_aligned(f), out_dev, nt, true, (cudaStream_t)stream, count_dev);
 }
 
 }  // extern "C"

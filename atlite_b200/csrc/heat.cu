@@ -75,11 +75,12 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<V
 }
 
 // MODE 0: fused reduce -> out (n_days, n_bus); 1: cells -> out (n_days, ny, nx);
-// MODE 2: per-cell sum over days accumulated into out (ny, nx)
+// MODE 2: per-cell sum over days accumulated into out (ny, nx), and the number of non-NaN
+// days into cnt_out (may be NULL)
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(CTA_THREADS)
     k_heat(const HeatParams hp, const GridDev gd, const PlanDev plan, float* __restrict__ out,
-           int n_days, int db) {
+           float* __restrict__ cnt_out, int n_days, int db) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ai = blockIdx.x * WARPS_PER_CTA + warp;
   int tile, s_beg = 0, s_end = 0;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
   }
   const TileGeomT<VEC> g = make_geom<VEC>(tile, lane, gd);
   const int d0 = blockIdx.y * db, d1 = min(n_days, d0 + db);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
   float v[4];
   for (int d = d0; d < d1; ++d) {
     heat_day(hp, g, d, v);
@@ -105,10 +106,17 @@ __global__ void __launch_bounds__(CTA_THREADS)
       store4(out + (int64_t)d * gd.S_out, gd, g, v);
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += (v[r] == v[r]) ? v[r] : 0.f;
+      for (int r = 0; r < 4; ++r) {
+        const bool ok = v[r] == v[r];
+        acc[r] += ok ? v[r] : 0.f;
+        cnt[r] += ok ? 1.f : 0.f;
+      }
     }
   }
-  if (MODE == 2) atomic_add4(out, gd, g, acc);
+  if (MODE == 2) {
+    atomic_add4(out, gd, g, acc);
+    if (cnt_out) atomic_add4(cnt_out, gd, g, cnt);
+  }
 }
 
 // Phys adaptor used only by the two-pass fallback (never on the fused path).
@@ -144,7 +152,7 @@ namespace atl {
 // for the whole time axis; see host_stream.cu).
 int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const float* temp,
                      const int32_t* d_days, int32_t base, const int64_t* day_start_host,
-                     int64_t n_days, float* out, cudaStream_t st) {
+                     int64_t n_days, float* out, cudaStream_t st, float* cnt_out) {
   ATL_REQUIRE(op && temp && out, "NULL argument");
   ATL_REQUIRE(n_days >= 0 && n_days < (1LL << 31), "bad day count");
   if (n_days == 0) return ATL_OK;
@@ -179,7 +187,7 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
       for (int64_t d = 0; d < n_days && rc == ATL_OK; d += blk) {
         const int64_t n = n_days - d < blk ? n_days - d : blk;
         rc = heat_launch_core(1, op, nullptr, temp + (day_start_host[d] - base) * op->grid.S, d_days + d,
-                              (int32_t)day_start_host[d], nullptr, n, scratch, st);
+                              (int32_t)day_start_host[d], nullptr, n, scratch, st, nullptr);
         if (rc == ATL_OK)
           rc = launch_csr_spmm(plan, scratch, n, out + (size_t)d * plan->n_bus, st);
       }
@@ -214,18 +222,18 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   }
   if (vec) {
     if (mode == 0)
-      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, (int)n_days, db);
+      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
     else if (mode == 1)
-      k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
+      k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, nullptr, (int)n_days, db);
     else
-      k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
+      k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, cnt_out, (int)n_days, db);
   } else {
     if (mode == 0)
-      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, (int)n_days, db);
+      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
     else if (mode == 1)
-      k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
+      k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, nullptr, (int)n_days, db);
     else
-      k_heat<2, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, (int)n_days, db);
+      k_heat<2, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, cnt_out, (int)n_days, db);
   }
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
@@ -244,14 +252,15 @@ int heat_upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out,
 }  // namespace atl
 
 static int heat_launch(int mode, const AtlHeatOp* op, const AtlPlan* plan, const float* temp,
-                       const int64_t* day_start, int64_t n_days, float* out, cudaStream_t st) {
+                       const int64_t* day_start, int64_t n_days, float* out, cudaStream_t st,
+                       float* cnt_out = nullptr) {
   ATL_REQUIRE(op && temp && day_start && out, "NULL argument");
   if (n_days <= 0) return ATL_OK;
   ATL_CUDA(cudaSetDevice(op->device));
   int32_t* d_days = nullptr;
   int rc = upload_days(day_start, n_days, &d_days, st);
   if (rc) return rc;
-  rc = heat_launch_core(mode, op, plan, temp, d_days, 0, day_start, n_days, out, st);
+  rc = heat_launch_core(mode, op, plan, temp, d_days, 0, day_start, n_days, out, st, cnt_out);
   cudaFreeAsync(d_days, st);
   return rc;
 }
@@ -299,9 +308,9 @@ int atl_heat_cells(const AtlHeatOp* op, const float* temperature_dev,
 }
 int atl_heat_timesum(const AtlHeatOp* op, const float* temperature_dev,
                      const int64_t* day_start_host, int64_t n_days, float* out_dev,
-                     void* stream) {
+                     float* count_dev, void* stream) {
   return heat_launch(2, op, nullptr, temperature_dev, day_start_host, n_days, out_dev,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, count_dev);
 }
 
 }  // extern "C"

@@ -255,7 +255,7 @@ using namespace atl;
 namespace atl {
 int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const float* temp,
                      const int32_t* d_days, int32_t base, const int64_t* day_start_host,
-                     int64_t n_days, float* out, cudaStream_t st);
+                     int64_t n_days, float* out, cudaStream_t st, float* cnt_out);
 int heat_upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out, cudaStream_t st);
 }
 
@@ -372,7 +372,7 @@ int atl_heat_reduce_host(const AtlHeatOp* op, const AtlPlan* plan, const float* 
   auto launch = [&](const std::vector<void*>& d, int64_t, int64_t n, float* out_dev,
                     cudaStream_t st) {
     int rc = heat_launch_core(0, op, plan, (const float*)d[0], d_days + cursor,
-                              (int32_t)day_start[cursor], day_start + cursor, n, out_dev, st);
+                              (int32_t)day_start[cursor], day_start + cursor, n, out_dev, st, nullptr);
     cursor += n;
     return rc;
   };

@@ -15,6 +15,11 @@
 //                           float (&v)[4], const float* smem) const;
 //        values of out-of-grid lanes are unspecified (finite border copies): they
 //        carry zero weight in every slot and are never stored
+//   static constexpr bool kHasExact;  if true, compute() may differ from the reference
+//        when an INPUT is NaN/Inf but then always yields a non-finite value, and
+//        compute_exact(...) (same signature) reproduces the reference's NaN rules; the
+//        kernels call it only for steps whose fast result came out non-finite
+//   static constexpr int kStage;  time steps a warp stages before one reduce phase
 // `t` is relative to the slab the functor's field pointers address.
 //
 // Loop structure: a warp owns one 32x4 tile and walks a block of `tb`
@@ -41,8 +46,8 @@ namespace atl {
 // must allow.
 template <class Phys, int B, int MINB, int G = 0>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
-    k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
-                   float* __restrict__ out, int nt, int tb) {
+    k_fused_reduce_v1(const Phys phys, const GridDev gd, const PlanDev plan,
+                      float* __restrict__ out, int nt, int tb) {
   extern __shared__ float smem[];
   phys.stage(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,6 +105,166 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   }
 }
 
+
+// ---------------------------------------------------------------- staged reduce
+// The round-2 kernel.  A warp still owns one 32x4 tile and walks `tb` consecutive
+// time steps, but it no longer reduces every step with warp shuffles against DENSE
+// 128-float weight vectors (4 FMAs + ~1.1 shuffles per slot and step whatever the
+// slot's fill: 70 of wind's 213 warp-instructions per step).  Instead the per-cell
+// values of TS steps are parked in shared memory, and the reduce runs with the lanes
+// spanning TIME: lane (q, r) owns the step pair r of the chunk and walks a q-th of the
+// slot's STORED matrix entries {cell, weight}; per entry it costs one broadcast 8-byte
+// load of the entry, one conflict-light 8-byte shared load of the cell's two steps and
+// two FMAs -- work proportional to the entries of the tile (~1.2 per cell for
+// NUTS-like shapes), independent of how many buses touch the tile, ~12 instructions
+// per step instead of ~70.  Entries a CSR matrix does not store are never multiplied,
+// so NaN/Inf cells poison exactly the buses that contain them (scipy semantics) with no
+// special path.
+//
+// Staging area of one warp: R = TS/2 rows (one per PAIR of consecutive steps); a row holds
+// the tile's 128 cells as float2 {even step, odd step} in stage_index order, then 8 * 16/R
+// bytes that stay 0.0f (the target of the plan's padding entries) and shift consecutive rows
+// by 16/R eight-byte bank pairs.  In the reduce phase the R lanes of a group read R
+// different rows at the same cell (bank pairs 16/R apart) and the 16/R groups that share a
+// shared-memory pass read CONSECUTIVE entries of the slot's list, which is sorted by stage
+// index -- neighbouring cells, i.e. the bank pairs in between: conflict-free for the usual
+// contiguous slot, never worse than 2-way.
+template <int TS>
+struct StageT {
+  static constexpr int kRows = TS / 2;
+  static constexpr int kShift = 16 / kRows > 0 ? 16 / kRows : 1;
+  static constexpr int kRowBytes = TILE_CELLS * 8 + 8 * kShift;
+  static constexpr int kWarpBytes = kRows * kRowBytes;
+  static constexpr int kCtaBytes = WARPS_PER_CTA * kWarpBytes;
+};
+__host__ __device__ constexpr int smem_table_bytes(int floats) { return (floats * 4 + 15) & ~15; }
+
+template <class Phys, int B, int MINB, int TS>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
+    k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
+                   float* __restrict__ out, int nt, int tb) {
+  static_assert(TS == 8 || TS == 16 || TS == 32, "TS/2 rows must divide the warp");
+  static_assert(B == 1 || B % 2 == 0, "steps are staged in pairs");
+  static_assert(TS % B == 0, "a chunk is a whole number of batches");
+  constexpr int R = TS / 2;    // rows = lanes along time in the reduce phase
+  constexpr int NQ = 32 / R;   // lanes sharing a row split the slot's entries NQ ways
+  using Stage = StageT<TS>;
+  extern __shared__ __align__(16) float smem[];
+  phys.stage(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ai = blockIdx.x * WARPS_PER_CTA + warp;
+  if (ai >= plan.n_active) return;
+  char* const stage = reinterpret_cast<char*>(smem) + smem_table_bytes(Phys::kSmemFloats) +
+                      warp * Stage::kWarpBytes;
+  const int tile = __ldg(plan.active_tiles + ai);
+  const auto g = make_geom<Phys::kVec>(tile, lane, gd);
+  const int s_beg = __ldg(plan.tile_slot_ptr + tile);
+  const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
+  const int t0 = blockIdx.y * tb;
+  const int t1 = min(nt, t0 + tb);
+  if (t0 >= t1) return;
+  const int tlast = t1 - 1;
+  const int nb = plan.n_bus;
+
+  typename Phys::Cell c;
+  phys.init(c, g, smem);
+  typename Phys::Raw r[B];
+  float v[B][4];
+  const int64_t S4 = gd.S * 4;
+  // Load indices are clamped to the block's last step instead of predicated: at most
+  // B - 1 redundant loads / evaluations per time block, their results never written.
+#pragma unroll
+  for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t0 + j, tlast) * S4, r[j]);
+
+  char* const st_lane = stage + lane * 8;  // staging: value i of this lane -> + 256 i
+  // reduce phase: lane = group * R + row; group q walks entries q, q + NQ, q + 2 NQ, ...
+  const int rp = lane & (R - 1), q = lane / R;
+  const char* const rd_row = stage + rp * Stage::kRowBytes;
+  constexpr int U = PAIR_PAD / NQ;  // entries per group and padding unit
+  static_assert(U >= 1 && U * NQ == PAIR_PAD, "PAIR_PAD must be a multiple of the group count");
+  if (lane < R) {  // the bytes behind the 128 cells of every row: 0.0f for the padding entries
+#pragma unroll
+    for (int k = 0; k < Stage::kShift; ++k)
+      *reinterpret_cast<float2*>(stage + lane * Stage::kRowBytes + PAD_OFF + 8 * k) = make_float2(0.f, 0.f);
+  }
+  const uint2* const pairs_q = reinterpret_cast<const uint2*>(plan.pairs) + q;
+
+#pragma unroll 1
+  for (int tc = t0; tc < t1; tc += TS) {
+    // ---- physics of up to TS steps -> staging area (registers only in between)
+#pragma unroll 1
+    for (int k = 0; k < TS; k += B) {
+      const int t = tc + k;
+      if (t >= t1) break;
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        phys.compute(c, g, min(t + j, tlast), r[j], v[j], smem);
+        zero_invalid(g, v[j]);
+      }
+      if constexpr (Phys::kHasExact) {
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < B; ++j) chk += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+        if (__any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f))) {  // cold: a NaN/Inf reached a result
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
+            phys.compute_exact(c, g, min(t + j, tlast), r[j], v[j], smem);
+            zero_invalid(g, v[j]);
+          }
+        }
+      }
+      // the loads of the NEXT batch (possibly the next chunk's first) go out now: they are in
+      // flight across the stores below and the whole reduce phase
+#pragma unroll
+      for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t + B + j, tlast) * S4, r[j]);
+      if (B == 1) {
+        char* const w = st_lane + (k >> 1) * Stage::kRowBytes + (k & 1) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(w + 256 * i) = v[0][i];
+      } else {
+#pragma unroll
+        for (int j = 0; j + 1 < B; j += 2) {
+          char* const w = st_lane + ((k + j) >> 1) * Stage::kRowBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float2*>(w + 256 * i) = make_float2(v[j][i], v[j + 1][i]);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- reduce: lanes along time, the slot's stored entries split NQ ways
+    const int nvalid = min(TS, t1 - tc);
+    float* const o0 = out + (size_t)(tc + 2 * rp) * nb;
+    const bool w0 = lane < R && 2 * rp < nvalid, w1 = lane < R && 2 * rp + 1 < nvalid;
+#pragma unroll 1
+    for (int s = s_beg; s < s_end; ++s) {
+      const int2 rec = __ldg(plan.slot_rec + s);
+      const uint2* p = pairs_q + rec.x;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+      for (int it = 0; it < rec.y; ++it, p += PAIR_PAD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint2 pw = __ldg(p + u * NQ);
+          const float2 x = *reinterpret_cast<const float2*>(rd_row + pw.x);
+          const float w = __uint_as_float(pw.y);
+          a0 = fmaf(w, x.x, a0);
+          a1 = fmaf(w, x.y, a1);
+        }
+      }
+#pragma unroll
+      for (int o = R; o < 32; o <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      }
+      const int row = __ldg(plan.slot_row + s);
+      if (w0) atomicAdd(o0 + row, a0);
+      if (w1) atomicAdd(o0 + nb + row, a1);
+    }
+    __syncwarp();  // the next chunk's stores must not overtake this chunk's reads
+  }
+}
+
 // MODE 0: store per-cell values out[(t - t_begin), y, x]
 // MODE 1: accumulate the (NaN-skipping) time sum into out[y, x]
 // Rolling software pipeline over B register sets: as soon as step t has been
@@ -107,10 +272,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 // of arithmetic (and the other warps) cover every load.  Load indices are clamped
 // to the block's last step instead of predicated (at most B - 1 redundant loads
 // and evaluations per time block, their results discarded).
+// MODE 1 also counts the valid (non-NaN) steps per cell into `cnt_out` (may be NULL): the
+// reference's per-cell mean skips NaN steps (convert.py:51-56).
 template <class Phys, int MODE, int B, int MINB>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
-    k_cells(const Phys phys, const GridDev gd, float* __restrict__ out, int t_begin,
-            int t_end, int tb) {
+    k_cells(const Phys phys, const GridDev gd, float* __restrict__ out,
+            float* __restrict__ cnt_out, int t_begin, int t_end, int tb) {
   extern __shared__ float smem[];
   phys.stage(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +292,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   phys.init(c, g, smem);
   typename Phys::Raw r[B];
   float v[4];
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
   const int64_t S4 = gd.S * 4;
   const int tl = t1 - 1;
 #pragma unroll
@@ -136,16 +303,27 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
     for (int j = 0; j < B; ++j) {
       const bool live = t + j < t1;
       phys.compute(c, g, min(t + j, tl), r[j], v, smem);
+      if constexpr (Phys::kHasExact) {  // cold, per lane: a NaN/Inf reached a result
+        if (!(fabsf((v[0] + v[1]) + (v[2] + v[3])) <= 3.0e38f))
+          phys.compute_exact(c, g, min(t + j, tl), r[j], v, smem);
+      }
       phys.load(c, g, (int64_t)min(t + j + B, tl) * S4, r[j]);
       if (MODE == 0) {
         if (live) store4(out + (int64_t)(t + j - t_begin) * gd.S_out, gd, g, v);
       } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += (live && v[q] == v[q]) ? v[q] : 0.f;
+        for (int q = 0; q < 4; ++q) {
+          const bool ok = live && v[q] == v[q];
+          acc[q] += ok ? v[q] : 0.f;
+          cnt[q] += ok ? 1.f : 0.f;
+        }
       }
     }
   }
-  if (MODE == 1) atomic_add4(out, gd, g, acc);
+  if (MODE == 1) {
+    atomic_add4(out, gd, g, acc);
+    if (cnt_out) atomic_add4(cnt_out, gd, g, cnt);
+  }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -189,7 +367,7 @@ inline int pick_tb(int n_cta_x, int64_t nt) {
 
 template <class Phys>
 int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begin,
-                 int64_t t_end, bool timesum, cudaStream_t st) {
+                 int64_t t_end, bool timesum, cudaStream_t st, float* cnt_out = nullptr) {
   if (t_end <= t_begin) return ATL_OK;
   const int n_tiles = gd.n_tx * gd.n_ty;
   const int gx = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -202,10 +380,10 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
   go.out_vec = (gd.nx % 4 == 0 && aligned16(out)) ? 1 : 0;
   if (timesum)
     k_cells<Phys, 1, Phys::kBatch, Phys::kMinBlocks>
-        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
+        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, cnt_out, (int)t_begin, (int)t_end, tb);
   else
     k_cells<Phys, 0, Phys::kBatch, Phys::kMinBlocks>
-        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, (int)t_begin, (int)t_end, tb);
+        <<<grid, CTA_THREADS, smem, st>>>(phys, go, out, nullptr, (int)t_begin, (int)t_end, tb);
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   return ATL_OK;
@@ -213,6 +391,24 @@ int launch_cells(const Phys& phys, const GridDev& gd, float* out, int64_t t_begi
 
 int launch_csr_spmm(const AtlPlan* plan, const float* dense, int64_t nt, float* out,
                     cudaStream_t st);
+
+template <class Phys, int TS>
+int launch_staged(const Phys& phys, const AtlPlan* plan, const GridDev& gd, const PlanDev& pd, float* acc,
+                  int64_t nt, int tb, int gx, cudaStream_t st) {
+  tb = ((tb + TS - 1) / TS) * TS;  // whole chunks per time block
+  dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
+  const size_t smem = smem_table_bytes(Phys::kSmemFloats) + StageT<TS>::kCtaBytes;
+  auto kern = k_fused_reduce<Phys, Phys::kBatch, Phys::kMinBlocks, TS>;
+  static bool attr_set[64] = {false};  // per instantiation and device (benign if set twice)
+  if (plan->device >= 0 && plan->device < 64 && !attr_set[plan->device]) {
+    ATL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ATL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    attr_set[plan->device] = true;
+  }
+  kern<<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb);
+  return ATL_OK;
+}
 
 // Fused path of one slab.  `Phys` must use the plan's lane layout.
 template <class Phys>
@@ -231,18 +427,20 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
     return ATL_OK;
   }
   const int gx = (plan->n_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  const int tb = tuning().tb > 0 ? tuning().tb : pick_tb(gx, nt);
-  dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
-  const size_t smem = Phys::kSmemFloats * sizeof(float);
+  int tb = tuning().tb > 0 ? tuning().tb : pick_tb(gx, nt);
   const GridDev gd = plan->grid;
-#define ATL_LAUNCH_FUSED(B, MINB, ...) \
-  k_fused_reduce<Phys, B, MINB, ##__VA_ARGS__><<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb)
-  switch (tuning().variant) {  // A/B experiments (ATL_VARIANT); 0 = the functor's own choice
-    case 1: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 0); break;  // pairwise reduce
-    case 2: ATL_LAUNCH_FUSED(4, 6, 1); break;                            // deeper batch
-    default: ATL_LAUNCH_FUSED(Phys::kBatch, Phys::kMinBlocks, 1); break;
+  const int variant = tuning().variant;
+  if (variant == 1) {  // round-1 kernel (shuffle reduce against dense weight vectors), kept for A/B
+    dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
+    k_fused_reduce_v1<Phys, Phys::kBatch, Phys::kMinBlocks, 1>
+        <<<grid, CTA_THREADS, Phys::kSmemFloats * sizeof(float), st>>>(phys, gd, pd, acc, (int)nt, tb);
+  } else if (variant == 2) {  // the other chunk length (A/B)
+    int rc = launch_staged<Phys, (Phys::kStage == 16 ? 8 : 16)>(phys, plan, gd, pd, acc, nt, tb, gx, st);
+    if (rc) return rc;
+  } else {
+    int rc = launch_staged<Phys, Phys::kStage>(phys, plan, gd, pd, acc, nt, tb, gx, st);
+    if (rc) return rc;
   }
-#undef ATL_LAUNCH_FUSED
   ++g_launches;
   ATL_CUDA(cudaGetLastError());
   if (det) {
@@ -299,10 +497,10 @@ int dispatch_reduce(Make make, const AtlPlan* plan, bool ptrs_aligned, float* ou
 
 template <class Make>
 int dispatch_cells(Make make, const GridDev& gd, bool ptrs_aligned, float* out, int64_t nt,
-                   bool timesum, cudaStream_t st) {
+                   bool timesum, cudaStream_t st, float* cnt_out = nullptr) {
   if (gd.pitch % 4 == 0 && ptrs_aligned)
-    return launch_cells(make(std::true_type{}), gd, out, 0, nt, timesum, st);
-  return launch_cells(make(std::false_type{}), gd, out, 0, nt, timesum, st);
+    return launch_cells(make(std::true_type{}), gd, out, 0, nt, timesum, st, cnt_out);
+  return launch_cells(make(std::false_type{}), gd, out, 0, nt, timesum, st, cnt_out);
 }
 
 }  // namespace atl

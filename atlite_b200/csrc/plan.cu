@@ -118,7 +118,9 @@ struct IdentityPhys {
     float v[4];
   };
   static constexpr int kSmemFloats = 0;
-  static constexpr int kBatch = 4, kMinBlocks = 8;
+  static constexpr int kBatch = 4, kMinBlocks = 6;
+  static constexpr bool kHasExact = false;
+  static constexpr int kStage = 16;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const { load4(f, tb, g, r.v); }
@@ -164,6 +166,13 @@ struct Tiling {
   int32_t n_tiles = 0, n_active = 0;
   std::vector<int32_t> tile_slot_ptr, slot_row, active;
   std::vector<float> w;  // n_slots * 128 weights in lane order (only if fused)
+  // the stored entries of every slot for the staged reduce: {stage byte offset, weight},
+  // sorted by stage index, duplicates of one (bus, cell) summed (csr_matrix semantics),
+  // explicit zeros kept; slot s owns pairs[slot_pair_ptr[s] .. slot_pair_ptr[s+1]), the first
+  // slot_pair_n[s] of which are real, the rest padding {PAD_OFF, 0} up to a multiple of PAIR_PAD
+  std::vector<int32_t> slot_pair_ptr, slot_pair_n;
+  std::vector<PairEnt> pairs;
+  int64_t n_pairs = 0;  // real entries
 };
 
 static int build_tiling(int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus, const int64_t* indptr,
@@ -201,7 +210,9 @@ static int build_tiling(int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus, co
       ents.push_back(e);
     }
   }
-  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.key < b.key; });
+  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
+    return a.key != b.key ? a.key < b.key : stage_index(a.local) < stage_index(b.local);
+  });
 
   int64_t n_slots = 0, n_active = 0;
   {
@@ -236,10 +247,29 @@ static int build_tiling(int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus, co
   T.w.assign((size_t)n_slots * TILE_CELLS, 0.f);
   T.active.clear();
   T.active.reserve((size_t)n_active);
+  T.slot_pair_ptr.assign((size_t)n_slots + 1, 0);
+  T.slot_pair_n.assign((size_t)n_slots, 0);
+  T.pairs.clear();
+  T.pairs.reserve(ents.size() + (size_t)n_slots * (PAIR_PAD / 2));
+  T.n_pairs = 0;
+  auto close_slot = [&](int64_t slot) {  // pad the finished slot's list
+    if (slot < 0) return;
+    T.slot_pair_n[(size_t)slot] = (int32_t)(T.pairs.size() - (size_t)T.slot_pair_ptr[(size_t)slot]);
+    while ((T.pairs.size() - (size_t)T.slot_pair_ptr[(size_t)slot]) % PAIR_PAD) {
+      PairEnt pad;
+      pad.off = PAD_OFF;
+      pad.w = 0.f;
+      T.pairs.push_back(pad);
+    }
+    T.slot_pair_ptr[(size_t)slot + 1] = (int32_t)T.pairs.size();
+  };
   int64_t s = -1, prev = -1, prev_tile = -1;
+  int32_t prev_local = -1;
   for (const Ent& e : ents) {
     if (e.key != prev) {
+      close_slot(s);
       prev = e.key;
+      prev_local = -1;
       ++s;
       const int64_t tile = e.key / n_bus;
       T.slot_row[(size_t)s] = (int32_t)(e.key - tile * n_bus);
@@ -250,7 +280,19 @@ static int build_tiling(int32_t ny, int32_t nx, int32_t pitch, int32_t n_bus, co
       }
     }
     T.w[(size_t)s * TILE_CELLS + e.local] += e.w;  // duplicates sum (csr_matrix semantics)
+    if (e.local == prev_local) {
+      T.pairs.back().w += e.w;
+    } else {
+      PairEnt pe;
+      pe.off = (uint32_t)stage_index(e.local) * 8u;
+      pe.w = e.w;
+      T.pairs.push_back(pe);
+      prev_local = e.local;
+      ++T.n_pairs;
+    }
   }
+  close_slot(s);
+  ATL_REQUIRE(T.pairs.size() < (1ull << 31), "too many matrix entries for one plan");
   for (int64_t t = 0; t < n_tiles; ++t) T.tile_slot_ptr[(size_t)t + 1] += T.tile_slot_ptr[(size_t)t];
   return ATL_OK;
 }
@@ -279,12 +321,42 @@ int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* i
   info->fused = T.fused ? 1 : 0;
   info->pitch = nx;
   info->vec = T.vec ? 1 : 0;
+  info->n_pairs = T.n_pairs;
   if (!want) return ATL_OK;
   ATL_REQUIRE(tile_slot_ptr_out && slot_row_out && slot_w_out, "all three output arrays are needed");
   ATL_REQUIRE(slot_capacity >= T.n_slots, "slot_capacity too small");
   std::memcpy(tile_slot_ptr_out, T.tile_slot_ptr.data(), T.tile_slot_ptr.size() * 4);
   std::memcpy(slot_row_out, T.slot_row.data(), T.slot_row.size() * 4);
   std::memcpy(slot_w_out, T.w.data(), T.w.size() * 4);
+  return ATL_OK;
+}
+
+int atl_plan_pairs_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr,
+                        const int32_t* indices, const double* data, int64_t* n_pairs_out,
+                        int32_t* slot_pair_ptr_out, int32_t* pair_cell_out, float* pair_w_out,
+                        int64_t slot_capacity, int64_t pair_capacity) {
+  ATL_REQUIRE(n_pairs_out, "n_pairs_out is NULL");
+  Tiling T;
+  int rc = build_tiling(ny, nx, 0, n_bus, indptr, indices, data, true, T);
+  if (rc) return rc;
+  *n_pairs_out = T.n_pairs;
+  if (!slot_pair_ptr_out && !pair_cell_out && !pair_w_out) return ATL_OK;
+  ATL_REQUIRE(slot_pair_ptr_out && pair_cell_out && pair_w_out, "all three output arrays are needed");
+  ATL_REQUIRE(slot_capacity >= T.n_slots && pair_capacity >= T.n_pairs, "output capacity too small");
+  // compact (unpadded) view: the padding entries {PAD_OFF, 0} are skipped
+  int64_t o = 0;
+  for (int64_t k = 0; k < T.n_slots; ++k) {
+    slot_pair_ptr_out[k] = (int32_t)o;
+    const int32_t b = T.slot_pair_ptr[(size_t)k];
+    ATL_REQUIRE((T.slot_pair_ptr[(size_t)k + 1] - b) % PAIR_PAD == 0, "internal: unpadded slot");
+    for (int32_t i = 0; i < T.slot_pair_n[(size_t)k]; ++i, ++o) {
+      pair_cell_out[o] = (int32_t)(T.pairs[(size_t)b + i].off / 8u);
+      pair_w_out[o] = T.pairs[(size_t)b + i].w;
+    }
+    for (int32_t i = b + T.slot_pair_n[(size_t)k]; i < T.slot_pair_ptr[(size_t)k + 1]; ++i)
+      ATL_REQUIRE(T.pairs[(size_t)i].off == PAD_OFF && T.pairs[(size_t)i].w == 0.f, "internal: bad padding");
+  }
+  slot_pair_ptr_out[T.n_slots] = (int32_t)o;
   return ATL_OK;
 }
 
@@ -340,6 +412,18 @@ int atl_plan_create_pitched(int device, int32_t ny, int32_t nx, int32_t pitch, i
     PLAN_CUDA(cudaMalloc((void**)&p->d_slot_w4, (T.w.size() + 3 * 128) * 4));
     PLAN_CUDA(cudaMemset(p->d_slot_w4, 0, (T.w.size() + 3 * 128) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_slot_w4, T.w.data(), T.w.size() * 4, cudaMemcpyHostToDevice));
+    p->n_pairs = T.n_pairs;
+    {
+      std::vector<int2> rec((size_t)T.n_slots);
+      for (int64_t k = 0; k < T.n_slots; ++k)
+        rec[(size_t)k] = make_int2(T.slot_pair_ptr[(size_t)k],
+                                   (T.slot_pair_ptr[(size_t)k + 1] - T.slot_pair_ptr[(size_t)k]) / PAIR_PAD);
+      PLAN_CUDA(cudaMalloc((void**)&p->d_slot_rec, std::max<size_t>(rec.size(), 1) * sizeof(int2)));
+      PLAN_CUDA(cudaMemcpy(p->d_slot_rec, rec.data(), rec.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    PLAN_CUDA(cudaMalloc((void**)&p->d_pairs, std::max<size_t>(T.pairs.size(), 1) * sizeof(PairEnt)));
+    PLAN_CUDA(cudaMemcpy(p->d_pairs, T.pairs.data(), T.pairs.size() * sizeof(PairEnt),
+                         cudaMemcpyHostToDevice));
     PLAN_CUDA(cudaMalloc((void**)&p->d_active, std::max<size_t>(T.active.size(), 1) * 4));
     PLAN_CUDA(cudaMemcpy(p->d_active, T.active.data(), T.active.size() * 4,
                          cudaMemcpyHostToDevice));
@@ -392,6 +476,7 @@ int atl_plan_info(const AtlPlan* plan, AtlPlanInfo* info) {
   info->fused = plan->fused ? 1 : 0;
   info->pitch = plan->grid.pitch;
   info->vec = plan->vec ? 1 : 0;
+  info->n_pairs = plan->n_pairs;
   return ATL_OK;
 }
 
@@ -401,6 +486,8 @@ void atl_plan_destroy(AtlPlan* p) {
   cudaFree(p->d_tile_slot_ptr);
   cudaFree(p->d_slot_row);
   cudaFree(p->d_slot_w4);
+  cudaFree(p->d_slot_rec);
+  cudaFree(p->d_pairs);
   cudaFree(p->d_active);
   cudaFree(p->d_slot_ident);
   cudaFree(p->d_row_slot_ptr);

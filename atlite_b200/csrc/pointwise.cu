@@ -26,7 +26,9 @@ struct PointwisePhys {
     float v[4];
   };
   static constexpr int kSmemFloats = 0;
-  static constexpr int kBatch = 4, kMinBlocks = 8;
+  static constexpr int kBatch = 4, kMinBlocks = 6;
+  static constexpr bool kHasExact = false;
+  static constexpr int kStage = 16;
   __device__ void stage(float*) const {}
   __device__ void init(Cell& c, const Geom& g, const float*) const {
 #pragma unroll
@@ -150,12 +152,12 @@ int atl_pointwise_cells(const AtlPointwiseOp* op, const float* field_dev, int64_
 }
 
 int atl_pointwise_timesum(const AtlPointwiseOp* op, const float* field_dev, int64_t nt,
-                          float* out_dev, void* stream) {
+                          float* out_dev, float* count_dev, void* stream) {
   ATL_REQUIRE(op && field_dev && out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   auto make = [&](auto vec) { return make_phys<decltype(vec)::value>(op, field_dev); };
   return dispatch_cells(make, op->grid, aligned16(field_dev), out_dev, nt, true,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, count_dev);
 }
 
 }  // extern "C"

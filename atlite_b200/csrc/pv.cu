@@ -52,6 +52,8 @@ struct PvPhys {
   const float4* tt;  // per time step (absolute index t_off + t)
   const float2* xt;  // per column
   const float* yt;   // per row, 8 floats
+  const float4* ot;  // per CELL orientation {cos b, sin b, cos phi, sin phi}, {sin^3(b/2), ..}: only when
+                     // the orientation callback returned (y, x) arrays (pv/orientation.py:107), else NULL
   int64_t S;
   int nx, ny;
   int t_off;
@@ -80,6 +82,11 @@ struct PvPhys {
   };
   static constexpr int kSmemFloats = 0;
   static constexpr int kBatch = FAST ? 2 : 1, kMinBlocks = FAST ? 5 : 4;
+  // compute() is the reference's arithmetic for finite inputs; a NaN input always surfaces as a
+  // non-finite result, for which compute_exact() applies the reference's NaN rules
+  // (pv/irradiation.py:198-200 NaN-preserving clip, :226 per-term fillna(0))
+  static constexpr bool kHasExact = true;
+  static constexpr int kStage = 16;
   __device__ void stage(float*) const {}
 
   __device__ void init(Cell& c, const Geom& g, const float*) const {
@@ -144,8 +151,18 @@ struct PvPhys {
     }
   }
 
-  __device__ void compute(const Cell& c, const Geom&, int t, const Raw& r, float (&v)[4],
-                          const float*) const {
+  __device__ __forceinline__ void compute(const Cell& c, const Geom& g, int t, const Raw& r, float (&v)[4],
+                                          const float* sm) const {
+    compute_impl<false>(c, g, t, r, v, sm);
+  }
+  __device__ __forceinline__ void compute_exact(const Cell& c, const Geom& g, int t, const Raw& r,
+                                             float (&v)[4], const float* sm) const {
+    compute_impl<true>(c, g, t, r, v, sm);
+  }
+
+  template <bool EXACT>
+  __device__ __forceinline__ void compute_impl(const Cell& c, const Geom& g, int t, const Raw& r,
+                                               float (&v)[4], const float*) const {
     float sd = 0.f, cd = 0.f, ch[NXC], sh[NXC];
     if (solar_src() == ATL_SOLAR_COMPUTED) {
       const float4 q = __ldg(tt + t_off + t);
@@ -160,6 +177,19 @@ struct PvPhys {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int a = ix(i), b = iy(i);
+      // ---- panel orientation: per row (tables in Cell) or per cell (orientation callback
+      // returning (y, x) arrays)
+      float cs = c.cs[b], ss = c.ss[b], cph = c.cph[b], sph = c.sph[b], hd3c = c.hd3[b];
+      float ou = c.u[b], ov = c.v[b], e1 = c.e1[b], e2 = c.e2[b];
+      if (!FAST && ot != nullptr) {
+        const int cell = min(g.cell_y(i), ny - 1) * nx + min(g.cell_x(i), nx - 1);
+        const float4 p0 = __ldg(ot + 2 * cell), p1 = __ldg(ot + 2 * cell + 1);
+        cs = p0.x; ss = p0.y; cph = p0.z; sph = p0.w; hd3c = p1.x;
+        ou = ss * cph;
+        ov = ss * sph;
+        e1 = fmaf(ou, c.cl[b], cs * c.sl[b]);
+        e2 = fmaf(cs, c.cl[b], -ou * c.sl[b]);
+      }
       // ---- solar position (pv/solar_position.py:103-114)
       float sinalt, cosalt, X, Y;
       if (solar_src() == ATL_SOLAR_COMPUTED) {
@@ -182,20 +212,20 @@ struct PvPhys {
         if (solar_src() == ATL_SOLAR_COMPUTED) {
           // u X + v Y + cs sinalt is linear in (cos h, sin h):
           //   sd (u cl + cs sl) + cd (cs cl - u sl) cos h - v cd sin h
-          cosinc = fmaf(-(c.v[b] * cd), sh[a], fmaf(cd * c.e2[b], ch[a], sd * c.e1[b]));
+          cosinc = fmaf(-(ov * cd), sh[a], fmaf(cd * e2, ch[a], sd * e1));
         } else {
-          cosinc = fmaf(c.u[b], X, fmaf(c.v[b], Y, c.cs[b] * sinalt));
+          cosinc = fmaf(ou, X, fmaf(ov, Y, cs * sinalt));
         }
-        cslope = c.cs[b];
+        cslope = cs;
       } else if (trk == ATL_TRACK_VERTICAL) {
-        cosinc = fmaf(c.ss[b], cosalt, c.cs[b] * sinalt);
-        cslope = c.cs[b];
+        cosinc = fmaf(ss, cosalt, cs * sinalt);
+        cslope = cs;
       } else if (trk == ATL_TRACK_DUAL) {
         cosinc = 1.f;
-        cslope = (trigon() == ATL_TRIGON_SIMPLE) ? sinalt : c.cs[b];  // irradiation.py:216-219
+        cslope = (trigon() == ATL_TRIGON_SIMPLE) ? sinalt : cs;  // irradiation.py:216-219
       } else {
         // q = cos a sin(az - phi), p = cos a cos(az - phi)
-        const float q = fmaf(Y, c.cph[b], -X * c.sph[b]);
+        const float q = fmaf(Y, cph, -X * sph);
         if (trk == ATL_TRACK_HORIZONTAL) {
           // rotation = atan(q / sinalt); slope = |rotation|; the panel azimuth is
           // phi + sign(rotation) pi/2, so cosinc = sign(sinalt) sqrt(sinalt^2 + q^2)
@@ -203,11 +233,11 @@ struct PvPhys {
           cosinc = sinalt > 0.f ? D : 0.f;
           cslope = __fdividef(fabsf(sinalt), D);
         } else {  // tilted_horizontal: rotation = atan2(q, den) after the +-pi fix-ups
-          const float p = fmaf(X, c.cph[b], Y * c.sph[b]);
-          const float den = fmaf(p, c.ss[b], sinalt * c.cs[b]);
+          const float p = fmaf(X, cph, Y * sph);
+          const float den = fmaf(p, ss, sinalt * cs);
           const float E = sqrtf(fmaf(q, q, den * den));
           cosinc = E;  // cos(rot) den + sin(rot) q
-          cslope = __fdividef(fabsf(den) * c.cs[b], E);
+          cslope = __fdividef(fabsf(den) * cs, E);
         }
       }
       cosinc = fmaxf(cosinc, 0.f);  // :188
@@ -216,10 +246,11 @@ struct PvPhys {
       const float toa_ = r.toa[i];
       float direct, diffuse;
       if (irr_branch() == ATL_IRR_DIRECT_DIFFUSE) {
-        direct = fminf(fmaxf(r.a[i], 0.f), toa_);
-        diffuse = fminf(fmaxf(r.b[i], 0.f), toa_ - direct);
+        // influx.clip(min=0, max=influx_toa): xarray's clip keeps NaN (in the value or the bound)
+        direct = fmin_nan(fmax_nan(r.a[i], 0.f), toa_);
+        diffuse = fmin_nan(fmax_nan(r.b[i], 0.f), toa_ - direct);
       } else {
-        const float inf_ = fminf(fmaxf(r.a[i], 0.f), toa_);
+        const float inf_ = fmin_nan(fmax_nan(r.a[i], 0.f), toa_);
         const float k = inf_ / toa_;  // 0/0 -> NaN -> fraction 0
         float fr = 0.f;
         if (clearsky == ATL_CLEARSKY_SIMPLE) {
@@ -259,7 +290,7 @@ struct PvPhys {
       if (trigon() == ATL_TRIGON_SIMPLE) {
         diffuse_t = fmaf(0.5f, cslope, 0.5f) * diffuse;
       } else {
-        float hd3 = c.hd3[b];
+        float hd3 = hd3c;
         if (trk == ATL_TRACK_HORIZONTAL || trk == ATL_TRACK_TILTED_HORIZONTAL) {
           const float s2 = sqrtf(fmaxf(fmaf(-0.5f, cslope, 0.5f), 0.f));  // sin(slope/2)
           hd3 = s2 * s2 * s2;
@@ -274,9 +305,14 @@ struct PvPhys {
       if (out == ATL_OUT_DIRECT) total = direct_t;  // pv/irradiation.py:238-245
       else if (out == ATL_OUT_DIFFUSE) total = diffuse_t;
       else if (out == ATL_OUT_GROUND) total = ground_t;
-      else if (trigon() == ATL_TRIGON_SIMPLE)  // one FMA chain on the hot path
-        total = fmaf(Rb, direct, fmaf(fmaf(0.5f, cslope, 0.5f), diffuse, ground_t));
-      else
+      else if (trigon() == ATL_TRIGON_SIMPLE) {
+        if (EXACT) {  // direct_t.fillna(0) + diffuse_t.fillna(0) + ground_t.fillna(0)   (:226)
+          total = ((direct_t == direct_t) ? direct_t : 0.f) + ((diffuse_t == diffuse_t) ? diffuse_t : 0.f) +
+                  ((ground_t == ground_t) ? ground_t : 0.f);
+        } else {  // one FMA chain on the hot path; NaN in any term -> NaN -> compute_exact
+          total = fmaf(Rb, direct, fmaf(fmaf(0.5f, cslope, 0.5f), diffuse, ground_t));
+        }
+      } else
         total = fmaf(Rb, direct, diffuse_t) + ground_t;
       // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
       // stored mode compares the stored altitude itself, as the reference does
@@ -316,6 +352,7 @@ struct AtlPvOp {
   float4* d_tt = nullptr;
   float2* d_xt = nullptr;
   float* d_yt = nullptr;
+  float4* d_ot = nullptr;  // per-cell orientation table (orientation_2d)
   bool fast;
 };
 
@@ -335,6 +372,7 @@ static PvPhys<FAST, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int6
   p.tt = op->d_tt;
   p.xt = op->d_xt;
   p.yt = op->d_yt;
+  p.ot = op->d_ot;
   p.S = op->grid.S;
   p.nx = op->grid.nx;
   p.ny = op->grid.ny;
@@ -428,7 +466,7 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
              cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR &&
              cfg->trigon_model == ATL_TRIGON_SIMPLE && cfg->panel_model == ATL_PANEL_HULD &&
-             cfg->output == ATL_OUT_PANEL;
+             cfg->output == ATL_OUT_PANEL && !cfg->orientation_2d;
   const double* P = cfg->panel;
   for (int i = 0; i < 12; ++i) op->pc[i] = 0.f;
   if (cfg->panel_model == ATL_PANEL_HULD) {
@@ -463,9 +501,22 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
     const double lon = cfg->lon_deg[i] * D2R;
     xt[(size_t)i] = make_float2((float)std::cos(lon), (float)std::sin(lon));
   }
+  // orientation_2d: slope_rad / azimuth_rad hold ny * nx entries; the per-row table then only
+  // serves the latitude terms (its orientation part is taken from the first column)
+  const int ostride = cfg->orientation_2d ? cfg->nx : 1;
+  std::vector<float4> ot;
+  if (cfg->orientation_2d) {
+    ot.resize((size_t)cfg->ny * cfg->nx * 2);
+    for (size_t k = 0; k < (size_t)cfg->ny * cfg->nx; ++k) {
+      const double sl = cfg->slope_rad[k], az = cfg->azimuth_rad[k];
+      ot[2 * k] = make_float4((float)std::cos(sl), (float)std::sin(sl), (float)std::cos(az), (float)std::sin(az));
+      ot[2 * k + 1] = make_float4((float)std::pow(std::sin(sl / 2.0), 3), 0.f, 0.f, 0.f);
+    }
+  }
   std::vector<float> yt((size_t)cfg->ny * 8);
   for (int j = 0; j < cfg->ny; ++j) {
-    const double lat = cfg->lat_deg[j] * D2R, sl = cfg->slope_rad[j], az = cfg->azimuth_rad[j];
+    const double lat = cfg->lat_deg[j] * D2R, sl = cfg->slope_rad[(size_t)j * ostride],
+                 az = cfg->azimuth_rad[(size_t)j * ostride];
     float* o = &yt[(size_t)j * 8];
     o[0] = (float)std::sin(lat);
     o[1] = (float)std::cos(lat);
@@ -486,6 +537,9 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_yt, yt.size() * sizeof(float));
   if (e == cudaSuccess)
     e = cudaMemcpy(op->d_yt, yt.data(), yt.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !ot.empty()) e = cudaMalloc((void**)&op->d_ot, ot.size() * sizeof(float4));
+  if (e == cudaSuccess && !ot.empty())
+    e = cudaMemcpy(op->d_ot, ot.data(), ot.size() * sizeof(float4), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     atl_pv_destroy(op);
     return cuda_fail(e, "atl_pv_create");
@@ -500,6 +554,7 @@ void atl_pv_destroy(AtlPvOp* op) {
   cudaFree(op->d_tt);
   cudaFree(op->d_xt);
   cudaFree(op->d_yt);
+  cudaFree(op->d_ot);
   delete op;
 }
 
@@ -547,7 +602,7 @@ int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt
 }
 
 int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
-                   float* out_dev, void* stream) {
+                   float* out_dev, float* count_dev, void* stream) {
   int rc = check(op, f, t0, nt);
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
@@ -555,10 +610,10 @@ int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t 
   const bool al = fields_aligned(f);
   if (op->fast) {
     auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
-    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);
+    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);
   }
   auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
-  return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);
+  return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);
 }
 
 }  // extern "C"

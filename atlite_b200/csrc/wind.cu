@@ -35,16 +35,6 @@ namespace atl {
 //              clamp f[0]; 1 <= c < n -> segment [V[c-1], V[c]) with x0 = V[c-1]
 //              (nearest float), slope = 0 on zero-width (duplicate-knot)
 //              segments; c >= n -> right clamp f[n-1]      (np.interp semantics)
-__device__ __forceinline__ float fmin_nan(float a, float b) {
-  float d;
-  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
-__device__ __forceinline__ float fmax_nan(float a, float b) {
-  float d;
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
 
 // One LUT lookup; the SAME function evaluates on the host for the CPU tests
 // (atl_wind_curve_eval_host), with the PTX clamp / floor spelled out.
@@ -122,6 +112,8 @@ struct WindPhys {                // duplicates of the loads, no uniform branches
   // <= 130 x 16 or <= 258 x 4 replicas, 2 floats each; fallback: 256 + 4*257
   static constexpr int kSmemFloats = 2 * 130 * 16;
   static constexpr int kBatch = 2, kMinBlocks = 6;
+  static constexpr bool kHasExact = false;  // NaN speeds / roughness propagate like np.interp's
+  static constexpr int kStage = 8;          // 16.5 KB of staging + the 16.6 KB table: 6 CTAs per SM
 
   __device__ void stage(float* smem) const {
     for (int i = threadIdx.x; i < n_stage; i += blockDim.x) smem[i] = curve[i];
@@ -643,7 +635,7 @@ int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, floa
 }
 
 int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, float* out_dev,
-                     void* stream) {
+                     float* count_dev, void* stream) {
   int rc = check_fields(op, f);
   if (rc) return rc;
   ATL_REQUIRE(out_dev, "NULL argument");
@@ -652,7 +644,7 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, fl
 #define ATL_WIND_CASE(M)                                                                  \
   case M: {                                                                               \
     auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
-    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream);  \
+    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);  \
   }
   switch (op->method) {
     ATL_WIND_CASE(ATL_WIND_NONE)

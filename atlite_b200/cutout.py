@@ -23,7 +23,15 @@ if HAVE_XARRAY:  # pragma: no cover
 
 
 class Cutout:
-    def __init__(self, path=None, data=None, time_shard=None, **kwargs):
+    """``devices``: which GPUs of this process convert the cutout.  ``None`` = the current
+    CUDA device; ``"all"`` or a list of device indices = the time axis of a HOST-resident
+    cutout (NumPy / pinned / lazily loaded xarray data) is cut into one contiguous shard per
+    device, every device streams and converts its shard from its own host thread, and the
+    shard results land in one host array -- the reference's single call in a single process
+    (convert.py:59-75), no ``torchrun`` needed.  (``time_shard=`` is the other multi-GPU mode:
+    one PROCESS per GPU under ``torchrun``, results gathered over NCCL, see dist.py.)"""
+
+    def __init__(self, path=None, data=None, time_shard=None, devices=None, **kwargs):
         if data is None:
             if path is None:
                 raise ValueError("Cutout needs `data=` (or a NetCDF `path` when xarray is installed)")
@@ -49,9 +57,27 @@ class Cutout:
                 data.coords["lat"] = data.coords["y"]
         self.path = path
         self.data = data
+        self._devices = devices
         # set by atlite_b200.dist.TimeShard: this process holds one contiguous
         # time shard of the cutout and results are gathered across ranks
         self.time_shard = time_shard
+
+    @property
+    def devices(self):
+        """Resolved list of CUDA device indices, or None (= the current device)."""
+        d = self._devices
+        if d is None:
+            return None
+        if isinstance(d, str):
+            if d != "all":
+                raise ValueError(f"devices must be None, 'all' or a list of device indices, not {d!r}")
+            import torch
+
+            d = list(range(torch.cuda.device_count()))
+        d = [int(k) for k in (d if hasattr(d, "__iter__") else [d])]
+        if not d:
+            raise RuntimeError("no CUDA device visible (atlite_b200 has no CPU fallback)")
+        return d
 
     # ---- geometry (cutout.py:300-376)
     @property
@@ -133,7 +159,7 @@ class Cutout:
             t.numpy()[...] = a
             keep.append(t)
             out[n] = (("time", "y", "x")[-a.ndim:], t.numpy())
-        res = Cutout(data=out, time_shard=self.time_shard)
+        res = Cutout(data=out, time_shard=self.time_shard, devices=self._devices)
         res._pinned = keep  # the tensors own the page-locked memory
         return res
 

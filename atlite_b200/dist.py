@@ -88,6 +88,17 @@ class TimeShard:
             lab = pd.DatetimeIndex(lab)
         return out, lab
 
+    def sum_planes(self, *planes):
+        """All-reduce (sum) per-cell planes, e.g. the NaN-skipping time sum and the number
+        of valid steps per cell of a time-aggregated per-cell output (one collective)."""
+        import torch
+        import torch.distributed as dist
+
+        ts = [p if isinstance(p, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p)) for p in planes]
+        t = self._device_for_comm(torch.stack([x.to(torch.float32) for x in ts]).contiguous())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return tuple(t[i] for i in range(len(ts)))
+
     def sum_over_ranks(self, local, n_t):
         """All-reduce a per-cell time sum and the number of steps it covers."""
         import torch

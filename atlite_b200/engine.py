@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -156,26 +157,37 @@ class Plan:
 
 
 _PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
+_PLAN_LOCK = threading.Lock()
+_PLAN_CACHE_SIZE = 4  # per device
 
 
-def get_plan(matrix, ny, nx, device=None, pitch=None):
-    """Plans are cached (LRU, 4 entries): the typical workflow evaluates many
-    technologies against the same shapes."""
+def matrix_digest(m):
+    """Content hash of a CSR matrix (a collision would silently reuse a wrong plan)."""
+    h = hashlib.blake2b(digest_size=16)
+    for a in (m.indptr, m.indices, m.data):
+        h.update(np.ascontiguousarray(a).view(np.uint8))
+    return (m.shape, m.nnz, str(m.indices.dtype), h.digest())
+
+
+def get_plan(matrix, ny, nx, device=None, pitch=None, digest=None):
+    """Plans are cached (LRU, 4 entries per device): the typical workflow evaluates many
+    technologies against the same shapes.  Thread-safe (one host thread per GPU in the
+    single-process multi-GPU path); ``digest`` = a precomputed ``matrix_digest``."""
     m = sp.csr_matrix(matrix)
     device = current_device() if device is None else device
     pitch = nx if pitch is None else int(pitch)
-    h = hashlib.blake2b(digest_size=16)  # content hash: a collision would silently reuse a wrong plan
-    for a in (m.indptr, m.indices, m.data):
-        h.update(np.ascontiguousarray(a).view(np.uint8))
-    key = (device, ny, nx, pitch, m.shape, m.nnz, str(m.indices.dtype), h.digest())
-    plan = _PLAN_CACHE.get(key)
-    if plan is None:
-        plan = Plan(m, ny, nx, device, pitch)
+    key = (device, ny, nx, pitch) + (matrix_digest(m) if digest is None else digest)
+    with _PLAN_LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None:
+            _PLAN_CACHE.move_to_end(key)
+            return plan
+    plan = Plan(m, ny, nx, device, pitch)  # built outside the lock: devices build concurrently
+    with _PLAN_LOCK:
         _PLAN_CACHE[key] = plan
-        while len(_PLAN_CACHE) > 4:
-            _PLAN_CACHE.popitem(last=False)
-    else:
-        _PLAN_CACHE.move_to_end(key)
+        mine = [k for k in _PLAN_CACHE if k[0] == device]
+        for k in mine[:-_PLAN_CACHE_SIZE]:
+            del _PLAN_CACHE[k]
     return plan
 
 
@@ -251,8 +263,12 @@ class PvOp(_Op):
         self._time = time_ns(time)
         self.nt = len(self._time)
         self._lon, self._lat = _lib.as_f64(lon), _lib.as_f64(lat)
-        self._slope = np.ascontiguousarray(np.broadcast_to(np.asarray(slope, dtype=np.float64), (ny,)))
-        self._az = np.ascontiguousarray(np.broadcast_to(np.asarray(azimuth, dtype=np.float64), (ny,)))
+        slope, azimuth = np.asarray(slope, dtype=np.float64), np.asarray(azimuth, dtype=np.float64)
+        self.orientation_2d = slope.ndim == 2 or azimuth.ndim == 2
+        oshape = (ny, nx) if self.orientation_2d else (ny,)
+        # (ny,) tables broadcast along x when the other one is 2-D
+        self._slope = np.ascontiguousarray(np.broadcast_to(slope[:, None] if (self.orientation_2d and slope.ndim == 1) else slope, oshape))
+        self._az = np.ascontiguousarray(np.broadcast_to(azimuth[:, None] if (self.orientation_2d and azimuth.ndim == 1) else azimuth, oshape))
         cfg = _lib.PvConfig()
         cfg.ny, cfg.nx, cfg.nt = ny, nx, self.nt
         cfg.time_ns = _lib.ptr(self._time).value
@@ -264,6 +280,7 @@ class PvOp(_Op):
         cfg.clearsky_model = clearsky_model
         cfg.irr_branch, cfg.albedo_src, cfg.solar_src = irr_branch, albedo_src, solar_src
         cfg.pitch = int(pitch)
+        cfg.orientation_2d = 1 if self.orientation_2d else 0
         cfg.output = _lib.OUTPUT[output]
         for i, v in enumerate(thermal):
             cfg.thermal[i] = float(v)
@@ -328,12 +345,12 @@ class PvOp(_Op):
         first = next(a for a in fields.values() if a is not None)
         nt = first.shape[0]
         if nt == 0:
-            return self._empty_like(first, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+            return self._empty_like(first, (2, self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(fields, host=False)
         torch = _torch()
         if timesum:
-            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=first.device)
-            _lib.check(lib.atl_pv_timesum(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+            out = torch.zeros((2, self.ny, self.nx), dtype=torch.float32, device=first.device)  # sum | valid steps
+            _lib.check(lib.atl_pv_timesum(self.handle, C.byref(f), t0, nt, _dptr(out[0]), _dptr(out[1]), _stream_ptr()))
         else:
             out = self._out((nt, self.ny, self.nx), first)
             _lib.check(lib.atl_pv_cells(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
@@ -396,12 +413,12 @@ class WindOp(_Op):
         lib = _lib.load()
         nt = wnd.shape[0]
         if nt == 0:
-            return self._empty_like(wnd, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+            return self._empty_like(wnd, (2, self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(wnd, aux, host=False)
         torch = _torch()
         if timesum:
-            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=wnd.device)
-            _lib.check(lib.atl_wind_timesum(self.handle, C.byref(f), nt, _dptr(out), _stream_ptr()))
+            out = torch.zeros((2, self.ny, self.nx), dtype=torch.float32, device=wnd.device)
+            _lib.check(lib.atl_wind_timesum(self.handle, C.byref(f), nt, _dptr(out[0]), _dptr(out[1]), _stream_ptr()))
         else:
             out = self._out((nt, self.ny, self.nx), wnd)
             _lib.check(lib.atl_wind_cells(self.handle, C.byref(f), nt, _dptr(out), _stream_ptr()))
@@ -448,12 +465,12 @@ class HeatOp(_Op):
         ds = np.ascontiguousarray(day_start, dtype=np.int64)
         nd = len(ds) - 1
         if nd == 0 or temperature.shape[0] == 0:
-            return self._empty_like(temperature, (self.ny, self.nx) if timesum else (nd, self.ny, self.nx))
+            return self._empty_like(temperature, (2, self.ny, self.nx) if timesum else (nd, self.ny, self.nx))
         t = self._dev(temperature)
         torch = _torch()
         if timesum:
-            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=t.device)
-            _lib.check(lib.atl_heat_timesum(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
+            out = torch.zeros((2, self.ny, self.nx), dtype=torch.float32, device=t.device)
+            _lib.check(lib.atl_heat_timesum(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out[0]), _dptr(out[1]), _stream_ptr()))
         else:
             out = self._out((nd, self.ny, self.nx), t)
             _lib.check(lib.atl_heat_cells(self.handle, _dptr(t), _lib.ptr(ds), nd, _dptr(out), _stream_ptr()))
@@ -508,12 +525,12 @@ class PointwiseOp(_Op):
         lib = _lib.load()
         nt = field.shape[0]
         if nt == 0:
-            return self._empty_like(field, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+            return self._empty_like(field, (2, self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f = self._dev(field)
         torch = _torch()
         if timesum:
-            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=f.device)
-            _lib.check(lib.atl_pointwise_timesum(self.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
+            out = torch.zeros((2, self.ny, self.nx), dtype=torch.float32, device=f.device)
+            _lib.check(lib.atl_pointwise_timesum(self.handle, _dptr(f), nt, _dptr(out[0]), _dptr(out[1]), _stream_ptr()))
         else:
             out = self._out((nt, self.ny, self.nx), f)
             _lib.check(lib.atl_pointwise_cells(self.handle, _dptr(f), nt, _dptr(out), _stream_ptr()))
@@ -589,12 +606,12 @@ class CspOp(_Op):
         first = fields["influx_direct"]
         nt = first.shape[0]
         if nt == 0:
-            return self._empty_like(first, (self.ny, self.nx) if timesum else (0, self.ny, self.nx))
+            return self._empty_like(first, (2, self.ny, self.nx) if timesum else (0, self.ny, self.nx))
         f, keep = self._fields(fields, host=False)
         torch = _torch()
         if timesum:
-            out = torch.zeros((self.ny, self.nx), dtype=torch.float32, device=first.device)
-            _lib.check(lib.atl_csp_timesum(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))
+            out = torch.zeros((2, self.ny, self.nx), dtype=torch.float32, device=first.device)
+            _lib.check(lib.atl_csp_timesum(self.handle, C.byref(f), t0, nt, _dptr(out[0]), _dptr(out[1]), _stream_ptr()))
         else:
             out = self._out((nt, self.ny, self.nx), first)
             _lib.check(lib.atl_csp_cells(self.handle, C.byref(f), t0, nt, _dptr(out), _stream_ptr()))

@@ -11,6 +11,7 @@ Host-side mirror of the arithmetic in the reference's ``atlite/datasets/era5.py`
     get_data_temperature (204-225)      t2m, stl4, d2m -> temperature, soil temperature,
                                            dewpoint temperature (renames)
     get_data_runoff  (228-238, 241-246) ro -> runoff (clipped at 0)
+    get_data_height  (era5.py:65-81, 247-256)  z (geopotential) -> height = z / g0, static (y, x)
     sanitize_wind / sanitize_influx / sanitize_runoff (141-146, 195-201, 241-246)
 
 The results are float32 torch CUDA tensors (float64 for the solar position, like the
@@ -126,14 +127,30 @@ def get_data_runoff(ds, sanitize=True, device=None):
     return Dataset({"runoff": (_dims(ro), ro)}, coords=_coords(ds), attrs={"module": "era5"})
 
 
+def get_data_height(ds, device=None):
+    """era5.py:65-81 (_add_height) / 247-256: geopotential ``z`` -> ``height = z / g0``
+    (g0 = 9.80665), the first time step if ``z`` has a time axis; a static (y, x) field."""
+    torch = _torch()
+    device = torch.device("cuda", current_device() if device is None else device)
+    z = _dev_f32(_raw(ds, "z"), device)
+    if z.ndim == 3:
+        z = z[0]
+    h = (z / 9.80665).contiguous()
+    return Dataset({"height": (("y", "x"), h)}, coords=_coords(ds), attrs={"module": "era5"})
+
+
 def prepare(ds, features=("wind", "influx", "temperature", "runoff"), sanitize=True, device=None):
     """All requested features of one raw dataset merged into a device-resident cutout
-    Dataset (what ``Cutout.prepare`` stores for ``module='era5'``)."""
+    Dataset (what ``Cutout.prepare`` stores for ``module='era5'``).  The static
+    ``height`` feature (era5.py:62) is added whenever the raw data carries ``z``."""
     fns = {"wind": get_data_wind, "influx": get_data_influx, "temperature": get_data_temperature,
-           "runoff": get_data_runoff}
+           "runoff": get_data_runoff, "height": get_data_height}
+    features = list(features)
+    if "height" not in features and "z" in ds:
+        features.append("height")
     merged = None
     for f in features:
-        kw = {} if f == "temperature" else {"sanitize": sanitize}
+        kw = {} if f in ("temperature", "height") else {"sanitize": sanitize}
         part = fns[f](ds, device=device, **kw)
         if merged is None:
             merged = part

@@ -264,6 +264,15 @@ class Dataset:
     def dims_of(self, name):
         return self._vars[name][0]
 
+    def isel_time(self, lo, hi):
+        """Steps [lo, hi) of every variable that has a time axis (views, no copies);
+        static (y, x) variables and the other coordinates are shared."""
+        out = Dataset(coords={k: (v[lo:hi] if k == "time" else v) for k, v in self.coords.items()},
+                      attrs=self.attrs)
+        for name, (dims, arr) in self._vars.items():
+            out._vars[name] = (dims, arr[lo:hi] if dims and dims[0] == "time" else arr)
+        return out
+
     def __getitem__(self, name):
         if name in self._vars:
             dims, arr = self._vars[name]
@@ -291,6 +300,72 @@ class Dataset:
 
     def __repr__(self):
         return f"<atlite_b200.Dataset vars={list(self._vars)} sizes={self.sizes}>"
+
+
+class LazyDataset(Dataset):
+    """A cutout whose (time, y, x) variables are read on demand: ``loaders`` maps a variable
+    name to ``load(lo, hi) -> ndarray`` returning steps [lo, hi) (a NetCDF / HDF5 / zarr
+    reader, a memory map ...).  ``convert_and_aggregate`` converts such a cutout time part
+    by time part (``time_chunk`` steps at a time, the reference opens cutouts with
+    ``chunks={"time": 100}``, cutout.py:143), so it never has to fit the host memory;
+    static (y, x) variables are passed as arrays in ``static``."""
+
+    lazy = True
+
+    def __init__(self, loaders, coords, static=None, attrs=None, time_chunk=100, dtypes=None):
+        super().__init__(static or {}, coords=coords, attrs=attrs)
+        self._loaders = dict(loaders)
+        self._dtypes = dict(dtypes or {})
+        self.time_chunk = int(time_chunk)
+        self.chunks = {"time": (self.time_chunk,)}
+        self.loaded_steps = 0  # bookkeeping for tests: steps read so far / largest single read
+        self.largest_read = 0
+
+    def __contains__(self, name):
+        return name in self._loaders or super().__contains__(name)
+
+    def __iter__(self):
+        return iter(list(self._loaders) + list(self._vars))
+
+    def keys(self):
+        return list(self._loaders) + list(self._vars)
+
+    @property
+    def data_vars(self):
+        out = {n: (("time", "y", "x"), None) for n in self._loaders}
+        out.update(self._vars)
+        return out
+
+    def dims_of(self, name):
+        return ("time", "y", "x") if name in self._loaders else super().dims_of(name)
+
+    def dtype_of(self, name):
+        return np.dtype(self._dtypes.get(name, np.float32))
+
+    def raw(self, name):
+        if name in self._loaders:
+            raise RuntimeError(f"variable {name!r} of a LazyDataset is only readable through isel_time(lo, hi)")
+        return super().raw(name)
+
+    def __getitem__(self, name):
+        if name in self._loaders:
+            n = len(self.coords["time"])
+            return self.isel_time(0, n)[name]
+        return super().__getitem__(name)
+
+    def isel_time(self, lo, hi):
+        out = Dataset(coords={k: (v[lo:hi] if k == "time" else v) for k, v in self.coords.items()},
+                      attrs=self.attrs)
+        for name, load in self._loaders.items():
+            arr = np.asarray(load(lo, hi))
+            if arr.shape[0] != hi - lo:
+                raise ValueError(f"loader of {name!r} returned {arr.shape[0]} steps for [{lo}, {hi})")
+            out._vars[name] = (("time", "y", "x"), arr)
+        for name, (dims, arr) in self._vars.items():
+            out._vars[name] = (dims, arr)
+        self.loaded_steps += hi - lo
+        self.largest_read = max(self.largest_read, hi - lo)
+        return out
 
 
 def make_dataarray(values, dims, coords, attrs=None, name=None):

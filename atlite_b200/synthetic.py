@@ -221,38 +221,85 @@ def make_layout(nx, ny, seed=SEEDS["layout"]):
 # ----------------------------------------------------------------------
 
 
-def make_pv_fields_device(time, x, y, device, seed=0):
+DEVICE_BLOCK = 73  # RNG block (time steps) of the device generators: 8760 = 120 * 73, so the
+                   # 1/2/4/8-way time shards of a year start on block boundaries
+
+
+def _device_blocks(nt, t_offset, block):
+    """(absolute block id, [lo, hi) inside the block, [dst_lo, dst_hi) in the shard)."""
+    first, last = t_offset // block, (t_offset + nt - 1) // block
+    for b in range(first, last + 1):
+        lo, hi = max(b * block, t_offset), min((b + 1) * block, t_offset + nt)
+        yield b, lo - b * block, hi - b * block, lo - t_offset, hi - t_offset
+
+
+def make_pv_fields_device(time, x, y, device, seed=0, names=None, t_offset=0, block=DEVICE_BLOCK):
+    """The five PV fields as float32 CUDA tensors (time, y, x), generated block by block
+    straight into the final tensors (temporaries stay below ~1.5 GB, so a cutout that
+    nearly fills the HBM can be built: 1440 x 720 x 8760 x 5 fields = 169 GiB).
+    The random numbers of a time block depend only on (seed, absolute block id):
+    ``time`` = steps [t_offset, t_offset + nt) of the full axis gives exactly the rows
+    the unsharded generator produces (the time shards of a multi-GPU run ARE the single
+    GPU's cutout).  ``names`` restricts the variables (default: all five)."""
     import torch
 
     nt, ny, nx = len(time), len(y), len(x)
+    names = ("influx_toa", "influx_direct", "influx_diffuse", "albedo", "temperature") if names is None else tuple(names)
+    f = {n: torch.empty((nt, ny, nx), dtype=torch.float32, device=device) for n in names}
+    if nt == 0:
+        return f
+    need_toa = any(n.startswith("influx") for n in names)
+    if need_toa:
+        sd, cd, ch0, sh0 = (torch.from_numpy(a).to(device) for a in solar_tables(time))
+        lon = torch.from_numpy(np.radians(x)).to(device)
+        lat = torch.from_numpy(np.radians(y)).to(device)
+        cosh = ch0[:, None] * torch.cos(lon)[None, :] - sh0[:, None] * torch.sin(lon)[None, :]
+        slat, clat = torch.sin(lat), torch.cos(lat)
     g = torch.Generator(device=device)
-    g.manual_seed(1234 + seed)
-    sd, cd, ch0, sh0 = (torch.from_numpy(a).to(device) for a in solar_tables(time))
-    lon = torch.from_numpy(np.radians(x)).to(device)
-    lat = torch.from_numpy(np.radians(y)).to(device)
-    cosh = ch0[:, None] * torch.cos(lon)[None, :] - sh0[:, None] * torch.sin(lon)[None, :]
-    toa = torch.empty((nt, ny, nx), dtype=torch.float32, device=device)
-    step = max(1, 64_000_000 // (ny * nx))
-    for i in range(0, nt, step):
-        j = min(nt, i + step)
-        s = (sd[i:j, None] * torch.sin(lat)[None, :])[:, :, None] + (
-            cd[i:j, None] * torch.cos(lat)[None, :]
-        )[:, :, None] * cosh[i:j, None, :]
-        toa[i:j] = (1361.0 * s.clamp(min=0.0, max=1.0)).to(torch.float32)
 
     def u(lo, hi):
-        return torch.rand((nt, ny, nx), dtype=torch.float32, device=device, generator=g) * (hi - lo) + lo
+        return torch.rand((block, ny, nx), dtype=torch.float32, device=device, generator=g) * (hi - lo) + lo
 
-    kt, fd = u(0.1, 0.8), u(0.2, 0.9)
-    f = {
-        "influx_toa": toa,
-        "influx_direct": toa * kt * (1.0 - fd),
-        "influx_diffuse": toa * kt * fd,
-    }
-    del kt, fd
-    f["albedo"] = u(0.05, 0.4)
-    f["temperature"] = u(255.0, 305.0)
+    for b, blo, bhi, i, j in _device_blocks(nt, t_offset, block):
+        g.manual_seed(1234 + 100_003 * seed + b)
+        kt, fd, alb, tmp = u(0.1, 0.8), u(0.2, 0.9), u(0.05, 0.4), u(255.0, 305.0)
+        if need_toa:
+            s = (sd[i:j, None] * slat[None, :])[:, :, None] + (cd[i:j, None] * clat[None, :])[:, :, None] * cosh[i:j, None, :]
+            toa = (1361.0 * s.clamp(min=0.0, max=1.0)).to(torch.float32)
+            del s
+            if "influx_toa" in f:
+                f["influx_toa"][i:j] = toa
+            if "influx_direct" in f:
+                f["influx_direct"][i:j] = toa * kt[blo:bhi] * (1.0 - fd[blo:bhi])
+            if "influx_diffuse" in f:
+                f["influx_diffuse"][i:j] = toa * kt[blo:bhi] * fd[blo:bhi]
+            del toa
+        if "albedo" in f:
+            f["albedo"][i:j] = alb[blo:bhi]
+        if "temperature" in f:
+            f["temperature"][i:j] = tmp[blo:bhi]
+        del kt, fd, alb, tmp
     return f
+
+
+def make_wind_fields_device(nt, ny, nx, device, seed=0, t_offset=0, block=DEVICE_BLOCK):
+    """wnd100m = 8 * Weibull(k=2) m/s and roughness = exp(U(ln 1e-4, ln 2)) m as float32
+    CUDA tensors (time, y, x); same distributions as ``make_fields``, torch RNG seeded per
+    absolute time block like ``make_pv_fields_device``."""
+    import torch
+
+    w = torch.empty((nt, ny, nx), dtype=torch.float32, device=device)
+    r = torch.empty_like(w)
+    g = torch.Generator(device=device)
+    lo, hi = float(np.log(1e-4)), float(np.log(2.0))
+    for b, blo, bhi, i, j in _device_blocks(nt, t_offset, block) if nt else ():
+        g.manual_seed(4321 + 100_003 * seed + b)
+        un = torch.rand((block, ny, nx), dtype=torch.float32, device=device, generator=g)
+        w[i:j] = (8.0 * torch.sqrt(-torch.log1p(-un)))[blo:bhi]  # Weibull(k=2) by inversion
+        un = torch.rand((block, ny, nx), dtype=torch.float32, device=device, generator=g)
+        r[i:j] = torch.exp(un * (hi - lo) + lo)[blo:bhi]
+        del un
+    return {"wnd100m": w, "roughness": r}
 
 
 def make_voronoi_shapes(x, y, n_shapes, seed=8, margin=0.0):

@@ -61,7 +61,7 @@ extern "C" {
 #define ATL_ERR_CUDA (-2)    /* CUDA runtime error (see atl_last_error) */
 #define ATL_ERR_NOMEM (-3)
 
-#define ATL_ABI_VERSION 3
+#define ATL_ABI_VERSION 4
 
 int atl_abi_version(void);
 const char* atl_last_error(void);
@@ -88,6 +88,7 @@ typedef struct {
   int32_t fused;          /* 1: fused tile path, 0: two-pass CSR fallback */
   int32_t pitch;          /* row pitch of the input fields (elements), >= nx */
   int32_t vec;            /* 1: 128-bit lane layout (pitch % 4 == 0), 0: scalar */
+  int64_t n_pairs;        /* stored (slot, cell) entries the staged reduce walks     */
 } AtlPlanInfo;
 
 /* indptr/indices/data: host CSR arrays (scipy layout), column index
@@ -109,6 +110,16 @@ int atl_plan_tiling_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* i
                          const int32_t* indices_host, const double* data_host,
                          AtlPlanInfo* info_out, int32_t* tile_slot_ptr_out,
                          int32_t* slot_row_out, float* slot_w_out, int64_t slot_capacity);
+/* Host-only view of the entry lists the staged reduce kernel walks (CPU tests): for slot s
+ * (same numbering as atl_plan_tiling_host) the entries slot_pair_ptr[s] .. slot_pair_ptr[s+1],
+ * each {pair_cell = position 32*i + lane of the cell in the warp's staging row, pair_w}.
+ * Duplicates of one (bus, cell) are summed, explicit zeros kept (scipy CSR semantics:
+ * aggregate.py:25 multiplies exactly the stored entries).  Always fills *n_pairs_out; the
+ * arrays only when all three are given. */
+int atl_plan_pairs_host(int32_t ny, int32_t nx, int32_t n_bus, const int64_t* indptr_host,
+                        const int32_t* indices_host, const double* data_host,
+                        int64_t* n_pairs_out, int32_t* slot_pair_ptr_out, int32_t* pair_cell_out,
+                        float* pair_w_out, int64_t slot_capacity, int64_t pair_capacity);
 void atl_plan_destroy(AtlPlan* plan);
 
 /* Generic (time, S) dense  x  CSR^T  ->  (time, n_bus)  (aggregate.py:24-32):
@@ -141,8 +152,8 @@ typedef struct {
   int64_t time_shift_ns;      /* SolarPosition(time_shift=...), default 0       */
   const double* lon_deg;      /* host, nx   (ds["lon"])                          */
   const double* lat_deg;      /* host, ny   (ds["lat"])                          */
-  const double* slope_rad;    /* host, ny   orientation(lon,lat,sp)["slope"]     */
-  const double* azimuth_rad;  /* host, ny   orientation(...)["azimuth"]          */
+  const double* slope_rad;    /* host, ny (ny*nx if orientation_2d)  orientation(lon,lat,sp)["slope"]   */
+  const double* azimuth_rad;  /* host, ny (ny*nx if orientation_2d)  orientation(...)["azimuth"]        */
   int32_t tracking, trigon_model, clearsky_model, irr_branch, albedo_src,
       solar_src, panel_model;
   double altitude_threshold_deg; /* pv/irradiation.py:155, default 1.0         */
@@ -152,6 +163,9 @@ typedef struct {
   int32_t output;             /* ATL_OUT_*; panel[] is ignored unless ATL_OUT_PANEL */
   double thermal[3];          /* ATL_OUT_SOLAR_THERMAL: c0, c1, t_store in deg C  */
   int32_t pitch;              /* row pitch of the device fields, 0 = nx            */
+  int32_t orientation_2d;     /* 1: slope_rad / azimuth_rad vary per cell, (ny, nx) row-major:
+                                 an orientation callback (pv/orientation.py:107) that returns
+                                 (y, x) arrays */
 } AtlPvConfig;
 
 typedef struct { /* device pointers to (nt_slab, ny, nx) slabs; unused = NULL */
@@ -176,9 +190,11 @@ int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f,
 /* per-cell result (aggregate_time=None, no matrix): out_dev (nt, ny, nx) */
 int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
                  float* out_dev, void* stream);
-/* per-cell time sum, ACCUMULATED into out_dev (ny, nx) (caller zero-fills) */
+/* per-cell NaN-skipping time sum, ACCUMULATED into out_dev (ny, nx) (caller zero-fills);
+ * count_dev (ny, nx, may be NULL) accumulates the number of non-NaN steps per cell: the
+ * reference's `da.mean("time")` divides by it (convert.py:51-56).  Same for every *_timesum. */
 int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
-                   float* out_dev, void* stream);
+                   float* out_dev, float* count_dev, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* Wind: extrapolate_wind_speed + np.interp power curve                */
@@ -210,7 +226,7 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
 int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt,
                    float* out_dev, void* stream);
 int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt,
-                     float* out_dev, void* stream);
+                     float* out_dev, float* count_dev, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* Heat demand: daily mean temperature -> degree days                  */
@@ -236,7 +252,7 @@ int atl_heat_cells(const AtlHeatOp* op, const float* temperature_dev,
                    void* stream);
 int atl_heat_timesum(const AtlHeatOp* op, const float* temperature_dev,
                      const int64_t* day_start_host, int64_t n_days, float* out_dev,
-                     void* stream);
+                     float* count_dev, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* Pointwise conversions of ONE (time, y, x) field:                    */
@@ -265,7 +281,7 @@ int atl_pointwise_reduce(const AtlPointwiseOp* op, const AtlPlan* plan, const fl
 int atl_pointwise_cells(const AtlPointwiseOp* op, const float* field_dev, int64_t nt,
                         float* out_dev, void* stream);
 int atl_pointwise_timesum(const AtlPointwiseOp* op, const float* field_dev, int64_t nt,
-                          float* out_dev, void* stream);
+                          float* out_dev, float* count_dev, void* stream);
 int atl_pointwise_reduce_host(const AtlPointwiseOp* op, const AtlPlan* plan,
                               const float* field_host, int64_t nt, float* out_host,
                               int64_t chunk_steps);
@@ -307,7 +323,7 @@ int atl_csp_reduce(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* 
 int atl_csp_cells(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t nt,
                   float* out_dev, void* stream);
 int atl_csp_timesum(const AtlCspOp* op, const AtlCspFields* f, int64_t t0, int64_t nt,
-                    float* out_dev, void* stream);
+                    float* out_dev, float* count_dev, void* stream);
 int atl_csp_reduce_host(const AtlCspOp* op, const AtlPlan* plan, const AtlCspFields* f_host,
                         int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps);
 

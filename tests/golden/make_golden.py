@@ -221,6 +221,61 @@ def main():
     print(f"{len(cases)} cases -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
 
 
+def nan_cases():
+    """NaN handling of the PV chain, from the reference's own source: per-cell convert_pv /
+    convert_irradiation outputs with a NaN planted in every input field in turn, at a daytime
+    and at a night-time cell (pv/irradiation.py:198-200 NaN-preserving clip, :226 per-term
+    fillna(0), :252 mask; pv/solar_panel_model.py:23-36).  -> tests/golden/reference_nan.npz"""
+    nx, ny, nt = 9, 6, 30
+    base = syn.make_dataset(nx, ny, nt, x0=2.0, y0=35.0, dx=1.0, dy=2.0, start="2013-06-21 00:00",
+                            extra=("humidity",))
+    x, y, time = base.coords["x"], base.coords["y"], base.coords["time"]
+    F = {k: np.array(base.raw(k)) for k in base.keys()}
+    pv_names = ["influx_toa", "influx_direct", "influx_diffuse", "albedo", "temperature"]
+    day = int(np.argmax(F["influx_toa"][:, 2, 3]))
+    night = int(np.argmin(F["influx_toa"][:, 2, 3]))
+    assert F["influx_toa"][day, 2, 3] > 500 and F["influx_toa"][night, 2, 3] == 0
+    out = {"x": x, "y": y, "time_ns": pd.DatetimeIndex(time).as_unit("ns").asi8, "day": day, "night": night}
+    cases = []
+    for k, name in enumerate(pv_names):
+        f = {n: F[n].copy() for n in pv_names}
+        f[name][day, 2, 3] = np.nan        # daytime cell
+        f[name][night, 1, 4] = np.nan      # night-time cell (masked: alt < 1 deg)
+        f[name][day, 4, k] = np.inf if name != "temperature" else -np.inf
+        out[f"in|{name}"] = f[name]
+        ds = ref_dataset(f, time, x, y)
+        for trigon in ("simple", "other"):
+            tag = f"{name}|{trigon}"
+            out[f"pv|{tag}"] = values_tb(conv.pv(MockCutout(ds), panel="CSi", orientation="latitude_optimal",
+                                                 trigon_model=trigon, aggregate_time=None))
+            out[f"pvbof|{tag}"] = values_tb(conv.pv(MockCutout(ds), panel="KANENA", orientation="latitude_optimal",
+                                                    trigon_model=trigon, aggregate_time=None))
+            for kind in ("total", "direct", "diffuse", "ground"):
+                out[f"irr_{kind}|{tag}"] = values_tb(conv.irradiation(
+                    MockCutout(ds), orientation="latitude_optimal", irradiation=kind, trigon_model=trigon,
+                    aggregate_time=None))
+            cases.append(tag)
+    # total influx (Reindl split) with NaN influx / humidity
+    infl = F["influx_direct"] + F["influx_diffuse"]
+    for name in ("influx", "humidity", "influx_toa"):
+        f = {"influx_toa": F["influx_toa"].copy(), "influx": infl.copy(), "albedo": F["albedo"].copy(),
+             "temperature": F["temperature"].copy(), "humidity": F["humidity"].copy()}
+        f[name][day, 2, 3] = np.nan
+        f[name][night, 1, 4] = np.nan
+        out[f"in_reindl|{name}"] = f[name]
+        ds = ref_dataset(f, time, x, y)
+        out[f"pv_reindl|{name}"] = values_tb(conv.pv(MockCutout(ds), panel="CSi", orientation="latitude_optimal",
+                                                     aggregate_time=None))
+    out["in_influx_total"] = infl
+    out["in_humidity"] = F["humidity"]
+    for n in pv_names:
+        out[f"base|{n}"] = F[n]
+    out["cases"] = np.array(cases)
+    path = os.path.join(HERE, "reference_nan.npz")
+    np.savez_compressed(path, **out)
+    print(f"{len(cases)} NaN cases -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
 def era5_cases():
     """The arithmetic of datasets/era5.py AFTER the download (get_data_wind :120-135,
     sanitize_wind :141-146, get_data_influx :163-188, sanitize_influx :195-201) executed from
@@ -273,3 +328,4 @@ def era5_cases():
 if __name__ == "__main__":
     main()
     era5_cases()
+    nan_cases()

@@ -23,7 +23,8 @@ def test_reference_arm_prints_one_json_line():
     assert j["impl"] == "reference" and j["value"] > 0 and j["unit"] == "grid-cell-timesteps/s"
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
-    assert "workload" in j["config"] and "200x200x8760" in j["config"]["workload"]
+    assert "workload" in j["config"] and "1440x720x8760" in j["config"]["workload"]  # the north-star cutout
+    assert j["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -118,7 +118,7 @@ def test_cabi_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"not exported: {missing}"
     assert set(_lib.EXPORTED_SYMBOLS) == declared
-    assert _lib.load().atl_abi_version() == 3
+    assert _lib.load().atl_abi_version() == 4
 
 
 def test_no_gpu_fails_loudly(have_gpu):

@@ -69,6 +69,75 @@ def test_tiling_reproduces_csr(ny, nx, n_bus, density, seed):
         assert (np.diff(r) > 0).all()
 
 
+def pair_lists(m, ny, nx, n_slots):
+    lib = _lib.load()
+    m = sp.csr_matrix(m)
+    indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    idx = np.ascontiguousarray(m.indices, dtype=np.int32)
+    dat = np.ascontiguousarray(m.data, dtype=np.float64)
+    n = C.c_int64(0)
+    args = (ny, nx, m.shape[0], _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat))
+    _lib.check(lib.atl_plan_pairs_host(*args, C.byref(n), None, None, None, 0, 0))
+    ptr = np.zeros(n_slots + 1, dtype=np.int32)
+    cell = np.zeros(max(n.value, 1), dtype=np.int32)
+    w = np.zeros(max(n.value, 1), dtype=np.float32)
+    _lib.check(lib.atl_plan_pairs_host(*args, C.byref(n), _lib.ptr(ptr), _lib.ptr(cell), _lib.ptr(w),
+                                       n_slots, max(n.value, 1)))
+    return n.value, ptr, cell[: n.value], w[: n.value]
+
+
+def dense_from_pairs(info, tsp, row, ptr, cell, w, n_bus, ny, nx):
+    """The staged reduce on paper: entry {c, w} of a slot of tile (ty, tx) multiplies the value
+    the lane c % 32 parked as its (c // 32)-th cell (include/atlite_b200.h, atl_plan_pairs_host)."""
+    vec = nx % 4 == 0
+    n_tx = -(-nx // 32)
+    out = np.zeros((n_bus, ny * nx), dtype=np.float64)
+    for tile in range(info.n_tiles):
+        ty, tx = divmod(tile, n_tx)
+        for s in range(tsp[tile], tsp[tile + 1]):
+            cs = cell[ptr[s]:ptr[s + 1]]
+            assert (np.diff(cs) > 0).all(), "entries of a slot are sorted by staging index, no duplicates"
+            for c, wt in zip(cs, w[ptr[s]:ptr[s + 1]]):
+                lane, i = c % 32, c // 32
+                ly, lx = (lane // 8, 4 * (lane % 8) + i) if vec else (i, lane)
+                iy, ix = ty * 4 + ly, tx * 32 + lx
+                assert iy < ny and ix < nx, "entry on an out-of-grid cell"
+                out[row[s], iy * nx + ix] += wt
+    return out
+
+
+@settings(max_examples=40, deadline=None)
+@given(ny=st.integers(1, 11), nx=st.integers(1, 70), n_bus=st.integers(1, 6),
+       density=st.floats(0.01, 0.6), seed=st.integers(0, 10_000))
+def test_pair_lists_reproduce_csr(ny, nx, n_bus, density, seed):
+    """The entry lists the staged reduce kernel walks hold exactly the stored entries."""
+    rng = np.random.default_rng(seed)
+    m = sp.random(n_bus, ny * nx, density=density, random_state=seed, format="csr",
+                  data_rvs=lambda k: rng.uniform(-2, 2, k))
+    info, tsp, row, _ = tiling(m, ny, nx)
+    n, ptr, cell, w = pair_lists(m, ny, nx, int(info.n_slots))
+    assert n == m.nnz == info.n_pairs and ptr[-1] == n
+    got = dense_from_pairs(info, tsp, row, ptr, cell, w, n_bus, ny, nx)
+    np.testing.assert_array_equal(got, np.asarray(m.astype(np.float32).todense(), dtype=np.float64))
+
+
+def test_pair_lists_keep_explicit_zeros_and_sum_duplicates():
+    ny, nx = 6, 40
+    S = ny * nx
+    indptr = np.array([0, 2, 3, 3, 5], dtype=np.int64)  # raw CSR with a duplicate column and a stored 0.0
+    idx = np.array([5, 5, 7, S - 1, S - 1], dtype=np.int32)
+    dat = np.array([1.0, 2.0, 0.0, -3.0, 0.5])
+    lib = _lib.load()
+    n = C.c_int64(0)
+    _lib.check(lib.atl_plan_pairs_host(ny, nx, 4, _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat), C.byref(n),
+                                       None, None, None, 0, 0))
+    assert n.value == 3  # (0,5) summed to 3.0, the stored zero (1,7) kept (scipy multiplies it), (3,S-1) summed
+    ptr, cell, w = np.zeros(4, np.int32), np.zeros(3, np.int32), np.zeros(3, np.float32)
+    _lib.check(lib.atl_plan_pairs_host(ny, nx, 4, _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat), C.byref(n),
+                                       _lib.ptr(ptr), _lib.ptr(cell), _lib.ptr(w), 3, 3))
+    assert sorted(w.tolist()) == [-2.5, 0.0, 3.0]
+
+
 def test_duplicates_zeros_and_empty_rows():
     ny, nx = 6, 40
     S = ny * nx

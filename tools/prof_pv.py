@@ -37,10 +37,13 @@ else:
 x, y = syn.make_coords(nx, ny, x0, y0, *((0.05, 0.05) if size == "c5" else ()))
 tm = syn.make_time(nt + 24 * 170)[24 * 170:] if size == "big" else syn.make_time(nt)
 f = syn.make_pv_fields_device(tm, x, y, dev, seed=7)
+wf = syn.make_wind_fields_device(nt, ny, nx, dev, seed=7) if kind.startswith("wind") else None
 pitch = nx
 if size == "oddpad":  # what Cutout.to_device() does
     pitch = nx + (-nx) % 4
     f = {k: torch.nn.functional.pad(v, (0, pitch - nx)).contiguous() for k, v in f.items()}
+    if wf is not None:
+        wf = {k: torch.nn.functional.pad(v, (0, pitch - nx)).contiguous() for k, v in wf.items()}
 plan = engine.get_plan(syn.make_shapes(nx, ny, nbus), ny, nx, pitch=pitch)
 coords = dict(time=tm, x=x, y=y, lon=x, lat=y)
 out_b = 0.0
@@ -49,16 +52,14 @@ if kind in ("pvsum", "pvcube"):  # no-matrix branch (convert.py:200-211): per-ce
     fn, bpc = (lambda: spec.cells(timesum=kind == "pvsum")), 20
     out_b = 0.0 if kind == "pvsum" else 4.0
 elif kind in ("windsum", "windcube"):
-    ds = ab.Dataset({"wnd100m": (f["temperature"] - 255.0) * 0.5, "roughness": f["albedo"] * 0.5 + 1e-3}, coords=coords)
-    ws = _WindSpec(ds, ab.get_windturbineconfig("Vestas_V112_3MW"))
+    ws = _WindSpec(ab.Dataset(wf, coords=coords), ab.get_windturbineconfig("Vestas_V112_3MW"))
     fn, bpc = (lambda: ws.cells(timesum=kind == "windsum")), 8
     out_b = 0.0 if kind == "windsum" else 4.0
 elif kind == "pv":
     spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
     fn, bpc = (lambda: spec.op.reduce(plan, spec.fields)), 20
 elif kind == "wind":
-    ds = ab.Dataset({"wnd100m": (f["temperature"] - 255.0) * 0.5, "roughness": f["albedo"] * 0.5 + 1e-3}, coords=coords)
-    ws = _WindSpec(ds, ab.get_windturbineconfig("Vestas_V112_3MW"))
+    ws = _WindSpec(ab.Dataset(wf, coords=coords), ab.get_windturbineconfig("Vestas_V112_3MW"))
     fn, bpc = (lambda: ws.op.reduce(plan, ws.wnd, ws.aux)), 8
 else:
     hs = _HeatSpec(ab.Dataset({"temperature": f["temperature"]}, coords=coords), 15.0, 1.0, 0.0, 0.0)
