@@ -175,6 +175,7 @@ _SIGNATURES = {
     "atl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "atl_launch_count": (C.c_int64, []),
     "atl_set_deterministic": (C.c_int, [C.c_int]),
+    "atl_device_local_cpus": (C.c_int, [C.c_int, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_create_pitched": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
@@ -279,6 +280,14 @@ def device_count():
     n = C.c_int(0)
     rc = load().atl_device_count(C.byref(n))
     return n.value if rc == ATL_OK else 0
+
+
+def device_local_cpus(device):
+    """CPU ids next to GPU `device` (its NUMA node), [] when the topology is unknown."""
+    n = C.c_int32(0)
+    buf = np.zeros(4096, dtype=np.int32)
+    check(load().atl_device_local_cpus(int(device), buf.ctypes.data_as(C.c_void_p), len(buf), C.byref(n)))
+    return [int(c) for c in buf[: min(n.value, len(buf))]]
 
 
 def ptr(a):

@@ -7,7 +7,12 @@
 //
 // Pinned (cudaHostAlloc / cudaHostRegister'ed) inputs are DMA'd directly;
 // pageable inputs go through a pinned staging ring (memcpy -> async H2D).
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -84,7 +89,74 @@ struct StagePool {
   }
   std::vector<std::pair<char*, size_t>> sizes;  // buffers currently lent out
 };
-static StagePool g_stage;
+// One pool per device: its buffers are allocated (and first touched) by a thread bound to
+// the CPUs next to that GPU, so they live on the GPU's NUMA node.
+static StagePool g_stage_pool[64];
+static StagePool& stage_pool(int device) { return g_stage_pool[(device >= 0 && device < 64) ? device : 0]; }
+
+// ---- NUMA placement.  On a two-socket box half of the GPUs hang off each socket; a host
+// thread that stages data for (or allocates pinned memory for) a GPU of the other socket
+// pays the inter-socket link for every byte.  While a call streams slabs to device d, the
+// calling thread -- and the staging-copy threads it spawns, which inherit the mask -- run on
+// the CPUs the kernel lists as local to that PCI device
+// (/sys/bus/pci/devices/<bus id>/local_cpulist).  ATL_NUMA_BIND=0 turns this off.
+static bool device_local_cpus(int device, cpu_set_t* out) {
+  static std::mutex mu;
+  static bool known[64] = {false}, ok[64] = {false};
+  static cpu_set_t sets[64];
+  if (device < 0 || device >= 64) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!known[device]) {
+    known[device] = true;
+    const char* env = getenv("ATL_NUMA_BIND");
+    char bus[64] = {0};
+    if (!(env && atoi(env) == 0) && cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+      for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+      char path[160];
+      snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+      if (FILE* fh = fopen(path, "r")) {
+        char line[4096] = {0};
+        if (fgets(line, sizeof line, fh)) {
+          CPU_ZERO(&sets[device]);
+          int n = 0;
+          for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = -1, b = -1;
+            if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+            } else if (sscanf(tok, "%d", &a) == 1) {
+              b = a;
+            }
+            for (int c = a; c >= 0 && c <= b && c < CPU_SETSIZE; ++c, ++n) CPU_SET(c, &sets[device]);
+          }
+          ok[device] = n > 0;
+        }
+        fclose(fh);
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (ok[device]) *out = sets[device];
+  return ok[device];
+}
+
+// RAII: bind the calling thread to the device's local CPUs (intersected with the mask it
+// already has), restore on scope exit.
+struct NumaBind {
+  cpu_set_t saved;
+  bool active = false;
+  explicit NumaBind(int device) {
+    cpu_set_t local;
+    if (!device_local_cpus(device, &local)) return;
+    if (sched_getaffinity(0, sizeof saved, &saved) != 0) return;
+    cpu_set_t both;
+    CPU_AND(&both, &saved, &local);
+    if (CPU_COUNT(&both) == 0) return;
+    active = sched_setaffinity(0, sizeof both, &both) == 0;
+  }
+  ~NumaBind() {
+    if (active) sched_setaffinity(0, sizeof saved, &saved);
+  }
+};
 
 // Pageable -> pinned copy on several host threads (one thread moves ~10 GB/s, the
 // PCIe link wants 50+).
@@ -127,6 +199,8 @@ static int stream_slabs(int device, const std::vector<SlabField>& fields, int64_
   ATL_REQUIRE(out_host, "NULL output");
   if (n_units <= 0) return ATL_OK;
   ATL_CUDA(cudaSetDevice(device));
+  NumaBind numa(device);
+  StagePool& g_stage = stage_pool(device);
   pool_keep_memory(device);
   auto ustart = [&](int64_t u) { return unit_start ? unit_start[u] : u; };
   const int64_t total_steps = ustart(n_units) - ustart(0);
@@ -261,7 +335,24 @@ int heat_upload_days(const int64_t* day_start, int64_t n_days, int32_t** d_out, 
 
 extern "C" {
 
-void atl_release_host_staging(void) { g_stage.release(); }
+void atl_release_host_staging(void) {
+  for (auto& p : g_stage_pool) p.release();
+}
+
+int atl_device_local_cpus(int device, int32_t* cpus_out, int32_t capacity, int32_t* n_out) {
+  ATL_REQUIRE(n_out, "n_out is NULL");
+  *n_out = 0;
+  cpu_set_t set;
+  if (!device_local_cpus(device, &set)) return ATL_OK;  // unknown topology: empty list
+  int32_t n = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c)
+    if (CPU_ISSET(c, &set)) {
+      if (cpus_out && n < capacity) cpus_out[n] = c;
+      ++n;
+    }
+  *n_out = n;
+  return ATL_OK;
+}
 
 int atl_pv_reduce_host(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f,
                        int64_t t0, int64_t nt, float* out_host, int64_t chunk_steps) {

@@ -71,6 +71,10 @@ int atl_device_count(int* count_out);
  * kernel sums each bus's slots in a fixed order -> bitwise-repeatable results at
  * ~2 % extra traffic.  Returns the previous setting. */
 int atl_set_deterministic(int on);
+/* CPUs the kernel lists as local to the GPU's PCI device (its NUMA node): host-streaming
+ * calls bind their staging threads there for the duration of the call (ATL_NUMA_BIND=0
+ * disables).  Fills up to `capacity` CPU ids, *n_out = how many there are (0 = unknown). */
+int atl_device_local_cpus(int device, int32_t* cpus_out, int32_t capacity, int32_t* n_out);
 
 /* ------------------------------------------------------------------ */
 /* Aggregation plan: the (n_bus x S) CSR indicator/layout matrix       */

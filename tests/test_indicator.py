@@ -74,6 +74,64 @@ def test_oracle_analytic_areas():
     np.testing.assert_allclose(m, [[1, 1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 0]])
 
 
+def _random_polygon(rng, cx, cy, r, n, hole=False):
+    """Star-shaped (hence simple) polygon around (cx, cy); optionally with a hole."""
+    ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    rad = rng.uniform(0.45 * r, r, n)
+    outer = np.c_[cx + rad * np.cos(ang), cy + rad * np.sin(ang)]
+    if not hole:
+        return outer
+    a2 = np.sort(rng.uniform(0, 2 * np.pi, 5))
+    inner = np.c_[cx + 0.3 * r * np.cos(a2), cy + 0.3 * r * np.sin(a2)]
+    return [outer, inner[::-1]]
+
+
+def test_float_oracle_against_exact_rational_arithmetic():
+    """The float64 oracle against the SAME quantity in exact rational arithmetic
+    (oracle/indicator_exact.py): no rounding on the checker's side, so the bound below is the
+    float oracle's own arithmetic error (shapely cannot run in this image)."""
+    import indicator_exact as IE
+
+    rng = np.random.default_rng(11)
+    x, y = syn.make_coords(9, 7, -1.0, 50.0, 0.5, 0.25)
+    shapes = [_random_polygon(rng, 0.8, 50.6, 1.3, 9), _random_polygon(rng, 1.9, 50.9, 0.9, 7, hole=True),
+              box(x[2] - 0.25, y[1] - 0.125, x[4] + 0.25, y[3] + 0.125),  # edges exactly on cell borders
+              _random_polygon(rng, -1.4, 49.9, 1.0, 6),                   # sticks out of the grid
+              np.array([[0.1, 50.1], [2.3, 50.15], [0.1, 50.2]])]          # sliver
+    rings = [gis.geometry_rings(s) for s in shapes]
+    exact = IE.indicator_fractions(x, y, rings)
+    m = IO.indicatormatrix(x, y, rings, keep=0.0).tocoo()
+    got = {(int(i), int(j)): v for i, j, v in zip(m.row, m.col, m.data)}
+    assert set(got) == set(exact)
+    worst = max(abs(got[k] - float(exact[k])) for k in exact)
+    assert worst < 1e-13, worst  # observed 1.7e-14 (coordinates ~50, cells 0.25: shoelace cancellation)
+    # exact partition facts: the border-aligned box covers exactly 3 x 3 whole cells
+    box_cells = {k: v for k, v in exact.items() if k[0] == 2}
+    assert len(box_cells) == 9 and all(v == 1 for v in box_cells.values())
+    # the hole is subtracted exactly: total == area(outer) - area(inner) in cell units
+    import fractions
+
+    def area(r):
+        pts = [(fractions.Fraction(float(a)), fractions.Fraction(float(b))) for a, b in r]
+        return abs(sum(pts[k][0] * pts[(k + 1) % len(pts)][1] - pts[(k + 1) % len(pts)][0] * pts[k][1]
+                       for k in range(len(pts)))) / 2
+
+    cell = fractions.Fraction(1, 2) * fractions.Fraction(1, 4)
+    total = sum(v for k, v in exact.items() if k[0] == 1)
+    assert total == (area(shapes[1][0]) - area(shapes[1][1])) / cell  # the polygon lies inside the grid
+
+
+def test_exact_checker_reference_kat():
+    """test/test_gis.py:322-332 in exact arithmetic: the first grid cell and the
+    reference's `iloc[-2]` cell as shapes -> exactly one entry, exactly 1."""
+    import indicator_exact as IE
+
+    for iy, ix in ((0, 0), (8, 10)):
+        cell = box(X[ix] - 0.125, Y[iy] - 0.125, X[ix] + 0.125, Y[iy] + 0.125)
+        ex = IE.indicator_fractions(X, Y, [gis.geometry_rings(cell)])
+        assert ex == {(0, iy * 12 + ix): 1}
+
+
 def test_shape_packing_accepts_geojson_geo_interface_and_arrays():
     ring, hole = box(0, 0, 4, 4), box(1, 1, 2, 2)
 
@@ -167,6 +225,28 @@ def test_gpu_matches_oracle_on_random_polygons():
     # same sparsity pattern as the oracle wherever the value is not at the keep threshold
     w = want.toarray()
     assert ((got.toarray() > 0) == (w > 0))[np.abs(w - 1e-10) > 1e-11].all()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_exact_rational_arithmetic():
+    """The CUDA kernels against exact rational areas (no float oracle in between)."""
+    import indicator_exact as IE
+
+    rng = np.random.default_rng(12)
+    x, y = syn.make_coords(9, 7, -1.0, 50.0, 0.5, 0.25)
+    shapes = [_random_polygon(rng, 0.8, 50.6, 1.3, 11), _random_polygon(rng, 1.9, 50.9, 0.9, 8, hole=True),
+              box(x[2] - 0.25, y[1] - 0.125, x[4] + 0.25, y[3] + 0.125),
+              _random_polygon(rng, -1.4, 49.9, 1.0, 6)]
+    exact = IE.indicator_fractions(x, y, [gis.geometry_rings(s) for s in shapes])
+    m = gis.compute_indicatormatrix(x, y, shapes).tocoo()
+    got = {(int(i), int(j)): v for i, j, v in zip(m.row, m.col, m.data)}
+    big = {k for k, v in exact.items() if v > 1e-9}
+    assert big <= set(got)
+    assert max(abs(got[k] - float(exact[k])) for k in big) < 2e-12
+    assert all(float(exact.get(k, 0)) < 1e-9 or k in big for k in got)
+    for k, v in got.items():
+        if k[0] == 2:
+            assert v == 1.0  # border-aligned box: exactly whole cells
 
 
 @pytest.mark.gpu
