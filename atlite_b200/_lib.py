@@ -163,6 +163,11 @@ class CspConfig(C.Structure):
     ]
 
 
+class ChunkSpec(C.Structure):
+    _fields_ = [("ny", C.c_int32), ("nx", C.c_int32), ("elem_bytes", C.c_int32), ("shuffle", C.c_int32),
+                ("deflate", C.c_int32), ("chunk", C.c_int64 * 3)]
+
+
 class CspFields(C.Structure):
     _fields_ = [("influx_direct", C.c_void_p), ("solar_altitude", C.c_void_p), ("solar_azimuth", C.c_void_p)]
 
@@ -200,6 +205,8 @@ _SIGNATURES = {
     "atl_indicator_nnz": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "atl_indicator_export": (C.c_int, [_P, _P, _P, _P]),
     "atl_indicator_destroy": (None, [_P]),
+    "atl_decode_chunks": (C.c_int, [C.c_char_p, C.POINTER(ChunkSpec), C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, _P,
+                                    C.c_int32]),
     "atl_wind_create": (C.c_int, [C.c_int, C.POINTER(WindConfig), C.POINTER(_P)]),
     "atl_wind_curve_eval_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
     "atl_wind_destroy": (None, [_P]),

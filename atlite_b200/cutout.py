@@ -35,13 +35,13 @@ class Cutout:
         if data is None:
             if path is None:
                 raise ValueError("Cutout needs `data=` (or a NetCDF `path` when xarray is installed)")
-            if not HAVE_XARRAY:
-                raise ImportError(
-                    "opening a NetCDF cutout needs xarray; pass `data=` "
-                    "(atlite_b200.Dataset of NumPy arrays) instead"
-                )
-            chunks = kwargs.pop("chunks", {"time": 100})
-            data = xr.open_dataset(str(path), chunks=chunks)
+            if HAVE_XARRAY:  # the reference's own way in (cutout.py:142-154): lazy, {"time": 100} chunks
+                chunks = kwargs.pop("chunks", {"time": 100})
+                data = xr.open_dataset(str(path), chunks=chunks)
+            else:  # without xarray: this package's readers (chunk container, NetCDF-4 via h5py, NetCDF-3)
+                from . import ingest
+
+                data = ingest.open_cutout(path)
         elif isinstance(data, dict):
             data = Dataset(
                 {k: v for k, v in data.items() if k not in ("time", "x", "y", "lon", "lat")},

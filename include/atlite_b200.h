@@ -132,6 +132,29 @@ int atl_spmm(const AtlPlan* plan, const float* dense_dev, int64_t nt,
              float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------ */
+/* Cutout ingest: parallel decode of compressed (time, y, x) chunks      */
+/* (the storage format of data.py:139,245-248: zlib + byte shuffle; the  */
+/* read path of cutout.py:142-154)                                       */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int32_t ny, nx;       /* grid of the variable                                   */
+  int32_t elem_bytes;   /* 2, 4 or 8                                              */
+  int32_t shuffle;      /* 1: HDF5 byte-shuffle filter was applied before deflate */
+  int32_t deflate;      /* 1: chunks are zlib streams; 0: stored raw              */
+  int64_t chunk[3];     /* chunk shape (time, y, x); edge chunks are stored whole */
+} AtlChunkSpec;
+/* Decode the listed chunks of one variable into dst_host, a C-contiguous (nt, ny, nx) slab
+ * holding steps [t0, t0 + nt): every chunk is pread from `path` at file_offset[c]
+ * (stored_bytes[c] bytes), inflated, un-shuffled and its part inside the slab copied to its
+ * place; chunk_origin[3c..3c+2] = (t, y, x) of the chunk's first element.  Chunks run in
+ * parallel on n_threads host threads (0 = all cores, at most 64).  Bytes are copied as
+ * stored (the caller converts endianness / packing).  No GPU involved. */
+int atl_decode_chunks(const char* path, const AtlChunkSpec* spec, int64_t n_chunks,
+                      const int64_t* file_offset, const int64_t* stored_bytes,
+                      const int64_t* chunk_origin, int64_t t0, int64_t nt, void* dst_host,
+                      int32_t n_threads);
+
+/* ------------------------------------------------------------------ */
 /* PV: SolarPosition -> SurfaceOrientation -> TiltedIrradiation ->     */
 /* SolarPanelModel (convert.py:840-854)                                */
 /* ------------------------------------------------------------------ */
