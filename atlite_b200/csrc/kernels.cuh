@@ -234,8 +234,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
     __syncwarp();
     // ---- reduce: lanes along time, the slot's stored entries split NQ ways
     const int nvalid = min(TS, t1 - tc);
-    float* const o0 = out + (size_t)(tc + 2 * rp) * nb;
-    const bool w0 = lane < R && 2 * rp < nvalid, w1 = lane < R && 2 * rp + 1 < nvalid;
+    // after the butterfly every lane holds both sums of its row: group 0 adds the even step,
+    // group 1 the odd one, in ONE atomic instruction
+    const int odd = lane >= R ? 1 : 0;
+    float* const o_mine = out + (size_t)(tc + 2 * rp + odd) * nb;
+    const bool w_mine = lane < 2 * R && 2 * rp + odd < nvalid;
 #pragma unroll 1
     for (int s = s_beg; s < s_end; ++s) {
       const int2 rec = __ldg(plan.slot_rec + s);
@@ -258,8 +261,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       }
       const int row = __ldg(plan.slot_row + s);
-      if (w0) atomicAdd(o0 + row, a0);
-      if (w1) atomicAdd(o0 + nb + row, a1);
+      if (w_mine) atomicAdd(o_mine + row, odd ? a1 : a0);
     }
     __syncwarp();  // the next chunk's stores must not overtake this chunk's reads
   }

@@ -81,8 +81,11 @@ __host__ __device__ __forceinline__ float lattice_interp(float x, const char* lu
   return y;
 }
 
-template <bool VEC, int METHOD>  // METHOD: ATL_WIND_NONE / _LOG / _POWER, compile time (no predicated
-struct WindPhys {                // duplicates of the loads, no uniform branches in the per-cell code)
+// METHOD: ATL_WIND_NONE / _LOG / _POWER and LMODE (0: binary search or general LUT, chosen at
+// run time; 1 + nj: lattice LUT with nj steps) are compile time: no predicated duplicates of
+// the loads, no uniform branches or re-loaded kernel parameters in the per-cell code.
+template <bool VEC, int METHOD, int LMODE>
+struct WindPhys {
   static constexpr bool kVec = VEC;
   using Geom = TileGeomT<VEC>;
   const float* wnd;
@@ -129,21 +132,11 @@ struct WindPhys {                // duplicates of the loads, no uniform branches
   // np.interp for the lane's 4 values at once.
   __device__ __forceinline__ void interp4(const Cell& c, const float (&x)[4], float (&r)[4],
                                           const float* sm) const {
-    if (use_lut == 2) {
+    if constexpr (LMODE >= 1) {
       const char* lut = reinterpret_cast<const char*>(sm) + lut_stride + c.rep_off;  // skip the guard
-      if (nj == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = lattice_interp<0>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
-      } else if (nj == 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = lattice_interp<1>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = lattice_interp<2>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
-      }
+      for (int i = 0; i < 4; ++i)
+        r[i] = lattice_interp<LMODE - 1>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0, k_jump, jump, k_end, y_end);
       return;
     }
     if (use_lut) {
@@ -208,9 +201,9 @@ struct AtlWindOp {
   float* d_curve = nullptr;
 };
 
-template <bool VEC, int METHOD>
-static WindPhys<VEC, METHOD> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
-  WindPhys<VEC, METHOD> p;
+template <bool VEC, int METHOD, int LMODE>
+static WindPhys<VEC, METHOD, LMODE> make_phys(const AtlWindOp* op, const AtlWindFields* f) {
+  WindPhys<VEC, METHOD, LMODE> p;
   p.wnd = f->wnd;
   p.aux = f->aux;
   p.curve = op->d_curve;
@@ -237,6 +230,14 @@ static WindPhys<VEC, METHOD> make_phys(const AtlWindOp* op, const AtlWindFields*
   p.y_end = op->y_end;
   return p;
 }
+
+// compile-time table mode of the operator: 0 generic (binary search / general LUT), 1 + nj lattice
+static int lut_mode(const AtlWindOp* op) { return op->use_lut == 2 ? 1 + op->nj : 0; }
+#define ATL_WIND_ALL_CASES                                                                          \
+  ATL_WIND_CASE(ATL_WIND_NONE, 0) ATL_WIND_CASE(ATL_WIND_NONE, 1) ATL_WIND_CASE(ATL_WIND_NONE, 2)   \
+  ATL_WIND_CASE(ATL_WIND_NONE, 3) ATL_WIND_CASE(ATL_WIND_LOG, 0) ATL_WIND_CASE(ATL_WIND_LOG, 1)     \
+  ATL_WIND_CASE(ATL_WIND_LOG, 2) ATL_WIND_CASE(ATL_WIND_LOG, 3) ATL_WIND_CASE(ATL_WIND_POWER, 0)    \
+  ATL_WIND_CASE(ATL_WIND_POWER, 1) ATL_WIND_CASE(ATL_WIND_POWER, 2) ATL_WIND_CASE(ATL_WIND_POWER, 3)
 
 static int check_fields(const AtlWindOp* op, const AtlWindFields* f) {
   ATL_REQUIRE(op && f && f->wnd, "NULL argument");
@@ -599,16 +600,12 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
               "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
-#define ATL_WIND_CASE(M)                                                                  \
-  case M: {                                                                               \
-    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+#define ATL_WIND_CASE(M, L)                                                               \
+  case 4 * M + L: {                                                                       \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);            \
   }
-  switch (op->method) {
-    ATL_WIND_CASE(ATL_WIND_NONE)
-    ATL_WIND_CASE(ATL_WIND_LOG)
-    ATL_WIND_CASE(ATL_WIND_POWER)
-  }
+  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }
@@ -620,16 +617,12 @@ int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, floa
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
-#define ATL_WIND_CASE(M)                                                                  \
-  case M: {                                                                               \
-    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+#define ATL_WIND_CASE(M, L)                                                               \
+  case 4 * M + L: {                                                                       \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);  \
   }
-  switch (op->method) {
-    ATL_WIND_CASE(ATL_WIND_NONE)
-    ATL_WIND_CASE(ATL_WIND_LOG)
-    ATL_WIND_CASE(ATL_WIND_POWER)
-  }
+  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }
@@ -641,16 +634,12 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, fl
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
-#define ATL_WIND_CASE(M)                                                                  \
-  case M: {                                                                               \
-    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M>(op, f); };      \
+#define ATL_WIND_CASE(M, L)                                                               \
+  case 4 * M + L: {                                                                       \
+    auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);  \
   }
-  switch (op->method) {
-    ATL_WIND_CASE(ATL_WIND_NONE)
-    ATL_WIND_CASE(ATL_WIND_LOG)
-    ATL_WIND_CASE(ATL_WIND_POWER)
-  }
+  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }

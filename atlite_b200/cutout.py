@@ -22,6 +22,56 @@ if HAVE_XARRAY:  # pragma: no cover
     import xarray as xr
 
 
+class _Registered:
+    """Owns a cudaHostRegister'ed NumPy array (unregisters it when collected)."""
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __del__(self):
+        try:
+            import torch
+
+            torch.cuda.cudart().cudaHostUnregister(self.arr.ctypes.data)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def _numa_sharded_copy(a, devices, shard_bounds, local_cpus):
+    """Copy ``a`` (time, y, x) into a fresh page-aligned array whose time shard r is written
+    -- first touched -- by a thread pinned to the CPUs local to devices[r]."""
+    import os
+    import threading
+
+    nbytes = a.nbytes
+    raw = np.empty(nbytes + 4096, dtype=np.uint8)  # untouched pages: placement happens at first write
+    off = (-raw.ctypes.data) % 4096
+    dst = raw[off:off + nbytes].view(a.dtype).reshape(a.shape)
+    nt = a.shape[0]
+
+    def work(r, dev):
+        lo, hi = shard_bounds(nt, len(devices), r)
+        old = None
+        try:
+            cpus = local_cpus(dev)
+            if cpus:
+                old = os.sched_getaffinity(0)
+                both = set(cpus) & set(old)
+                if both:
+                    os.sched_setaffinity(0, both)  # pid 0 = the calling thread
+            dst[lo:hi] = a[lo:hi]
+        finally:
+            if old is not None:
+                os.sched_setaffinity(0, old)
+
+    ths = [threading.Thread(target=work, args=(r, d)) for r, d in enumerate(devices)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return dst
+
+
 class Cutout:
     """``devices``: which GPUs of this process convert the cutout.  ``None`` = the current
     CUDA device; ``"all"`` or a list of device indices = the time axis of a HOST-resident
@@ -138,14 +188,22 @@ class Cutout:
         return gis.compute_indicatormatrix(self.coords["x"], self.coords["y"], shapes)
 
     # ---- host residency
-    def pin_host(self, variables=None):
+    def pin_host(self, variables=None, devices=None):
         """Return a Cutout whose (time, y, x) variables live in page-locked host memory
-        (float32 NumPy views of pinned torch tensors).  Host-streamed conversions then DMA
-        the time slabs directly at PCIe rate instead of staging pageable memory through
-        the library's pinned ring."""
+        (float32 NumPy arrays).  Host-streamed conversions then DMA the time slabs directly at
+        PCIe rate instead of staging pageable memory through the library's pinned ring.
+
+        With ``devices`` (default: this cutout's ``devices``) the copy is NUMA-aware: the steps
+        each GPU will stream (``dist.shard_bounds``) are first touched -- hence physically
+        placed -- by a thread running on the CPUs next to that GPU, so that on a two-socket box
+        no shard crosses the inter-socket link on its way to its GPU."""
         import torch
 
+        from . import _lib
+        from .dist import shard_bounds
+
         ds = self.data
+        devs = self.devices if devices is None else Cutout(data=ds, devices=devices).devices
         names = list(ds.data_vars) if variables is None else list(variables)
         out = Dataset(coords={k: np.asarray(getattr(v, "values", v)) for k, v in dict(ds.coords).items()
                               if k in ("time", "x", "y", "lon", "lat")},
@@ -155,12 +213,20 @@ class Cutout:
             a = _convert._to_host(_convert._raw(ds, n))
             if not (n.startswith("solar_") and a.dtype == np.float64):
                 a = np.asarray(a, dtype=np.float32)
+            if devs and len(devs) > 1 and a.ndim == 3:
+                dst = _numa_sharded_copy(a, devs, shard_bounds, _lib.device_local_cpus)
+                rc = torch.cuda.cudart().cudaHostRegister(dst.ctypes.data, dst.nbytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister failed ({rc}) for variable {n!r}")
+                keep.append(_Registered(dst))
+                out[n] = (("time", "y", "x"), dst)
+                continue
             t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
             t.numpy()[...] = a
             keep.append(t)
             out[n] = (("time", "y", "x")[-a.ndim:], t.numpy())
-        res = Cutout(data=out, time_shard=self.time_shard, devices=self._devices)
-        res._pinned = keep  # the tensors own the page-locked memory
+        res = Cutout(data=out, time_shard=self.time_shard, devices=self._devices if devices is None else devices)
+        res._pinned = keep  # these objects own the page-locked memory
         return res
 
     # ---- device residency
