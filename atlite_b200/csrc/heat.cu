@@ -20,6 +20,7 @@ struct HeatParams {
 };
 
 constexpr int HEAT_UNROLL = 6;
+constexpr int HEAT_STAGE = 16;  // days a warp parks in shared memory before one reduce phase
 
 // One chunk of up to HEAT_UNROLL consecutive time steps for the lane's 4 cells.
 template <bool VEC>
@@ -97,12 +98,29 @@ __global__ void __launch_bounds__(CTA_THREADS)
   const int d0 = blockIdx.y * db, d1 = min(n_days, d0 + db);
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
   float v[4];
+  if (MODE == 0) {
+    // daily values of HEAT_STAGE days are parked in shared memory, then reduced with the lanes
+    // along the days (kernels.cuh: staged_reduce); NaN days poison exactly the buses whose
+    // stored entries meet them
+    extern __shared__ __align__(16) float smem[];
+    char* const stage = reinterpret_cast<char*>(smem) + warp * StageT<HEAT_STAGE>::kWarpBytes;
+    stage_init<HEAT_STAGE>(stage, lane);
+    for (int dc = d0; dc < d1; dc += HEAT_STAGE) {
+      const int n = min(HEAT_STAGE, d1 - dc);
+      for (int k = 0; k < n; ++k) {
+        heat_day(hp, g, dc + k, v);
+        zero_invalid(g, v);
+        stage_store1<HEAT_STAGE>(stage, lane, k, v);
+      }
+      __syncwarp();
+      staged_reduce<HEAT_STAGE>(stage, plan, s_beg, s_end, out, dc, n, lane);
+      __syncwarp();
+    }
+    return;
+  }
   for (int d = d0; d < d1; ++d) {
     heat_day(hp, g, d, v);
-    if (MODE == 0) {
-      zero_invalid(g, v);
-      reduce_slots(v, s_beg, s_end, plan, out + (size_t)d * plan.n_bus, lane);
-    } else if (MODE == 1) {
+    if (MODE == 1) {
       store4(out + (int64_t)d * gd.S_out, gd, g, v);
     } else {
 #pragma unroll
@@ -209,6 +227,11 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   hp.cooling = op->cooling;
   int db = (int)((n_days * gx + 148LL * 4 * 8 - 1) / (148LL * 4 * 8));
   db = db < 1 ? 1 : (db > 8 ? 8 : db);
+  size_t smem = 0;
+  if (mode == 0) {  // whole staging chunks per block
+    db = HEAT_STAGE;
+    smem = StageT<HEAT_STAGE>::kCtaBytes;
+  }
   dim3 grid(gx, (unsigned)((n_days + db - 1) / db));
   // lane layout: the plan's for the fused reduce, else by grid width / alignment
   const bool al = aligned16(temp);
@@ -222,14 +245,14 @@ int heat_launch_core(int mode, const AtlHeatOp* op, const AtlPlan* plan, const f
   }
   if (vec) {
     if (mode == 0)
-      k_heat<0, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
+      k_heat<0, true><<<grid, CTA_THREADS, smem, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
     else if (mode == 1)
       k_heat<1, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, nullptr, (int)n_days, db);
     else
       k_heat<2, true><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, cnt_out, (int)n_days, db);
   } else {
     if (mode == 0)
-      k_heat<0, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
+      k_heat<0, false><<<grid, CTA_THREADS, smem, st>>>(hp, gdo, pd, det_acc ? det_acc : out, nullptr, (int)n_days, db);
     else if (mode == 1)
       k_heat<1, false><<<grid, CTA_THREADS, 0, st>>>(hp, gdo, pd, out, nullptr, (int)n_days, db);
     else

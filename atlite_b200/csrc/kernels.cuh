@@ -139,15 +139,86 @@ struct StageT {
 };
 __host__ __device__ constexpr int smem_table_bytes(int floats) { return (floats * 4 + 15) & ~15; }
 
+// The bytes behind the 128 cells of every staging row hold 0.0f (the padding entries of the
+// plan point there).
+template <int TS>
+__device__ __forceinline__ void stage_init(char* stage, int lane) {
+  using Stage = StageT<TS>;
+  if (lane < Stage::kRows) {
+#pragma unroll
+    for (int k = 0; k < Stage::kShift; ++k)
+      *reinterpret_cast<float2*>(stage + lane * Stage::kRowBytes + PAD_OFF + 8 * k) = make_float2(0.f, 0.f);
+  }
+}
+
+// Park the lane's 4 values of one step (row = step pair, half = parity) / of a step pair.
+template <int TS>
+__device__ __forceinline__ void stage_store1(char* stage, int lane, int k, const float (&v)[4]) {
+  char* const w = stage + lane * 8 + (k >> 1) * StageT<TS>::kRowBytes + (k & 1) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(w + 256 * i) = v[i];
+}
+template <int TS>
+__device__ __forceinline__ void stage_store2(char* stage, int lane, int k_even, const float (&v0)[4],
+                                             const float (&v1)[4]) {
+  char* const w = stage + lane * 8 + (k_even >> 1) * StageT<TS>::kRowBytes;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(w + 256 * i) = make_float2(v0[i], v1[i]);
+}
+
+// The reduce phase of one chunk: rows [row0, row0 + nvalid) of `out` receive the sums of the
+// staged steps.  Lane = group * R + row: lane (q, r) owns the step pair r and walks the
+// entries q, q + NQ, q + 2 NQ, ... of every slot's list; one butterfly over the groups, then
+// group 0 adds the even step and group 1 the odd one in ONE atomic instruction.
+// (__syncwarp() before -- the stores of all lanes must be visible -- and after.)
+template <int TS>
+__device__ __forceinline__ void staged_reduce(const char* stage, const PlanDev& plan, int s_beg, int s_end,
+                                              float* __restrict__ out, int row0, int nvalid, int lane) {
+  static_assert(TS == 8 || TS == 16 || TS == 32, "TS/2 rows must divide the warp");
+  using Stage = StageT<TS>;
+  constexpr int R = TS / 2;   // rows = lanes along time
+  constexpr int NQ = 32 / R;  // lanes sharing a row split a slot's entries NQ ways
+  constexpr int U = PAIR_PAD / NQ;  // entries per group and padding unit
+  static_assert(U >= 1 && U * NQ == PAIR_PAD, "PAIR_PAD must be a multiple of the group count");
+  const int rp = lane & (R - 1), q = lane / R;
+  const char* const rd_row = stage + rp * Stage::kRowBytes;
+  const uint2* const pairs_q = reinterpret_cast<const uint2*>(plan.pairs) + q;
+  const int nb = plan.n_bus;
+  const int odd = lane >= R ? 1 : 0;
+  float* const o_mine = out + (size_t)(row0 + 2 * rp + odd) * nb;
+  const bool w_mine = lane < 2 * R && 2 * rp + odd < nvalid;
+#pragma unroll 1
+  for (int s = s_beg; s < s_end; ++s) {
+    const int2 rec = __ldg(plan.slot_rec + s);
+    const uint2* p = pairs_q + rec.x;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+    for (int it = 0; it < rec.y; ++it, p += PAIR_PAD) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint2 pw = __ldg(p + u * NQ);
+        const float2 x = *reinterpret_cast<const float2*>(rd_row + pw.x);
+        const float w = __uint_as_float(pw.y);
+        a0 = fmaf(w, x.x, a0);
+        a1 = fmaf(w, x.y, a1);
+      }
+    }
+#pragma unroll
+    for (int o = R; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    const int row = __ldg(plan.slot_row + s);
+    if (w_mine) atomicAdd(o_mine + row, odd ? a1 : a0);
+  }
+}
+
 template <class Phys, int B, int MINB, int TS>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
     k_fused_reduce(const Phys phys, const GridDev gd, const PlanDev plan,
                    float* __restrict__ out, int nt, int tb) {
-  static_assert(TS == 8 || TS == 16 || TS == 32, "TS/2 rows must divide the warp");
   static_assert(B == 1 || B % 2 == 0, "steps are staged in pairs");
   static_assert(TS % B == 0, "a chunk is a whole number of batches");
-  constexpr int R = TS / 2;    // rows = lanes along time in the reduce phase
-  constexpr int NQ = 32 / R;   // lanes sharing a row split the slot's entries NQ ways
   using Stage = StageT<TS>;
   extern __shared__ __align__(16) float smem[];
   phys.stage(smem);
@@ -164,7 +235,6 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   const int t1 = min(nt, t0 + tb);
   if (t0 >= t1) return;
   const int tlast = t1 - 1;
-  const int nb = plan.n_bus;
 
   typename Phys::Cell c;
   phys.init(c, g, smem);
@@ -175,19 +245,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   // B - 1 redundant loads / evaluations per time block, their results never written.
 #pragma unroll
   for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t0 + j, tlast) * S4, r[j]);
-
-  char* const st_lane = stage + lane * 8;  // staging: value i of this lane -> + 256 i
-  // reduce phase: lane = group * R + row; group q walks entries q, q + NQ, q + 2 NQ, ...
-  const int rp = lane & (R - 1), q = lane / R;
-  const char* const rd_row = stage + rp * Stage::kRowBytes;
-  constexpr int U = PAIR_PAD / NQ;  // entries per group and padding unit
-  static_assert(U >= 1 && U * NQ == PAIR_PAD, "PAIR_PAD must be a multiple of the group count");
-  if (lane < R) {  // the bytes behind the 128 cells of every row: 0.0f for the padding entries
-#pragma unroll
-    for (int k = 0; k < Stage::kShift; ++k)
-      *reinterpret_cast<float2*>(stage + lane * Stage::kRowBytes + PAD_OFF + 8 * k) = make_float2(0.f, 0.f);
-  }
-  const uint2* const pairs_q = reinterpret_cast<const uint2*>(plan.pairs) + q;
+  stage_init<TS>(stage, lane);
 
 #pragma unroll 1
   for (int tc = t0; tc < t1; tc += TS) {
@@ -218,51 +276,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 #pragma unroll
       for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t + B + j, tlast) * S4, r[j]);
       if (B == 1) {
-        char* const w = st_lane + (k >> 1) * Stage::kRowBytes + (k & 1) * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(w + 256 * i) = v[0][i];
+        stage_store1<TS>(stage, lane, k, v[0]);
       } else {
 #pragma unroll
-        for (int j = 0; j + 1 < B; j += 2) {
-          char* const w = st_lane + ((k + j) >> 1) * Stage::kRowBytes;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float2*>(w + 256 * i) = make_float2(v[j][i], v[j + 1][i]);
-        }
+        for (int j = 0; j + 1 < B; j += 2) stage_store2<TS>(stage, lane, k + j, v[j], v[j + 1]);
       }
     }
     __syncwarp();
-    // ---- reduce: lanes along time, the slot's stored entries split NQ ways
-    const int nvalid = min(TS, t1 - tc);
-    // after the butterfly every lane holds both sums of its row: group 0 adds the even step,
-    // group 1 the odd one, in ONE atomic instruction
-    const int odd = lane >= R ? 1 : 0;
-    float* const o_mine = out + (size_t)(tc + 2 * rp + odd) * nb;
-    const bool w_mine = lane < 2 * R && 2 * rp + odd < nvalid;
-#pragma unroll 1
-    for (int s = s_beg; s < s_end; ++s) {
-      const int2 rec = __ldg(plan.slot_rec + s);
-      const uint2* p = pairs_q + rec.x;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 2
-      for (int it = 0; it < rec.y; ++it, p += PAIR_PAD) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const uint2 pw = __ldg(p + u * NQ);
-          const float2 x = *reinterpret_cast<const float2*>(rd_row + pw.x);
-          const float w = __uint_as_float(pw.y);
-          a0 = fmaf(w, x.x, a0);
-          a1 = fmaf(w, x.y, a1);
-        }
-      }
-#pragma unroll
-      for (int o = R; o < 32; o <<= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      }
-      const int row = __ldg(plan.slot_row + s);
-      if (w_mine) atomicAdd(o_mine + row, odd ? a1 : a0);
-    }
+    staged_reduce<TS>(stage, plan, s_beg, s_end, out, tc, min(TS, t1 - tc), lane);
     __syncwarp();  // the next chunk's stores must not overtake this chunk's reads
   }
 }
