@@ -8,8 +8,11 @@ Workload = the BASELINE.json north star: synthetic ERA5 1440 x 720 x 8760
 orientation="latitude_optimal") aggregated to 3000 NUTS-like shapes.  One
 "step" = one full pass of the hot path over that cutout: 9.08e9
 cell-timesteps, 181.6 GB (169.2 GiB) of float32 input, all of it resident in
-HBM at N = 1 (when the device cannot hold it, the year is processed as resident
-parts one after the other and the part times are summed; `config.parts`).
+HBM.  Inputs may take at most 80 % of the device memory (a full device stops
+answering the box's health checks), so at N = 1 the year is processed as TWO
+resident half-years one after the other -- each timed over its own `--steps`
+passes with its own warm-up -- and the two times are summed (`config.parts`;
+one launch per part through the operator's `t0` slab argument).
 
 N > 1 (torchrun, one rank per GPU) is STRONG scaling: the same cutout, its
 time axis sharded T/N per rank (atlite_b200.dist.shard_bounds; the synthetic
@@ -50,6 +53,7 @@ X0, Y0 = -180.0, -90.0
 PANEL, ORIENT, TURBINE = "CSi", "latitude_optimal", "Vestas_V112_3MW"
 BYTES_PER_CELL_TS = 20.0  # 5 float32 fields
 E2E_MAX_STEPS = 1095  # host-streamed slab per rank (22.7 GB of pinned host memory)
+VRAM_FRACTION = 0.80  # share of the device memory the resident inputs may take
 WORKLOAD = (f"synthetic ERA5 {NX}x{NY}x{NT}, cutout.pv(panel=CSi, orientation=latitude_optimal) "
             f"-> {NBUS} shapes (BASELINE.json north star)")
 METRIC = "grid-cell-timesteps/s on PV convert+aggregate"
@@ -175,26 +179,63 @@ class CpuArm:
                 p.kill()  # the exact processes this object started
 
 
-def _cpu_plan(target_s):
-    """Chunk length per worker: the reference computes in dask chunks of {"time": 100}
-    (cutout.py:143) -- 4.0e6 elements per array at the 200 x 200 config.  On the
-    1440 x 720 grid one step already is 1.04e6 cells, and a 100-step chunk would need
-    ~25 GB of float64 temporaries per worker, so the chunk is bounded by time and host
-    memory instead (never below 4 steps = 4.1e6 elements per array, the element count of
-    the reference's own chunks at configs[1])."""
+def _host_limits():
+    """(usable cores, usable bytes of RAM) of THIS container: the scheduler affinity mask and
+    the cgroup CPU quota / memory limit when there are any, not the bare host's numbers -- a
+    process pool sized for the host inside a smaller cgroup takes the whole box down."""
     import psutil
 
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        cores = os.cpu_count() or 1
     avail = psutil.virtual_memory().available
-    per_step_bytes = NX * NY * 8 * 30  # ~30 live float64 (time, y, x) temporaries in convert_pv
-    by_mem = int(0.4 * avail / cores / per_step_bytes)
+    try:  # cgroup v2
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            cores = max(1, min(cores, int(float(quota) / float(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    for lim_f, use_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            with open(lim_f) as fh:
+                lim = fh.read().strip()
+            with open(use_f) as fh:
+                use = int(fh.read().strip())
+            if lim != "max" and int(lim) < (1 << 60):
+                avail = min(avail, max(0, int(lim) - use))
+            break
+        except Exception:  # noqa: BLE001
+            continue
+    return cores, avail
+
+
+def _cpu_plan(target_s):
+    """Workers and chunk length of the CPU arm.  The reference computes in dask chunks of
+    {"time": 100} (cutout.py:143) -- 4.0e6 elements per array at the 200 x 200 config.  On the
+    1440 x 720 grid one step already is 1.04e6 cells, so the chunk is bounded by the time
+    target and by host memory instead (never below 4 steps = 4.1e6 elements per array, the
+    element count of the reference's own chunks at configs[1]).  A worker needs ~0.35 GB
+    (interpreter, NumPy / SciPy / pandas, the 3000-shape matrix) plus ~0.12 GB per step of its
+    chunk (inputs + the float64 temporaries alive at once; measured: 0.61 GB peak for 4 steps);
+    the pool is sized to stay below a QUARTER of the memory this container may use."""
+    cores, avail = _host_limits()
+    budget = 0.25 * avail
     rate_guess = 3.0e6  # cell-ts/s/core with every core busy (3.6e6 measured on the 8-core build box)
-    by_time = int(target_s * rate_guess / (NX * NY))
-    return cores, int(np.clip(min(by_mem, by_time, 100), 4, 100))
+    chunk = int(np.clip(target_s * rate_guess / (NX * NY), 4, 100))
+    workers = cores
+    while workers > 1 and workers * (0.35e9 + 0.12e9 * chunk) > budget:
+        if chunk > 4:
+            chunk = max(4, chunk // 2)
+        else:
+            workers = max(1, workers * 3 // 4)
+    return workers, chunk
 
 
 def cpu_measure(rounds, warmup, target_s=12.0):
-    cores, chunk = _cpu_plan(target_s)
+    cores, chunk = _cpu_plan(target_s)  # cores = worker processes actually used
     arm = CpuArm(cores, chunk, rounds + warmup)
     try:
         for _ in range(warmup):
@@ -410,9 +451,12 @@ def run_ours(args):
 
     # ---- PV north star: this rank's shard, resident in HBM (in `parts` when it cannot be)
     need = (hi - lo) * S * BYTES_PER_CELL_TS
-    free, _total = torch.cuda.mem_get_info()
+    free, total_mem = torch.cuda.mem_get_info()
+    # never fill the device: at most VRAM_FRACTION of it holds inputs (a box whose GPU memory is
+    # exhausted stops answering its health checks); generation temporaries need ~3 GiB more
+    usable = min(free - (6 << 30), VRAM_FRACTION * total_mem)
     parts = 1
-    while need / parts + (3 << 30) > free and parts < 16:
+    while need / parts > usable and parts < 16:
         parts += 1
     clk = ClockSampler(comm.local_rank)
     my_rows = (sum(counts[:rank]), sum(counts[:rank + 1]))
