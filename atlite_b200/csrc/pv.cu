@@ -322,7 +322,11 @@ struct PvPhys {
                                                            : (r.salt[i] < alt_thr);
       const bool keep_it = !low & !(influx_ <= 0.01f);
       const float G = keep_it ? total : 0.f;
-      if (out == ATL_OUT_PANEL) {
+      if (!EXACT && !FAST && G != G) {
+        // a NaN irradiance must SURFACE (Bofinger's threshold and the solar-thermal `where`
+        // would turn it into a finite 0): the kernels then re-evaluate with compute_exact
+        v[i] = G;
+      } else if (out == ATL_OUT_PANEL) {
         v[i] = panel(G, r.temp[i]);
       } else if (out == ATL_OUT_SOLAR_THERMAL) {
         // eta = c0 - c1 * ((t_store - T) / irr.where(irr != 0)).fillna(0); output.where(> 0, 0)

@@ -509,7 +509,11 @@ def run_ours(args):
         pass
 
     # ---- e2e through the public API on pinned host arrays: a bounded slab of this rank's shard
-    ne = min(E2E_MAX_STEPS, hi - lo)
+    # pinned host memory is charged to the container's memory cgroup: every rank of this box takes
+    # at most its share of a quarter of what the container may still use
+    _, host_avail = _host_limits()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    ne = int(min(E2E_MAX_STEPS, hi - lo, max(24, 0.25 * host_avail / local_world // (S * BYTES_PER_CELL_TS))))
     fe = syn.make_pv_fields_device(time_axis[lo:lo + ne], x, y, dev, seed=0, t_offset=lo)
     spec = _PvSpec(ab.Dataset(fe, coords=dict(time=time_axis[lo:lo + ne], **co)),
                    ab.get_solarpanelconfig(PANEL), ab.get_orientation(ORIENT))
