@@ -20,7 +20,7 @@ struct HeatParams {
 };
 
 constexpr int HEAT_UNROLL = 6;
-constexpr int HEAT_STAGE = 16;  // days a warp parks in shared memory before one reduce phase
+constexpr int HEAT_STAGE = 8;  // days a warp parks in shared memory before one reduce phase
 
 // One chunk of up to HEAT_UNROLL consecutive time steps for the lane's 4 cells.
 template <bool VEC>
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
     extern __shared__ __align__(16) float smem[];
     char* const stage = reinterpret_cast<char*>(smem) + warp * StageT<HEAT_STAGE>::kWarpBytes;
     stage_init<HEAT_STAGE>(stage, lane);
+    const bool cached = tile_cache_load<HEAT_STAGE>(stage, plan, s_beg, s_end, lane);
     for (int dc = d0; dc < d1; dc += HEAT_STAGE) {
       const int n = min(HEAT_STAGE, d1 - dc);
       for (int k = 0; k < n; ++k) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
         stage_store1<HEAT_STAGE>(stage, lane, k, v);
       }
       __syncwarp();
-      staged_reduce<HEAT_STAGE>(stage, plan, s_beg, s_end, out, dc, n, lane);
+      staged_reduce<HEAT_STAGE>(stage, plan, s_beg, s_end, out, dc, n, lane, cached);
       __syncwarp();
     }
     return;

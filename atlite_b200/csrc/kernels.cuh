@@ -129,13 +129,18 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 // shared-memory pass read CONSECUTIVE entries of the slot's list, which is sorted by stage
 // index -- neighbouring cells, i.e. the bank pairs in between: conflict-free for the usual
 // contiguous slot, never worse than 2-way.
+constexpr int ENT_CAP = 256;  // entries of the warp's tile kept in shared memory (8 B each)
+constexpr int SLOT_CAP = 24;  // slot records of the warp's tile kept in shared memory (16 B each)
 template <int TS>
 struct StageT {
   static constexpr int kRows = TS / 2;
   static constexpr int kShift = 16 / kRows > 0 ? 16 / kRows : 1;
   static constexpr int kRowBytes = TILE_CELLS * 8 + 8 * kShift;
-  static constexpr int kWarpBytes = kRows * kRowBytes;
+  static constexpr int kEntOff = kRows * kRowBytes;          // entry cache (16-byte aligned)
+  static constexpr int kSlotOff = kEntOff + ENT_CAP * 8;     // slot-record cache
+  static constexpr int kWarpBytes = kSlotOff + SLOT_CAP * 16;
   static constexpr int kCtaBytes = WARPS_PER_CTA * kWarpBytes;
+  static_assert(kEntOff % 16 == 0, "entry cache must be 16-byte aligned");
 };
 __host__ __device__ constexpr int smem_table_bytes(int floats) { return (floats * 4 + 15) & ~15; }
 
@@ -166,6 +171,32 @@ __device__ __forceinline__ void stage_store2(char* stage, int lane, int k_even, 
   for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(w + 256 * i) = make_float2(v0[i], v1[i]);
 }
 
+// A warp keeps its tile for many chunks, so the tile's slot records {first entry, entry count /
+// PAIR_PAD, bus} and entry lists are copied into shared memory once (they are contiguous in the
+// plan): the reduce phase then depends on shared-memory latency only, not on whether L1 / L2
+// still hold the lists.  Tiles with more than SLOT_CAP slots or ENT_CAP entries (rare: the
+// average is 4 slots / 160 entries) keep reading the plan from global memory.
+template <int TS>
+__device__ __forceinline__ bool tile_cache_load(char* stage, const PlanDev& plan, int s_beg, int s_end,
+                                                int lane) {
+  using Stage = StageT<TS>;
+  const int K = s_end - s_beg;
+  if (K <= 0 || K > SLOT_CAP) return false;
+  const int base = __ldg(plan.slot_rec + s_beg).x;
+  const int2 last = __ldg(plan.slot_rec + s_end - 1);
+  const int total = last.x + last.y * PAIR_PAD - base;
+  if (total > ENT_CAP) return false;
+  int4* const slots = reinterpret_cast<int4*>(stage + Stage::kSlotOff);
+  uint2* const ent = reinterpret_cast<uint2*>(stage + Stage::kEntOff);
+  if (lane < K) {
+    const int2 r = __ldg(plan.slot_rec + s_beg + lane);
+    slots[lane] = make_int4(r.x - base, r.y, __ldg(plan.slot_row + s_beg + lane), 0);
+  }
+  const uint2* const src = reinterpret_cast<const uint2*>(plan.pairs) + base;
+  for (int i = lane; i < total; i += 32) ent[i] = __ldg(src + i);
+  return true;
+}
+
 // The reduce phase of one chunk: rows [row0, row0 + nvalid) of `out` receive the sums of the
 // staged steps.  Lane = group * R + row: lane (q, r) owns the step pair r and walks the
 // entries q, q + NQ, q + 2 NQ, ... of every slot's list; one butterfly over the groups, then
@@ -173,7 +204,8 @@ __device__ __forceinline__ void stage_store2(char* stage, int lane, int k_even, 
 // (__syncwarp() before -- the stores of all lanes must be visible -- and after.)
 template <int TS>
 __device__ __forceinline__ void staged_reduce(const char* stage, const PlanDev& plan, int s_beg, int s_end,
-                                              float* __restrict__ out, int row0, int nvalid, int lane) {
+                                              float* __restrict__ out, int row0, int nvalid, int lane,
+                                              bool cached) {
   static_assert(TS == 8 || TS == 16 || TS == 32, "TS/2 rows must divide the warp");
   using Stage = StageT<TS>;
   constexpr int R = TS / 2;   // rows = lanes along time
@@ -182,11 +214,43 @@ __device__ __forceinline__ void staged_reduce(const char* stage, const PlanDev& 
   static_assert(U >= 1 && U * NQ == PAIR_PAD, "PAIR_PAD must be a multiple of the group count");
   const int rp = lane & (R - 1), q = lane / R;
   const char* const rd_row = stage + rp * Stage::kRowBytes;
-  const uint2* const pairs_q = reinterpret_cast<const uint2*>(plan.pairs) + q;
   const int nb = plan.n_bus;
   const int odd = lane >= R ? 1 : 0;
   float* const o_mine = out + (size_t)(row0 + 2 * rp + odd) * nb;
   const bool w_mine = lane < 2 * R && 2 * rp + odd < nvalid;
+  auto finish = [&](float a0, float a1, int row) {
+#pragma unroll
+    for (int o = R; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (w_mine) atomicAdd(o_mine + row, odd ? a1 : a0);
+  };
+  if (cached) {
+    const int4* const slots = reinterpret_cast<const int4*>(stage + Stage::kSlotOff);
+    const uint2* const ent_q = reinterpret_cast<const uint2*>(stage + Stage::kEntOff) + q;
+    const int K = s_end - s_beg;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const int4 sr = slots[k];
+      const uint2* p = ent_q + sr.x;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+      for (int it = 0; it < sr.y; ++it, p += PAIR_PAD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint2 pw = p[u * NQ];
+          const float2 x = *reinterpret_cast<const float2*>(rd_row + pw.x);
+          const float w = __uint_as_float(pw.y);
+          a0 = fmaf(w, x.x, a0);
+          a1 = fmaf(w, x.y, a1);
+        }
+      }
+      finish(a0, a1, sr.z);
+    }
+    return;
+  }
+  const uint2* const pairs_q = reinterpret_cast<const uint2*>(plan.pairs) + q;
 #pragma unroll 1
   for (int s = s_beg; s < s_end; ++s) {
     const int2 rec = __ldg(plan.slot_rec + s);
@@ -203,13 +267,7 @@ __device__ __forceinline__ void staged_reduce(const char* stage, const PlanDev& 
         a1 = fmaf(w, x.y, a1);
       }
     }
-#pragma unroll
-    for (int o = R; o < 32; o <<= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    const int row = __ldg(plan.slot_row + s);
-    if (w_mine) atomicAdd(o_mine + row, odd ? a1 : a0);
+    finish(a0, a1, __ldg(plan.slot_row + s));
   }
 }
 
@@ -246,6 +304,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 #pragma unroll
   for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t0 + j, tlast) * S4, r[j]);
   stage_init<TS>(stage, lane);
+  const bool cached = tile_cache_load<TS>(stage, plan, s_beg, s_end, lane);
 
 #pragma unroll 1
   for (int tc = t0; tc < t1; tc += TS) {
@@ -283,7 +342,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
       }
     }
     __syncwarp();
-    staged_reduce<TS>(stage, plan, s_beg, s_end, out, tc, min(TS, t1 - tc), lane);
+    staged_reduce<TS>(stage, plan, s_beg, s_end, out, tc, min(TS, t1 - tc), lane, cached);
     __syncwarp();  // the next chunk's stores must not overtake this chunk's reads
   }
 }
@@ -425,8 +484,6 @@ int launch_staged(const Phys& phys, const AtlPlan* plan, const GridDev& gd, cons
   static bool attr_set[64] = {false};  // per instantiation and device (benign if set twice)
   if (plan->device >= 0 && plan->device < 64 && !attr_set[plan->device]) {
     ATL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ATL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
     attr_set[plan->device] = true;
   }
   kern<<<grid, CTA_THREADS, smem, st>>>(phys, gd, pd, acc, (int)nt, tb);

@@ -375,7 +375,7 @@ def test_no_matrix_modes(ds_full):
     assert_parity(leg.values, pvw.sum(0), 72.0, what="pv legacy sum")
     hd = c.heat_demand(aggregate_time=None)
     hw, labels = O.convert_heat_demand(od, 15.0, 1.0, 0.0, 0.0)
-    assert_parity(hd.values, hw, 50.0, what="heat cells")
+    assert_parity(hd.values, hw, 50.0, what="heat cells", unit=300.0)  # differences of ~288 K float32 values
     assert_parity(c.heat_demand(aggregate_time="sum").values, hw.sum(0), 150.0, what="heat sum")
 
 
@@ -678,7 +678,7 @@ def test_per_cell_mean_skips_nan_steps_like_the_reference():
     got = np.asarray(ab.Cutout(data=dt).heat_demand(aggregate_time="mean").values)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        assert_parity(got, np.nanmean(hw, axis=0), 50.0, what="heat nanmean")
+        assert_parity(got, np.nanmean(hw, axis=0), 50.0, what="heat nanmean", unit=300.0)
 
 
 def test_orientation_callback_returning_yx_arrays(ds_full, shapes):
@@ -876,7 +876,7 @@ def test_north_star_1440x720_3000_shapes_vs_oracle_windows():
         assert_parity(pv_cube[:, ys, xs], O.convert_pv(od, panel, orient), what="pv north-star window")
         assert_parity(w_cube[:, ys, xs], O.convert_wind(od, turb), what="wind north-star window")
         assert_parity(h_cube[:, ys, xs], O.convert_heat_demand(od, 15.0, 1.0, 0.0, 0.0)[0], 50.0,
-                      what="heat north-star window")
+                      what="heat north-star window", unit=300.0)
     assert (pv_cube > 0).any() and (pv_cube == 0).any()
     del pv_cube, w_cube, h_cube
     # ---- (b) whole buses of the fused (physics + shape reduce) results

@@ -26,13 +26,22 @@ from atlite_b200.dist import shard_bounds  # noqa: E402
 
 warnings.simplefilter("ignore")
 ap = argparse.ArgumentParser()
-ap.add_argument("--steps-per-gpu", type=int, default=365)
+ap.add_argument("--steps-per-gpu", type=int, default=240)
 ap.add_argument("--kind", default="pv")
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
 
 NX, NY, NBUS = 1440, 720, 3000
 ndev = torch.cuda.device_count()
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import _host_limits  # noqa: E402  (cgroup-aware host memory)
+
+_, host_avail = _host_limits()
+per_step = NX * NY * 4 * (5 if args.kind == "pv" else 2)
+# the pageable source and its pinned copy both live in host memory: stay below 40 % of what the
+# container may use
+args.steps_per_gpu = int(min(args.steps_per_gpu, 0.4 * host_avail / (2 * per_step * ndev)))
+assert args.steps_per_gpu >= 24, "not enough host memory for this measurement"
 nt = args.steps_per_gpu * ndev
 x, y = syn.make_coords(NX, NY, -180.0, -90.0)
 tm = syn.make_time(nt + 24 * 150)[24 * 150:]
