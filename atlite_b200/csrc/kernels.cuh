@@ -313,27 +313,23 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
     for (int k = 0; k < TS; k += B) {
       const int t = tc + k;
       if (t >= t1) break;
+      // rolling pipeline over the B register sets: as soon as a step has been evaluated, its raw
+      // registers are re-loaded with step t + B, so every load has B - 1 steps of arithmetic (and
+      // the other warps) between issue and first use; across a chunk boundary it additionally
+      // flies through the whole reduce phase
 #pragma unroll
       for (int j = 0; j < B; ++j) {
         phys.compute(c, g, min(t + j, tlast), r[j], v[j], smem);
         zero_invalid(g, v[j]);
-      }
-      if constexpr (Phys::kHasExact) {
-        float chk = 0.f;
-#pragma unroll
-        for (int j = 0; j < B; ++j) chk += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
-        if (__any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f))) {  // cold: a NaN/Inf reached a result
-#pragma unroll
-          for (int j = 0; j < B; ++j) {
+        if constexpr (Phys::kHasExact) {
+          const float chk = (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+          if (__any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f))) {  // cold: a NaN/Inf reached a result
             phys.compute_exact(c, g, min(t + j, tlast), r[j], v[j], smem);
             zero_invalid(g, v[j]);
           }
         }
+        phys.load(c, g, (int64_t)min(t + B + j, tlast) * S4, r[j]);
       }
-      // the loads of the NEXT batch (possibly the next chunk's first) go out now: they are in
-      // flight across the stores below and the whole reduce phase
-#pragma unroll
-      for (int j = 0; j < B; ++j) phys.load(c, g, (int64_t)min(t + B + j, tlast) * S4, r[j]);
       if (B == 1) {
         stage_store1<TS>(stage, lane, k, v[0]);
       } else {

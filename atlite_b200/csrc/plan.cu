@@ -120,7 +120,7 @@ struct IdentityPhys {
   static constexpr int kSmemFloats = 0;
   static constexpr int kBatch = 4, kMinBlocks = 6;
   static constexpr bool kHasExact = false;
-  static constexpr int kStage = 16;
+  static constexpr int kStage = 8;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const { load4(f, tb, g, r.v); }

@@ -86,7 +86,7 @@ struct PvPhys {
   // non-finite result, for which compute_exact() applies the reference's NaN rules
   // (pv/irradiation.py:198-200 NaN-preserving clip, :226 per-term fillna(0))
   static constexpr bool kHasExact = true;
-  static constexpr int kStage = 16;
+  static constexpr int kStage = 8;   // 6.6 KB per warp: occupancy stays register-bound (5 CTAs)
   __device__ void stage(float*) const {}
 
   __device__ void init(Cell& c, const Geom& g, const float*) const {

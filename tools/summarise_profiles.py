@@ -63,17 +63,20 @@ def full(rep):
 
 
 if __name__ == "__main__":
-    SUF = sys.argv[2] if len(sys.argv) > 2 else "r1"
-    src = f"gpurun_out/launches_bench_{SUF}.csv" if len(sys.argv) > 2 else "gpurun_out/launches_bench.csv"
-    for ln in launches(src, f"profiles/{TAG}_launches_bench.csv")[:10]:
-        print(ln)
+    import glob
+    import os
+
+    SUF = sys.argv[2] if len(sys.argv) > 2 else TAG
+    src = f"gpurun_out/launches_bench_{SUF}.csv"
+    if os.path.exists(src):
+        for ln in launches(src, f"profiles/{TAG}_launches_bench.csv")[:10]:
+            print(ln)
     summ = {}
-    for tag, rep in (("pv_200x200x8760_100shapes", f"gpurun_out/prof_pv_small_{SUF}.ncu-rep"),
-                     ("pv_1440x720x432_3000shapes", f"gpurun_out/prof_pv_big_{SUF}.ncu-rep"),
-                     ("wind_200x200x8760_100shapes", f"gpurun_out/prof_wind_small_{SUF}.ncu-rep"),
-                     ("heat_200x200x8760_100shapes", f"gpurun_out/prof_heat_small_{SUF}.ncu-rep")):
+    names = {"small": "200x200x8760_100shapes", "big": "1440x720x432_3000shapes"}
+    for rep in sorted(glob.glob(f"gpurun_out/prof_*_{SUF}.ncu-rep")):
+        kind, size = os.path.basename(rep).split("_")[1:3]
         try:
-            summ[tag] = full(rep)
+            summ[f"{kind}_{names.get(size, size)}"] = full(rep)
         except Exception as e:  # noqa: BLE001
             print("skip", rep, e)
     json.dump(summ, open(f"profiles/{TAG}_ncu_full_summary.json", "w"), indent=1)
@@ -81,6 +84,7 @@ if __name__ == "__main__":
         print("==", tag, s["Kernel Name"][0][:70])
         for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
                   "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-                  "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):
-            print("  ", k, s[k])
+                  "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+                  "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"):
+            print("  ", k, s.get(k))
         print("   stalls", s["top_stalls_warps_per_issue"])
