@@ -180,6 +180,7 @@ _SIGNATURES = {
     "atl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "atl_launch_count": (C.c_int64, []),
     "atl_set_deterministic": (C.c_int, [C.c_int]),
+    "atl_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "atl_device_local_cpus": (C.c_int, [C.c_int, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "atl_plan_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "atl_plan_create_pitched": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
@@ -272,6 +273,11 @@ def check(rc):
 def set_deterministic(on=True):
     """Bitwise-repeatable fused reductions (fixed summation order); returns the previous setting."""
     return bool(load().atl_set_deterministic(1 if on else 0))
+
+
+def set_tuning(variant=0, tb=0):
+    """Select the fused kernel variant (see atl_set_tuning in include/atlite_b200.h)."""
+    check(load().atl_set_tuning(int(variant), int(tb)))
 
 
 def release_host_staging():

@@ -19,7 +19,9 @@
 //        when an INPUT is NaN/Inf but then always yields a non-finite value, and
 //        compute_exact(...) (same signature) reproduces the reference's NaN rules; the
 //        kernels call it only for steps whose fast result came out non-finite
-//   static constexpr int kStage;  time steps a warp stages before one reduce phase
+//   static constexpr bool kStaged; int kStage, kBatchStaged, kMinBlocksStaged;  which fused kernel
+//        serves this physics by default (staged reduce or shuffle reduce), the chunk length and
+//        batch / occupancy parameters of the staged kernel
 // `t` is relative to the slab the functor's field pointers address.
 //
 // Loop structure: a warp owns one 32x4 tile and walks a block of `tb`
@@ -80,6 +82,18 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
         phys.compute(c, g, t + j, r[j], v[j], smem);
         zero_invalid(g, v[j]);
       }
+      if constexpr (Phys::kHasExact) {  // cold: a NaN/Inf reached a result -> the reference's NaN rules
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < B; ++j) chk += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+        if (__any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f))) {
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
+            phys.compute_exact(c, g, t + j, r[j], v[j], smem);
+            zero_invalid(g, v[j]);
+          }
+        }
+      }
       if (k + 1 < nfull) {
 #pragma unroll
         for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
@@ -101,6 +115,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
     phys.load(c, g, sb, r[0]);
     phys.compute(c, g, t, r[0], v[0], smem);
     zero_invalid(g, v[0]);
+    if constexpr (Phys::kHasExact) {
+      if (__any_sync(0xffffffffu, !(fabsf((v[0][0] + v[0][1]) + (v[0][2] + v[0][3])) <= 3.0e38f))) {
+        phys.compute_exact(c, g, t, r[0], v[0], smem);
+        zero_invalid(g, v[0]);
+      }
+    }
     reduce_slots(v[0], s_beg, s_end, plan, out + (size_t)t * nb, lane);
   }
 }
@@ -230,12 +250,66 @@ __device__ __forceinline__ void staged_reduce(const char* stage, const PlanDev& 
     const int4* const slots = reinterpret_cast<const int4*>(stage + Stage::kSlotOff);
     const uint2* const ent_q = reinterpret_cast<const uint2*>(stage + Stage::kEntOff) + q;
     const int K = s_end - s_beg;
+    // two slots at a time: their load -> load -> FMA chains are independent, which halves the
+    // latency a warp spends in this phase (the phase is latency-, not issue-bound)
+    int k = 0;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (; k + 1 < K; k += 2) {
+      const int4 sa = slots[k], sb = slots[k + 1];
+      const uint2 *pa = ent_q + sa.x, *pb = ent_q + sb.x;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      const int nmin = min(sa.y, sb.y);
+      int it = 0;
+#pragma unroll 2
+      for (; it < nmin; ++it, pa += PAIR_PAD, pb += PAIR_PAD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint2 wa = pa[u * NQ], wb = pb[u * NQ];
+          const float2 xa = *reinterpret_cast<const float2*>(rd_row + wa.x);
+          const float2 xb = *reinterpret_cast<const float2*>(rd_row + wb.x);
+          a0 = fmaf(__uint_as_float(wa.y), xa.x, a0);
+          a1 = fmaf(__uint_as_float(wa.y), xa.y, a1);
+          b0 = fmaf(__uint_as_float(wb.y), xb.x, b0);
+          b1 = fmaf(__uint_as_float(wb.y), xb.y, b1);
+        }
+      }
+#pragma unroll 2
+      for (int ia = it; ia < sa.y; ++ia, pa += PAIR_PAD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint2 wa = pa[u * NQ];
+          const float2 xa = *reinterpret_cast<const float2*>(rd_row + wa.x);
+          a0 = fmaf(__uint_as_float(wa.y), xa.x, a0);
+          a1 = fmaf(__uint_as_float(wa.y), xa.y, a1);
+        }
+      }
+#pragma unroll 2
+      for (int ib = it; ib < sb.y; ++ib, pb += PAIR_PAD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint2 wb = pb[u * NQ];
+          const float2 xb = *reinterpret_cast<const float2*>(rd_row + wb.x);
+          b0 = fmaf(__uint_as_float(wb.y), xb.x, b0);
+          b1 = fmaf(__uint_as_float(wb.y), xb.y, b1);
+        }
+      }
+#pragma unroll
+      for (int o = R; o < 32; o <<= 1) {  // both butterflies interleaved
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+      }
+      if (w_mine) {
+        atomicAdd(o_mine + sa.z, odd ? a1 : a0);
+        atomicAdd(o_mine + sb.z, odd ? b1 : b0);
+      }
+    }
+    if (k < K) {
       const int4 sr = slots[k];
       const uint2* p = ent_q + sr.x;
       float a0 = 0.f, a1 = 0.f;
-#pragma unroll 2
+#pragma unroll 4
       for (int it = 0; it < sr.y; ++it, p += PAIR_PAD) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -476,7 +550,7 @@ int launch_staged(const Phys& phys, const AtlPlan* plan, const GridDev& gd, cons
   tb = ((tb + TS - 1) / TS) * TS;  // whole chunks per time block
   dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
   const size_t smem = smem_table_bytes(Phys::kSmemFloats) + StageT<TS>::kCtaBytes;
-  auto kern = k_fused_reduce<Phys, Phys::kBatch, Phys::kMinBlocks, TS>;
+  auto kern = k_fused_reduce<Phys, Phys::kBatchStaged, Phys::kMinBlocksStaged, TS>;
   static bool attr_set[64] = {false};  // per instantiation and device (benign if set twice)
   if (plan->device >= 0 && plan->device < 64 && !attr_set[plan->device]) {
     ATL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -506,11 +580,14 @@ int launch_fused(const Phys& phys, const AtlPlan* plan, float* out, int64_t nt, 
   int tb = tuning().tb > 0 ? tuning().tb : pick_tb(gx, nt);
   const GridDev gd = plan->grid;
   const int variant = tuning().variant;
-  if (variant == 1) {  // round-1 kernel (shuffle reduce against dense weight vectors), kept for A/B
+  // ATL_VARIANT: 0 = the functor's own choice (Phys::kStaged), 1 = shuffle reduce against dense
+  // weight vectors, 2 = staged reduce (chunk Phys::kStage), 3 = staged reduce, the other chunk length
+  const bool staged = variant == 0 ? Phys::kStaged : variant != 1;
+  if (!staged) {
     dim3 grid(gx, (unsigned)((nt + tb - 1) / tb));
     k_fused_reduce_v1<Phys, Phys::kBatch, Phys::kMinBlocks, 1>
         <<<grid, CTA_THREADS, Phys::kSmemFloats * sizeof(float), st>>>(phys, gd, pd, acc, (int)nt, tb);
-  } else if (variant == 2) {  // the other chunk length (A/B)
+  } else if (variant == 3) {
     int rc = launch_staged<Phys, (Phys::kStage == 16 ? 8 : 16)>(phys, plan, gd, pd, acc, nt, tb, gx, st);
     if (rc) return rc;
   } else {

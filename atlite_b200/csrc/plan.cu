@@ -58,7 +58,7 @@ int launch_gather_slots(const AtlPlan* plan, const float* partial, int64_t nt, f
   return ATL_OK;
 }
 
-const Tuning& tuning() {
+static Tuning& tuning_mut() {
   static Tuning t = [] {
     Tuning x;
     if (const char* v = getenv("ATL_VARIANT")) x.variant = atoi(v);
@@ -67,6 +67,7 @@ const Tuning& tuning() {
   }();
   return t;
 }
+const Tuning& tuning() { return tuning_mut(); }
 
 void set_error(const std::string& msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -120,7 +121,8 @@ struct IdentityPhys {
   static constexpr int kSmemFloats = 0;
   static constexpr int kBatch = 4, kMinBlocks = 6;
   static constexpr bool kHasExact = false;
-  static constexpr int kStage = 8;
+  static constexpr bool kStaged = false;
+  static constexpr int kStage = 8, kBatchStaged = kBatch, kMinBlocksStaged = kMinBlocks;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const { load4(f, tb, g, r.v); }
@@ -142,6 +144,12 @@ int atl_set_deterministic(int on) {
   const int prev = g_deterministic ? 1 : 0;
   g_deterministic = on != 0;
   return prev;
+}
+int atl_set_tuning(int variant, int tb) {
+  ATL_REQUIRE(variant >= 0 && variant <= 3 && tb >= 0, "variant must be 0..3, tb >= 0");
+  tuning_mut().variant = variant;
+  tuning_mut().tb = tb;
+  return ATL_OK;
 }
 const char* atl_last_error(void) { return g_err.c_str(); }
 int64_t atl_launch_count(void) { return g_launches; }

@@ -86,7 +86,11 @@ struct PvPhys {
   // non-finite result, for which compute_exact() applies the reference's NaN rules
   // (pv/irradiation.py:198-200 NaN-preserving clip, :226 per-term fillna(0))
   static constexpr bool kHasExact = true;
-  static constexpr int kStage = 8;   // 6.6 KB per warp: occupancy stays register-bound (5 CTAs)
+  // measured (profiles/r2_variants.jsonl): the shuffle reduce streams PV at 0.98-1.03 of the
+  // HBM peak, the staged reduce at 0.80-0.91 (fewer instructions, but its two-phase structure
+  // exposes more latency at 20 warps per SM)
+  static constexpr bool kStaged = false;
+  static constexpr int kStage = 8, kBatchStaged = kBatch, kMinBlocksStaged = kMinBlocks;
   __device__ void stage(float*) const {}
 
   __device__ void init(Cell& c, const Geom& g, const float*) const {

@@ -114,9 +114,10 @@ struct WindPhys {
   // general LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; lattice:
   // <= 130 x 16 or <= 258 x 4 replicas, 2 floats each; fallback: 256 + 4*257
   static constexpr int kSmemFloats = 2 * 130 * 16;
-  static constexpr int kBatch = 4, kMinBlocks = 5;  // 4 register sets in the rolling load pipeline
+  static constexpr int kBatch = 2, kMinBlocks = 6;
   static constexpr bool kHasExact = false;  // NaN speeds / roughness propagate like np.interp's
-  static constexpr int kStage = 8;          // 16.5 KB of staging + the 16.6 KB table: 6 CTAs per SM
+  static constexpr bool kStaged = false;
+  static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)
 
   __device__ void stage(float* smem) const {
     for (int i = threadIdx.x; i < n_stage; i += blockDim.x) smem[i] = curve[i];

@@ -71,6 +71,12 @@ int atl_device_count(int* count_out);
  * kernel sums each bus's slots in a fixed order -> bitwise-repeatable results at
  * ~2 % extra traffic.  Returns the previous setting. */
 int atl_set_deterministic(int on);
+/* Which fused kernel serves the *_reduce entry points (default 0, or env ATL_VARIANT / ATL_TB):
+ * 0 = each operator's measured best, 1 = shuffle reduce against dense per-slot weight vectors,
+ * 2 = staged reduce over the per-slot entry lists (8-step chunks), 3 = the same with 16-step
+ * chunks; tb = time steps per thread block (0 = automatic).  Results are the same up to
+ * float32 summation order. */
+int atl_set_tuning(int variant, int tb);
 /* CPUs the kernel lists as local to the GPU's PCI device (its NUMA node): host-streaming
  * calls bind their staging threads there for the duration of the call (ATL_NUMA_BIND=0
  * disables).  Fills up to `capacity` CPU ids, *n_out = how many there are (0 = unknown). */
