@@ -168,6 +168,9 @@ def _gloo_worker(rank, world, port, q):
         plane = np.full((3, 4), float(rank + 1), dtype=np.float32)
         tot, n = TimeShard().sum_over_ranks(plane, 10 * (rank + 1))
         assert np.allclose(tot.numpy(), sum(range(1, world + 1))) and n == 10 * sum(range(1, world + 1))
+        # (sum, valid-step count) planes of a time-aggregated per-cell output: one all-reduce
+        tot, cnt = TimeShard().sum_planes(plane, np.full((3, 4), 5.0 * (rank + 1), dtype=np.float32))
+        assert np.allclose(tot.numpy(), sum(range(1, world + 1))) and np.allclose(cnt.numpy(), 5 * sum(range(1, world + 1)))
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))
