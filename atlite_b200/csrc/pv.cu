@@ -38,14 +38,6 @@ enum {  // panel coefficient slots (float, device)
 // influx_diffuse + albedo variables, simple trigon model, Huld panel.
 // FAST=false keeps every switch at run time (stored solar position, Reindl
 // split, outflux albedo, tracking modes, Hay-Davies, Bofinger).
-// cold path of the simple trigon model: total_t with every NaN term replaced by 0
-// (pv/irradiation.py:226).  Out of line on purpose: a call is never if-converted into
-// predicated instructions that would occupy issue slots of the hot loop.
-static __device__ __noinline__ float total_fillna(float direct_t, float diffuse_t, float ground_t) {
-  return ((direct_t == direct_t) ? direct_t : 0.f) + ((diffuse_t == diffuse_t) ? diffuse_t : 0.f) +
-         ((ground_t == ground_t) ? ground_t : 0.f);
-}
-
 template <bool FAST, bool VEC>
 struct PvPhys {
   static constexpr bool kVec = VEC;
@@ -90,10 +82,13 @@ struct PvPhys {
   };
   static constexpr int kSmemFloats = 0;
   static constexpr int kBatch = FAST ? 2 : 1, kMinBlocks = FAST ? 5 : 4;
-  // NaN inputs follow the reference inside compute(): NaN-preserving clips
-  // (pv/irradiation.py:198-200) and, on a cold out-of-line path, the per-term fillna(0) of the
-  // simple trigon model (:226)
-  static constexpr bool kHasExact = false;
+  // compute() is the reference's arithmetic for finite inputs, straight-line code (no per-cell
+  // branches: they would split the 4-cell basic block and cost ~7 % of PV's throughput);
+  // NaN-preserving clips (pv/irradiation.py:198-200) make a NaN input always surface as a
+  // non-finite result.  The kernels test the RESULTS of a step and only then call
+  // compute_exact(), out of line, which adds the per-term fillna(0) of the simple trigon model
+  // (:226) and keeps Bofinger / solar-thermal NaNs from being masked by their `where`s.
+  static constexpr bool kHasExact = true;
   // measured (profiles/r2_variants.jsonl): the shuffle reduce streams PV at 0.98-1.03 of the
   // HBM peak, the staged reduce at 0.80-0.91 (fewer instructions, but its two-phase structure
   // exposes more latency at 20 warps per SM)
@@ -164,7 +159,17 @@ struct PvPhys {
   }
 
   __device__ __forceinline__ void compute(const Cell& c, const Geom& g, int t, const Raw& r, float (&v)[4],
-                                          const float*) const {
+                                          const float* sm) const {
+    compute_impl<false>(c, g, t, r, v, sm);
+  }
+  __device__ __noinline__ void compute_exact(const Cell& c, const Geom& g, int t, const Raw& r,
+                                             float (&v)[4], const float* sm) const {
+    compute_impl<true>(c, g, t, r, v, sm);
+  }
+
+  template <bool EXACT>
+  __device__ __forceinline__ void compute_impl(const Cell& c, const Geom& g, int t, const Raw& r,
+                                               float (&v)[4], const float*) const {
     float sd = 0.f, cd = 0.f, ch[NXC], sh[NXC];
     if (solar_src() == ATL_SOLAR_COMPUTED) {
       const float4 q = __ldg(tt + t_off + t);
@@ -308,11 +313,12 @@ struct PvPhys {
       else if (out == ATL_OUT_DIFFUSE) total = diffuse_t;
       else if (out == ATL_OUT_GROUND) total = ground_t;
       else if (trigon() == ATL_TRIGON_SIMPLE) {
-        // one FMA chain on the hot path; a NaN in any term (NaN input, 0 * inf) makes it NaN and
-        // only then the reference's direct_t.fillna(0) + diffuse_t.fillna(0) + ground_t.fillna(0)
-        // (:226) is evaluated, out of line
-        total = fmaf(Rb, direct, fmaf(fmaf(0.5f, cslope, 0.5f), diffuse, ground_t));
-        if (total != total) total = total_fillna(direct_t, diffuse_t, ground_t);
+        if (EXACT) {  // direct_t.fillna(0) + diffuse_t.fillna(0) + ground_t.fillna(0)   (:226)
+          total = ((direct_t == direct_t) ? direct_t : 0.f) + ((diffuse_t == diffuse_t) ? diffuse_t : 0.f) +
+                  ((ground_t == ground_t) ? ground_t : 0.f);
+        } else {  // one FMA chain on the hot path; NaN in any term -> NaN -> compute_exact
+          total = fmaf(Rb, direct, fmaf(fmaf(0.5f, cslope, 0.5f), diffuse, ground_t));
+        }
       } else
         total = fmaf(Rb, direct, diffuse_t) + ground_t;
       // computed mode: alt < thr  <=>  sin(alt) < sin(thr) on [-pi/2, pi/2];
@@ -323,7 +329,11 @@ struct PvPhys {
                                                            : (r.salt[i] < alt_thr);
       const bool keep_it = !low & !(influx_ <= 0.01f);
       const float G = keep_it ? total : 0.f;
-      if (out == ATL_OUT_PANEL) {
+      if (!EXACT && !FAST && G != G) {
+        // a NaN irradiance must SURFACE (Bofinger's threshold and the solar-thermal `where`
+        // would turn it into a finite 0): the kernels then re-evaluate with compute_exact
+        v[i] = G;
+      } else if (out == ATL_OUT_PANEL) {
         v[i] = panel(G, r.temp[i]);
       } else if (out == ATL_OUT_SOLAR_THERMAL) {
         // eta = c0 - c1 * ((t_store - T) / irr.where(irr != 0)).fillna(0); output.where(> 0, 0)

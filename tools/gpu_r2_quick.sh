@@ -7,5 +7,6 @@ cp gpurun_out/parity_errors.json gpurun_out/parity_errors_$TAG.json 2>/dev/null
 for v in 0 2; do for k in wind pv heat; do for s in small big; do
   ATL_VARIANT=$v timeout 120 python tools/prof_pv.py $k $s 7
 done; done; done > gpurun_out/prof_$TAG.jsonl 2>gpurun_out/prof_$TAG.err
+for k in pvsum pvcube windsum; do timeout 120 python tools/prof_pv.py $k c5 7; done >> gpurun_out/prof_$TAG.jsonl 2>>gpurun_out/prof_$TAG.err
 grep -E "passed|failed" gpurun_out/pytest_full_$TAG.log | tail -3; grep -E "^FAILED|^ERROR" gpurun_out/pytest_full_$TAG.log | head
 cat gpurun_out/prof_$TAG.jsonl; tail -3 gpurun_out/prof_$TAG.err
