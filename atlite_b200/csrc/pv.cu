@@ -162,9 +162,19 @@ struct PvPhys {
                                           const float* sm) const {
     compute_impl<false>(c, g, t, r, v, sm);
   }
-  __device__ __noinline__ void compute_exact(const Cell& c, const Geom& g, int t, const Raw& r,
-                                             float (&v)[4], const float* sm) const {
-    compute_impl<true>(c, g, t, r, v, sm);
+  // Out of line, and every argument BY VALUE (copied to the call's parameter area on the cold
+  // path only): taking references here would pin Cell / Raw / the functor in local memory for
+  // the whole kernel and halve the hot path's throughput (measured: profiles/r2_variants*.jsonl).
+  static __device__ __noinline__ float4 exact_by_value(const PvPhys self, const Cell c, const Geom g, int t,
+                                                       const Raw r) {
+    float v[4];
+    self.template compute_impl<true>(c, g, t, r, v, nullptr);
+    return make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ __forceinline__ void compute_exact(const Cell& c, const Geom& g, int t, const Raw& r,
+                                                float (&v)[4], const float*) const {
+    const float4 o = exact_by_value(*this, c, g, t, r);
+    v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
   }
 
   template <bool EXACT>
