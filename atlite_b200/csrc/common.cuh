@@ -373,10 +373,14 @@ __device__ __forceinline__ void reduce_slots2(const float (&v0)[4], const float 
 __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float (&v1)[4],
                                                int s_beg, int s_end, const PlanDev& plan,
                                                float* __restrict__ out_row0, int lane) {
-  // No probe of the inputs: a NaN/Inf cell makes every sum it takes part in non-finite (also
-  // through a zero weight, 0 * NaN), so the finished sums of a group are tested instead -- one
-  // compare + vote per group -- and only then the group is redone on the exact path, which
-  // multiplies stored entries only (scipy CSR semantics).
+  const float chk = ((v0[0] + v0[1]) + (v0[2] + v0[3])) + ((v1[0] + v1[1]) + (v1[2] + v1[3]));
+  const bool bad = !(fabsf(chk) <= 3.0e38f);
+  if (__any_sync(0xffffffffu, bad)) {
+    reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s_beg, s_end, plan, out_row0, lane);
+    reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s_beg, s_end, plan, out_row0 + plan.n_bus,
+                       lane);
+    return;
+  }
   const bool hi = lane >= 16;
   float* const my_row = out_row0 + (hi ? plan.n_bus : 0);
   float vk[4], vs[4];  // the step this half-warp keeps / sends
@@ -405,14 +409,7 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
     a[0] += __shfl_xor_sync(0xffffffffu, a[1], 4);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-    const bool mine = s + f < s_end;
-    if (__any_sync(0xffffffffu, mine && !(fabsf(a[0]) <= 3.0e38f))) {  // cold
-      const int e = s + 4 < s_end ? s + 4 : s_end;
-      reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s, e, plan, out_row0, lane);
-      reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s, e, plan, out_row0 + plan.n_bus, lane);
-      continue;
-    }
-    if ((lane & 3) == 0 && mine) atomicAdd(my_row + __ldg(rp), a[0]);
+    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(rp), a[0]);
   }
   if (s < s_end) {  // one slot left
     const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
@@ -421,11 +418,6 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
     keep += __shfl_xor_sync(0xffffffffu, send, 16);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-    if (__any_sync(0xffffffffu, !(fabsf(keep) <= 3.0e38f))) {  // cold
-      reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s, s_end, plan, out_row0, lane);
-      reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s, s_end, plan, out_row0 + plan.n_bus, lane);
-      return;
-    }
     if ((lane & 15) == 0) atomicAdd(my_row + __ldg(plan.slot_row + s), keep);
   }
 }
