@@ -370,12 +370,14 @@ __device__ __forceinline__ void reduce_slots2(const float (&v0)[4], const float 
 // belong to the next tile (or the zero padding of the array); their sums live in
 // separate accumulators and are dropped.  A single left-over slot takes the
 // pairwise path.
+// PROBE = false: the caller has already established that no lane holds a NaN/Inf value.
+template <bool PROBE = true>
 __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float (&v1)[4],
                                                int s_beg, int s_end, const PlanDev& plan,
                                                float* __restrict__ out_row0, int lane) {
   const float chk = ((v0[0] + v0[1]) + (v0[2] + v0[3])) + ((v1[0] + v1[1]) + (v1[2] + v1[3]));
   const bool bad = !(fabsf(chk) <= 3.0e38f);
-  if (__any_sync(0xffffffffu, bad)) {
+  if (PROBE && __any_sync(0xffffffffu, bad)) {
     reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s_beg, s_end, plan, out_row0, lane);
     reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s_beg, s_end, plan, out_row0 + plan.n_bus,
                        lane);

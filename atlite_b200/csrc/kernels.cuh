@@ -82,11 +82,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
         phys.compute(c, g, t + j, r[j], v[j], smem);
         zero_invalid(g, v[j]);
       }
-      if constexpr (Phys::kHasExact) {  // cold: a NaN/Inf reached a result -> the reference's NaN rules
+      bool bad = false;  // kHasExact: one probe serves the physics' NaN rules AND the reduce
+      if constexpr (Phys::kHasExact) {
         float chk = 0.f;
 #pragma unroll
         for (int j = 0; j < B; ++j) chk += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
-        if (__any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f))) {
+        bad = __any_sync(0xffffffffu, !(fabsf(chk) <= 3.0e38f));
+        if (bad) {  // cold: a NaN/Inf reached a result -> the reference's NaN rules
 #pragma unroll
           for (int j = 0; j < B; ++j) {
             phys.compute_exact(c, g, t + j, r[j], v[j], smem);
@@ -101,10 +103,19 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
       }
 #pragma unroll
       for (int j = 0; j + 1 < B; j += 2) {
-        if (G)  // slots in groups of four (transposed butterfly)
-          reduce_slots2g(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
-        else
-          reduce_slots2(v[j], v[j + 1], s_beg, s_end, plan, out + (size_t)(t + j) * nb, lane);
+        float* const o = out + (size_t)(t + j) * nb;
+        if constexpr (Phys::kHasExact) {
+          if (bad) {  // cold: what is left non-finite is meant to be; stored entries only
+            reduce_slots_exact(v[j][0], v[j][1], v[j][2], v[j][3], s_beg, s_end, plan, o, lane);
+            reduce_slots_exact(v[j + 1][0], v[j + 1][1], v[j + 1][2], v[j + 1][3], s_beg, s_end, plan, o + nb, lane);
+          } else {
+            reduce_slots2g<false>(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
+          }
+        } else if (G) {  // slots in groups of four (transposed butterfly)
+          reduce_slots2g(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
+        } else {
+          reduce_slots2(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
+        }
       }
       if (B & 1) reduce_slots(v[B - 1], s_beg, s_end, plan, out + (size_t)(t + B - 1) * nb, lane);
     }
