@@ -33,13 +33,23 @@ enum {  // panel coefficient slots (float, device)
   PC_A = 0, PC_B, PC_C, PC_D, PC_FRACTION, PC_TSTD, PC_DEN, PC_SCALE, PC_THRESHOLD
 };
 
-// FAST = the ERA5 default configuration compiled to constants: fixed panel
+// MODE: 0 = every switch at run time (Reindl split, outflux albedo, tracking modes, Hay-Davies,
+// Bofinger, irradiation / solar-thermal outputs, per-cell orientation); 1 / 2 / 3 = the ERA5
+// default configuration compiled to constants with the solar position computed in-kernel (1: the
+// synthetic / pre-2023 cutouts) or read from the cutout as float64 (2: what real ERA5 cutouts
+// store, datasets/era5.py:182-188) / float32 (3).
+// FAST (MODE != 0) = the ERA5 default configuration compiled to constants: fixed panel
 // (tracking None), solar position computed in-kernel, influx_direct +
 // influx_diffuse + albedo variables, simple trigon model, Huld panel.
 // FAST=false keeps every switch at run time (stored solar position, Reindl
 // split, outflux albedo, tracking modes, Hay-Davies, Bofinger).
-template <bool FAST, bool VEC>
+template <int MODE, bool VEC>
 struct PvPhys {
+  static constexpr bool FAST = MODE >= 1 && MODE <= 3;
+  // MODE 4: ERA5 inputs (direct + diffuse influx, albedo variable) and the solar position computed
+  // in-kernel are compiled in, tracking / trigon model / panel / output / per-cell orientation stay
+  // run-time switches: only 5 fields are live per step, so two steps fit in flight
+  static constexpr bool ERA5_INPUTS = FAST || MODE == 4;
   static constexpr bool kVec = VEC;
   using Geom = TileGeomT<VEC>;
   // cell i of a lane -> index into the per-column / per-row constant arrays: the
@@ -67,10 +77,13 @@ struct PvPhys {
   __device__ __forceinline__ int panel_model() const { return FAST ? ATL_PANEL_HULD : panel_model_; }
   __device__ __forceinline__ int output() const { return FAST ? ATL_OUT_PANEL : output_; }
   __device__ __forceinline__ int irr_branch() const {
-    return FAST ? ATL_IRR_DIRECT_DIFFUSE : irr_branch_;
+    return ERA5_INPUTS ? ATL_IRR_DIRECT_DIFFUSE : irr_branch_;
   }
-  __device__ __forceinline__ int albedo_src() const { return FAST ? ATL_ALBEDO_VAR : albedo_src_; }
-  __device__ __forceinline__ int solar_src() const { return FAST ? ATL_SOLAR_COMPUTED : solar_src_; }
+  __device__ __forceinline__ int albedo_src() const { return ERA5_INPUTS ? ATL_ALBEDO_VAR : albedo_src_; }
+  __device__ __forceinline__ int solar_src() const {
+    return (MODE == 1 || MODE == 4) ? ATL_SOLAR_COMPUTED
+           : MODE == 2 ? ATL_SOLAR_STORED_F64 : MODE == 3 ? ATL_SOLAR_STORED_F32 : solar_src_;
+  }
 
   struct Cell {
     float clon[NXC], slon[NXC];
@@ -81,7 +94,9 @@ struct PvPhys {
     float toa[4], a[4], b[4], alb[4], temp[4], hum[4], salt[4], saz[4];
   };
   static constexpr int kSmemFloats = 0;
-  static constexpr int kBatch = FAST ? 2 : 1, kMinBlocks = FAST ? 5 : 4;
+  // two steps in flight whenever the configuration is compiled in; the stored-solar modes carry
+  // 7 fields per step (28 raw registers): 4 CTAs per SM
+  static constexpr int kBatch = MODE != 0 ? 2 : 1, kMinBlocks = MODE == 1 ? 5 : 4;
   // compute() is the reference's arithmetic for finite inputs, straight-line code (no per-cell
   // branches: they would split the 4-cell basic block and cost ~7 % of PV's throughput);
   // NaN-preserving clips (pv/irradiation.py:198-200) make a NaN input always surface as a
@@ -216,8 +231,19 @@ struct PvPhys {
         cosalt = sqrtf(fmaxf(fmaf(-sinalt, sinalt, 1.f), 0.f));
       } else {
         float saz_s, saz_c;
-        sincosf(r.salt[i], &sinalt, &cosalt);
-        sincosf(r.saz[i], &saz_s, &saz_c);
+        if (MODE != 1 && MODE != 4) {  // every stored-solar configuration
+          // altitude in [-pi/2, pi/2], azimuth in [0, 2 pi) brought into (-pi, pi]: inside the range
+          // where the MUFU sine / cosine are good to 2^-21 absolute (4e-7: 2e-5 of sin(1 deg), the
+          // smallest unmasked sin(altitude)); sincosf's full range reduction costs ~100 instructions
+          const float az = r.saz[i] > 3.14159265f ? r.saz[i] - 6.28318531f : r.saz[i];
+          sinalt = __sinf(r.salt[i]);
+          cosalt = __cosf(r.salt[i]);
+          saz_s = __sinf(az);
+          saz_c = __cosf(az);
+        } else {  // (not reached: these modes compute the solar position)
+          sincosf(r.salt[i], &sinalt, &cosalt);
+          sincosf(r.saz[i], &saz_s, &saz_c);
+        }
         X = cosalt * saz_c;
         Y = cosalt * saz_s;
       }
@@ -374,12 +400,12 @@ struct AtlPvOp {
   float2* d_xt = nullptr;
   float* d_yt = nullptr;
   float4* d_ot = nullptr;  // per-cell orientation table (orientation_2d)
-  bool fast;
+  int mode;                // PvPhys MODE
 };
 
-template <bool FAST, bool VEC>
-static PvPhys<FAST, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t0) {
-  PvPhys<FAST, VEC> p;
+template <int MODE, bool VEC>
+static PvPhys<MODE, VEC> make_phys(const AtlPvOp* op, const AtlPvFields* f, int64_t t0) {
+  PvPhys<MODE, VEC> p;
   p.toa = f->influx_toa;
   p.dir = f->influx_direct;
   p.dif = f->influx_diffuse;
@@ -484,10 +510,13 @@ int atl_pv_create(int device, const AtlPvConfig* cfg, AtlPvOp** op_out) {
   op->th_tstore = (float)(cfg->thermal[2] + 273.15);
   op->sin_thr = (float)std::sin(cfg->altitude_threshold_deg * D2R);
   op->alt_thr = (float)(cfg->altitude_threshold_deg * D2R);
-  op->fast = cfg->tracking == ATL_TRACK_NONE && cfg->solar_src == ATL_SOLAR_COMPUTED &&
-             cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR &&
-             cfg->trigon_model == ATL_TRIGON_SIMPLE && cfg->panel_model == ATL_PANEL_HULD &&
-             cfg->output == ATL_OUT_PANEL && !cfg->orientation_2d;
+  const bool era5_default = cfg->tracking == ATL_TRACK_NONE && cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE &&
+                            cfg->albedo_src == ATL_ALBEDO_VAR && cfg->trigon_model == ATL_TRIGON_SIMPLE &&
+                            cfg->panel_model == ATL_PANEL_HULD && cfg->output == ATL_OUT_PANEL &&
+                            !cfg->orientation_2d;
+  const bool era5_inputs = cfg->irr_branch == ATL_IRR_DIRECT_DIFFUSE && cfg->albedo_src == ATL_ALBEDO_VAR;
+  op->mode = era5_default ? (cfg->solar_src == ATL_SOLAR_COMPUTED ? 1 : cfg->solar_src == ATL_SOLAR_STORED_F64 ? 2 : 3)
+             : (era5_inputs && cfg->solar_src == ATL_SOLAR_COMPUTED) ? 4 : 0;
   const double* P = cfg->panel;
   for (int i = 0; i < 12; ++i) op->pc[i] = 0.f;
   if (cfg->panel_model == ATL_PANEL_HULD) {
@@ -599,12 +628,14 @@ int atl_pv_reduce(const AtlPvOp* op, const AtlPlan* plan, const AtlPvFields* f, 
               "plan / operator grid (or pitch) mismatch");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = fields_aligned(f);
-  if (op->fast) {
-    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
-    return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);
+#define ATL_PV_MODE(M)                                                                  \
+  case M: {                                                                             \
+    auto make = [&](auto vec) { return make_phys<M, decltype(vec)::value>(op, f, t0); }; \
+    return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);                                                                          \
   }
-  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
-  return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);
+  switch (op->mode) { ATL_PV_MODE(0) ATL_PV_MODE(1) ATL_PV_MODE(2) ATL_PV_MODE(3) ATL_PV_MODE(4) }
+#undef ATL_PV_MODE
+  return ATL_ERR_INVALID;
 }
 
 int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
@@ -614,12 +645,14 @@ int atl_pv_cells(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = fields_aligned(f);
-  if (op->fast) {
-    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
-    return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);
+#define ATL_PV_MODE(M)                                                                  \
+  case M: {                                                                             \
+    auto make = [&](auto vec) { return make_phys<M, decltype(vec)::value>(op, f, t0); }; \
+    return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);                                                                          \
   }
-  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
-  return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);
+  switch (op->mode) { ATL_PV_MODE(0) ATL_PV_MODE(1) ATL_PV_MODE(2) ATL_PV_MODE(3) ATL_PV_MODE(4) }
+#undef ATL_PV_MODE
+  return ATL_ERR_INVALID;
 }
 
 int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t nt,
@@ -629,12 +662,14 @@ int atl_pv_timesum(const AtlPvOp* op, const AtlPvFields* f, int64_t t0, int64_t 
   ATL_REQUIRE(out_dev, "NULL argument");
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = fields_aligned(f);
-  if (op->fast) {
-    auto make = [&](auto vec) { return make_phys<true, decltype(vec)::value>(op, f, t0); };
-    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);
+#define ATL_PV_MODE(M)                                                                  \
+  case M: {                                                                             \
+    auto make = [&](auto vec) { return make_phys<M, decltype(vec)::value>(op, f, t0); }; \
+    return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);                                                                          \
   }
-  auto make = [&](auto vec) { return make_phys<false, decltype(vec)::value>(op, f, t0); };
-  return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);
+  switch (op->mode) { ATL_PV_MODE(0) ATL_PV_MODE(1) ATL_PV_MODE(2) ATL_PV_MODE(3) ATL_PV_MODE(4) }
+#undef ATL_PV_MODE
+  return ATL_ERR_INVALID;
 }
 
 }  // extern "C"
