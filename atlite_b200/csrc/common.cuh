@@ -386,10 +386,13 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
   const bool hi = lane >= 16;
   float* const my_row = out_row0 + (hi ? plan.n_bus : 0);
   float vk[4], vs[4];  // the step this half-warp keeps / sends
+  float2 ks[4];        // ... as {keep, send} pairs: both dot products of a slot share the weights, so
+                       // one packed FFMA2 (weight broadcast) does what two FFMAs did
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     vk[i] = hi ? v1[i] : v0[i];
     vs[i] = hi ? v0[i] : v1[i];
+    ks[i] = make_float2(vk[i], vs[i]);
   }
   const int f = (lane >> 2) & 3;
   int s = s_beg;
@@ -401,8 +404,12 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 w = __ldg(wp + (f ^ i) * 32);
-      a[i] = fmaf(w.x, vk[0], fmaf(w.y, vk[1], fmaf(w.z, vk[2], w.w * vk[3])));
-      b[i] = fmaf(w.x, vs[0], fmaf(w.y, vs[1], fmaf(w.z, vs[2], w.w * vs[3])));
+      const float2 ab = __ffma2_rn(make_float2(w.x, w.x), ks[0],
+                                   __ffma2_rn(make_float2(w.y, w.y), ks[1],
+                                              __ffma2_rn(make_float2(w.z, w.z), ks[2],
+                                                         __fmul2_rn(make_float2(w.w, w.w), ks[3]))));
+      a[i] = ab.x;
+      b[i] = ab.y;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] += __shfl_xor_sync(0xffffffffu, b[i], 16);

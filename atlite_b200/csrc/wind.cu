@@ -168,16 +168,25 @@ struct WindPhys {
   __device__ void compute(const Cell& c, const Geom&, int, const Raw& r, float (&v)[4],
                           const float* sm) const {
     float x[4];
+    if (METHOD == ATL_WIND_LOG) {
+      // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
+      // (not rewritten as v + v*c/(..): z0 = 0 must give NaN = inf/inf like the reference).
+      // The subtractions and products run on the packed FP32 pipe, two cells per instruction.
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      x[i] = r.w[i];
-      if (METHOD == ATL_WIND_LOG) {
-        // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
-        // (not rewritten as v + v*c/(..): z0 = 0 must give NaN = inf/inf like the reference)
-        const float L = __log2f(r.a[i]);
-        x[i] = x[i] * __fdividef(lg2_to - L, lg2_from - L);
-      } else if (METHOD == ATL_WIND_POWER) {
-        x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
+      for (int p = 0; p < 2; ++p) {
+        const float2 nL = make_float2(-__log2f(r.a[2 * p]), -__log2f(r.a[2 * p + 1]));
+        const float2 num = __fadd2_rn(nL, make_float2(lg2_to, lg2_to));
+        const float2 den = __fadd2_rn(nL, make_float2(lg2_from, lg2_from));
+        const float2 q = __fmul2_rn(num, make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y)));
+        const float2 xv = __fmul2_rn(make_float2(r.w[2 * p], r.w[2 * p + 1]), q);
+        x[2 * p] = xv.x;
+        x[2 * p + 1] = xv.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[i] = r.w[i];
+        if (METHOD == ATL_WIND_POWER) x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
     }
     interp4(c, x, v, sm);

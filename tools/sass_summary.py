@@ -21,16 +21,20 @@ CSRC = os.path.join(ROOT, "atlite_b200", "csrc")
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 
 KERNELS = {
-    "pv_fused": ("pv.o", r"k_fused_reduceINS_6PvPhysILb1ELb1EEELi2ELi5ELi16"),
-    "pv_fused_general": ("pv.o", r"k_fused_reduceINS_6PvPhysILb0ELb1EEELi1ELi4ELi16"),
-    "wind_fused_log": ("wind.o", r"k_fused_reduceINS_8WindPhysILb1ELi1EEELi2ELi6ELi"),
-    "heat_fused": ("heat.o", r"k_heatILi0ELb1"),
-    "spmm_fused": ("plan.o", r"k_fused_reduceINS_12IdentityPhysILb1EEELi4"),
-    "pv_cells_timesum": ("pv.o", r"7k_cellsINS_6PvPhysILb1ELb1EEELi1"),
+    "pv_fused (shuffle reduce, ERA5 default, solar position in-kernel)": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi1ELb1EEELi2ELi5ELi1"),
+    "pv_fused_stored_solar_f64": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi2ELb1EEELi2ELi4ELi1"),
+    "pv_fused_era5_inputs_runtime_switches (mode 4)": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi4ELb1EEELi2ELi4ELi1"),
+    "pv_fused_general (mode 0)": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi0ELb1EEELi1ELi4ELi1"),
+    "pv_fused_staged_variant": ("pv.o", r"k_fused_reduceINS_6PvPhysILi1ELb1EEELi2ELi5ELi8"),
+    "wind_fused_log_lattice1 (shuffle reduce)": ("wind.o", r"k_fused_reduce_v1INS_8WindPhysILb1ELi1ELi2EEELi2ELi6ELi1"),
+    "wind_fused_staged_variant": ("wind.o", r"k_fused_reduceINS_8WindPhysILb1ELi1ELi2EEELi4ELi5ELi8"),
+    "heat_fused (staged reduce)": ("heat.o", r"k_heatILi0ELb1"),
+    "spmm_fused": ("plan.o", r"k_fused_reduce_v1INS_12IdentityPhysILb1EEELi4"),
+    "pv_cells_timesum": ("pv.o", r"7k_cellsINS_6PvPhysILi1ELb1EEELi1"),
 }
 CLASSES = [
-    ("fp32_fma", r"^(FFMA|FMUL|FADD|FMNMX|FSEL|FSETP|FCHK|FSET)"),
     ("fp32_packed", r"^(FFMA2|FMUL2|FADD2)"),
+    ("fp32_fma", r"^(FFMA|FMUL|FADD|FMNMX|FSEL|FSETP|FCHK|FSET)"),
     ("mufu", r"^MUFU"),
     ("convert", r"^(F2I|I2F|F2F|I2FP|F2FP)"),
     ("int_alu", r"^(IADD3|IADD|IMAD|LOP3|SHF|LEA|ISETP|SEL|VIADD|VIMNMX|VIADDMNMX|IMNMX|PRMT|LOP|IABS|MOV|HFMA2|SGXT|BMSK|PLOP3|P2R|R2P|POPC|FLO)"),
