@@ -79,7 +79,7 @@ __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<V
 // MODE 2: per-cell sum over days accumulated into out (ny, nx), and the number of non-NaN
 // days into cnt_out (may be NULL)
 template <int MODE, bool VEC>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 6)  // latency-bound (ncu: long_scoreboard): 24 warps per SM
     k_heat(const HeatParams hp, const GridDev gd, const PlanDev plan, float* __restrict__ out,
            float* __restrict__ cnt_out, int n_days, int db) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

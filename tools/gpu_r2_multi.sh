@@ -8,6 +8,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_multi_${TAG}_n$N.log 2>&1
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_n$N.json 2> gpurun_out/bench_${TAG}_n$N.err
+for s in small big; do timeout 120 python tools/prof_pv.py wind $s 7; timeout 120 python tools/prof_pv.py heat $s 7; done > gpurun_out/prof_${TAG}_n$N.jsonl 2>/dev/null
 timeout 900 python tools/e2e_multi.py --kind pv > gpurun_out/e2e_multi_${TAG}_n$N.json 2> gpurun_out/e2e_multi_${TAG}_n$N.err
 tail -3 gpurun_out/pytest_multi_${TAG}_n$N.log; head -c 2500 gpurun_out/bench_${TAG}_n$N.json; echo; tail -3 gpurun_out/bench_${TAG}_n$N.err
-cat gpurun_out/e2e_multi_${TAG}_n$N.json; tail -3 gpurun_out/e2e_multi_${TAG}_n$N.err
+cat gpurun_out/prof_${TAG}_n$N.jsonl; cat gpurun_out/e2e_multi_${TAG}_n$N.json; tail -3 gpurun_out/e2e_multi_${TAG}_n$N.err
