@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   phys.init(c, g, smem);
   typename Phys::Raw r[B];
   float v[4];
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int n_nan[4] = {0, 0, 0, 0};
   const int64_t S4 = gd.S * 4;
   const int tl = t1 - 1;
 #pragma unroll
@@ -466,8 +467,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
     for (int j = 0; j < B; ++j) {
       const bool live = t + j < t1;
       phys.compute(c, g, min(t + j, tl), r[j], v, smem);
-      if constexpr (Phys::kHasExact) {  // cold, per lane: a NaN/Inf reached a result
-        if (!(fabsf((v[0] + v[1]) + (v[2] + v[3])) <= 3.0e38f))
+      if constexpr (Phys::kHasExact) {  // cold, warp-uniform: a NaN/Inf reached a result
+        if (__any_sync(0xffffffffu, !(fabsf((v[0] + v[1]) + (v[2] + v[3])) <= 3.0e38f)))
           phys.compute_exact(c, g, min(t + j, tl), r[j], v, smem);
       }
       phys.load(c, g, (int64_t)min(t + j + B, tl) * S4, r[j]);
@@ -475,17 +476,22 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
         if (live) store4(out + (int64_t)(t + j - t_begin) * gd.S_out, gd, g, v);
       } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool ok = live && v[q] == v[q];
-          acc[q] += ok ? v[q] : 0.f;
-          cnt[q] += ok ? 1.f : 0.f;
+        for (int q = 0; q < 4; ++q) {  // NaN steps are skipped and counted (one predicated add)
+          const bool ok = v[q] == v[q];
+          acc[q] += (live && ok) ? v[q] : 0.f;
+          if (live && !ok) ++n_nan[q];
         }
       }
     }
   }
   if (MODE == 1) {
     atomic_add4(out, gd, g, acc);
-    if (cnt_out) atomic_add4(cnt_out, gd, g, cnt);
+    if (cnt_out) {  // valid steps of this block = its steps minus the NaN ones
+      float cnt[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cnt[q] = (float)(t1 - t0 - n_nan[q]);
+      atomic_add4(cnt_out, gd, g, cnt);
+    }
   }
 }
 
