@@ -114,7 +114,7 @@ struct WindPhys {
   // general LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; lattice:
   // <= 130 x 16 or <= 258 x 4 replicas, 2 floats each; fallback: 256 + 4*257
   static constexpr int kSmemFloats = 2 * 130 * 16;
-  static constexpr int kBatch = 2, kMinBlocks = 7;  // issue-bound at 75 % issue-active with 24 warps: 28 warps
+  static constexpr int kBatch = 2, kMinBlocks = 6;  // (7 CTAs = 28 warps per SM measured the same: issue-bound)
   static constexpr bool kHasExact = false;  // NaN speeds / roughness propagate like np.interp's
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)
