@@ -325,8 +325,26 @@ class Comm:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa_bound = self._bind_to_gpu_node()
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+
+    def _bind_to_gpu_node(self):
+        """One process per GPU: run this rank (its pinned allocations, its staging threads) on the
+        CPUs next to its GPU, as `numactl --cpunodebind` would -- on a two-socket box half of the
+        ranks otherwise stream their host slabs across the inter-socket link."""
+        if self.world == 1:
+            return False
+        try:
+            from atlite_b200 import _lib
+
+            cpus = set(_lib.device_local_cpus(self.local_rank)) & set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return True
+        except Exception:  # noqa: BLE001
+            pass
+        return False
 
     def sync(self):
         self.torch.cuda.synchronize()
@@ -568,6 +586,7 @@ def run_ours(args):
                 "sample": f"each rank streams the first {ne} steps of its shard from pinned host memory "
                           f"({world * ne} of {NT} steps per pass)",
                 "api": "atlite_b200.Cutout(data=<pinned host arrays>).pv('CSi','latitude_optimal',matrix=...,aggregate_time=None)",
+                "rank_bound_to_gpu_numa_node": comm.numa_bound,
                 "max_rel_diff_vs_device_path": agree},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
