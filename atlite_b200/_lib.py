@@ -210,6 +210,7 @@ _SIGNATURES = {
                                     C.c_int32]),
     "atl_wind_create": (C.c_int, [C.c_int, C.POINTER(WindConfig), C.POINTER(_P)]),
     "atl_wind_curve_eval_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
+    "atl_wind_curve_info_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "atl_wind_destroy": (None, [_P]),
     "atl_wind_reduce": (C.c_int, [_P, _P, C.POINTER(WindFields), C.c_int64, _P, _P]),
     "atl_wind_cells": (C.c_int, [_P, C.POINTER(WindFields), C.c_int64, _P, _P]),

@@ -221,6 +221,13 @@ __device__ __forceinline__ const float* at_bytes(const float* f, int64_t b) {
 __device__ __forceinline__ const double* at_bytes(const double* f, int64_t b) {
   return reinterpret_cast<const double*>(reinterpret_cast<const char*>(f) + 2 * b);
 }
+// One MUFU.RCP (div.approx / __fdividef(1.f, x) add a canonicalising FADD behind it).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ void load4(const float* __restrict__ f, int64_t tb,
                                       const TileGeomT<false>& g, float (&o)[4]) {
 #pragma unroll

@@ -36,29 +36,21 @@
 
 namespace atl {
 
-// A warp owns one 32x4 tile and walks `tb` consecutive time steps in batches of
-// B.  Per batch: the arithmetic of the B resident steps runs first, then the
-// loads of the NEXT batch are issued into the now-dead raw registers, and only
-// then the shuffle-reduce + atomics of the current batch execute -- so B steps of
-// loads are in flight across the whole reduce phase at no extra register cost.
-// Steps are reduced two at a time, slots four at a time, in one transposed
-// butterfly (reduce_slots2g; G = 0 selects the older pairwise reduce_slots2).  B is chosen per
-// physics so that B x (#fields) 16-byte loads per lane cover the HBM latency
-// (PV: 2 x 5, wind: 4 x 2, SpMM: 4 x 1).  MINB = CTAs/SM the register allocator
-// must allow.
-template <class Phys, int B, int MINB, int G = 0>
-__global__ void __launch_bounds__(CTA_THREADS, MINB)
-    k_fused_reduce_v1(const Phys phys, const GridDev gd, const PlanDev plan,
-                      float* __restrict__ out, int nt, int tb) {
-  extern __shared__ float smem[];
-  phys.stage(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ai = blockIdx.x * WARPS_PER_CTA + warp;
-  if (ai >= plan.n_active) return;
-  const int tile = __ldg(plan.active_tiles + ai);
-  const auto g = make_geom<Phys::kVec>(tile, lane, gd);
-  const int s_beg = __ldg(plan.tile_slot_ptr + tile);
-  const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
+// Physics that are issue-bound rather than HBM-bound opt into two copies of the time walk
+// (`static constexpr bool kSplitMask = true`), see fused_v1_walk.
+template <class P, class = void>
+struct split_mask : std::false_type {};
+template <class P>
+struct split_mask<P, std::void_t<decltype(P::kSplitMask)>> : std::bool_constant<P::kSplitMask> {};
+
+// The time walk of one warp tile.  MASK = the tile overhangs the grid (row padding / last tile
+// column): only then are the values of out-of-grid lanes zeroed; interior tiles (the vast
+// majority) run the copy of the loop without the selects (about one instruction in eight of
+// the wind kernel).  The choice is warp-uniform, made once per tile.
+template <class Phys, int B, int G, bool MASK, class Geom>
+__device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& gd, const PlanDev& plan,
+                                              float* __restrict__ out, int nt, int tb, const Geom& g,
+                                              int s_beg, int s_end, int lane, const float* smem) {
   const int t0 = blockIdx.y * tb;
   const int t1 = min(nt, t0 + tb);
   const int nb = plan.n_bus;
@@ -80,7 +72,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 #pragma unroll
       for (int j = 0; j < B; ++j) {
         phys.compute(c, g, t + j, r[j], v[j], smem);
-        zero_invalid(g, v[j]);
+        if (MASK) zero_invalid(g, v[j]);
       }
       bool bad = false;  // kHasExact: one probe serves the physics' NaN rules AND the reduce
       if constexpr (Phys::kHasExact) {
@@ -92,7 +84,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
 #pragma unroll
           for (int j = 0; j < B; ++j) {
             phys.compute_exact(c, g, t + j, r[j], v[j], smem);
-            zero_invalid(g, v[j]);
+            if (MASK) zero_invalid(g, v[j]);
           }
         }
       }
@@ -125,14 +117,47 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB)
   for (; t < t1; ++t, sb += S4) {
     phys.load(c, g, sb, r[0]);
     phys.compute(c, g, t, r[0], v[0], smem);
-    zero_invalid(g, v[0]);
+    if (MASK) zero_invalid(g, v[0]);
     if constexpr (Phys::kHasExact) {
       if (__any_sync(0xffffffffu, !(fabsf((v[0][0] + v[0][1]) + (v[0][2] + v[0][3])) <= 3.0e38f))) {
         phys.compute_exact(c, g, t, r[0], v[0], smem);
-        zero_invalid(g, v[0]);
+        if (MASK) zero_invalid(g, v[0]);
       }
     }
     reduce_slots(v[0], s_beg, s_end, plan, out + (size_t)t * nb, lane);
+  }
+}
+
+// A warp owns one 32x4 tile and walks `tb` consecutive time steps in batches of
+// B.  Per batch: the arithmetic of the B resident steps runs first, then the
+// loads of the NEXT batch are issued into the now-dead raw registers, and only
+// then the shuffle-reduce + atomics of the current batch execute -- so B steps of
+// loads are in flight across the whole reduce phase at no extra register cost.
+// Steps are reduced two at a time, slots four at a time, in one transposed
+// butterfly (reduce_slots2g; G = 0 selects the older pairwise reduce_slots2).  B is chosen per
+// physics so that B x (#fields) 16-byte loads per lane cover the HBM latency
+// (PV: 2 x 5, wind: 4 x 2, SpMM: 4 x 1).  MINB = CTAs/SM the register allocator
+// must allow.
+template <class Phys, int B, int MINB, int G = 0>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
+    k_fused_reduce_v1(const Phys phys, const GridDev gd, const PlanDev plan,
+                      float* __restrict__ out, int nt, int tb) {
+  extern __shared__ float smem[];
+  phys.stage(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ai = blockIdx.x * WARPS_PER_CTA + warp;
+  if (ai >= plan.n_active) return;
+  const int tile = __ldg(plan.active_tiles + ai);
+  const auto g = make_geom<Phys::kVec>(tile, lane, gd);
+  const int s_beg = __ldg(plan.tile_slot_ptr + tile);
+  const int s_end = __ldg(plan.tile_slot_ptr + tile + 1);
+  if constexpr (split_mask<Phys>::value) {
+    if (__any_sync(0xffffffffu, g.valid != 0xFu))
+      fused_v1_walk<Phys, B, G, true>(phys, gd, plan, out, nt, tb, g, s_beg, s_end, lane, smem);
+    else
+      fused_v1_walk<Phys, B, G, false>(phys, gd, plan, out, nt, tb, g, s_beg, s_end, lane, smem);
+  } else {
+    fused_v1_walk<Phys, B, G, true>(phys, gd, plan, out, nt, tb, g, s_beg, s_end, lane, smem);
   }
 }
 

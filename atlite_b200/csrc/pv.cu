@@ -241,7 +241,7 @@ struct PvPhys {
       const float2 diffuse = make_float2(fmin_nan(fmax_nan(r.b[i0], 0.f), room.x),
                                          fmin_nan(fmax_nan(r.b[i1], 0.f), room.y));
       const float2 influx = __fadd2_rn(direct, diffuse);
-      const float2 rcp = make_float2(__fdividef(1.f, sinalt[p].x), __fdividef(1.f, sinalt[p].y));  // MUFU.RCP
+      const float2 rcp = make_float2(rcp_approx(sinalt[p].x), rcp_approx(sinalt[p].y));
       const float2 Rb = __fmul2_rn(ci, rcp);
       const float2 ground = __fmul2_rn(__fmul2_rn(make_float2(r.alb[i0], r.alb[i1]), influx), bc(gfac));
       const float2 total = __ffma2_rn(Rb, direct, __ffma2_rn(diffuse, bc(dfac), ground));

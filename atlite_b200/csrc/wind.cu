@@ -10,6 +10,15 @@
 
 #include "kernels.cuh"
 
+// experiment knobs (tools/build_variants.sh)
+#ifndef ATL_WIND_SAT_R
+#define ATL_WIND_SAT_R 8  // replicas of the saturating table's 256 rows (8: 16 KB, 16: 32 KB)
+#endif
+#ifndef ATL_WIND_B
+#define ATL_WIND_B 2
+#define ATL_WIND_MINB 6
+#endif
+
 namespace atl {
 
 // Power curve in shared memory.
@@ -81,8 +90,31 @@ __host__ __device__ __forceinline__ float lattice_interp(float x, const char* lu
   return y;
 }
 
+// Saturating lattice mode: 256 rows; row 0 = flat left end, rows 1..NB = the NB lattice buckets
+// (steps folded in, see build_curve), rows NB+1..255 = flat right end.  The float -> u8
+// conversion (one F2I.U8.FLOOR) saturates to [0, 255] and sends NaN to 0, so the speed needs no
+// clamps: 5 instructions per cell (FFMA, F2I, IMAD, LDS.64, FFMA).  A flat row times an
+// infinite speed is NaN -- CLAMPED = true (the kernels' cold exact path, taken when a fast
+// result is not finite) evaluates the same table with the speed clamped to the knot range
+// first, which is np.interp for +-inf and keeps NaN.
+template <bool CLAMPED>
+__host__ __device__ __forceinline__ float sat_interp(float x, const char* lut, int stride,
+                                                     float x_lo, float x_hi, float inv_w, float c0) {
+#ifdef __CUDA_ARCH__
+  const float xc = CLAMPED ? fmin_nan(fmax_nan(x, x_lo), x_hi) : x;
+  unsigned int b;
+  asm("cvt.rmi.u8.f32 %0, %1;" : "=r"(b) : "f"(fmaf(xc, inv_w, c0)));
+#else
+  const float xc = (!CLAMPED || x != x) ? x : std::fmin(std::fmax(x, x_lo), x_hi);
+  const float t = std::fmaf(xc, inv_w, c0);
+  const unsigned int b = (t != t) ? 0u : (unsigned int)std::fmin(std::fmax(std::floor(t), 0.f), 255.f);
+#endif
+  const float2 e = *reinterpret_cast<const float2*>(lut + b * stride);
+  return fmaf(e.x, xc, e.y);
+}
+
 // METHOD: ATL_WIND_NONE / _LOG / _POWER and LMODE (0: binary search or general LUT, chosen at
-// run time; 1 + nj: lattice LUT with nj steps) are compile time: no predicated duplicates of
+// run time; 1 + nj: lattice LUT with nj steps; 4: saturating lattice LUT) are compile time: no predicated duplicates of
 // the loads, no uniform branches or re-loaded kernel parameters in the per-cell code.
 template <bool VEC, int METHOD, int LMODE>
 struct WindPhys {
@@ -95,6 +127,7 @@ struct WindPhys {
   int method;
   int n_knots, NK;
   float lg2_to, lg2_from, lg2_ratio;
+  float neg_lg2_to, neg_lg2_from;
   float x_lo, x_hi;
   int use_lut, n_stage;   // use_lut: 0 binary search, 1 general LUT, 2 lattice LUT
   float inv_w, c0;        // bucket = floor(x * inv_w + c0)
@@ -113,9 +146,12 @@ struct WindPhys {
   };
   // general LUT: <= 129 buckets x 8 replicas or <= 1025 x 1, 4 floats each; lattice:
   // <= 130 x 16 or <= 258 x 4 replicas, 2 floats each; fallback: 256 + 4*257
-  static constexpr int kSmemFloats = 2 * 130 * 16;
-  static constexpr int kBatch = 2, kMinBlocks = 6;  // (7 CTAs = 28 warps per SM measured the same: issue-bound)
-  static constexpr bool kHasExact = false;  // NaN speeds / roughness propagate like np.interp's
+  static constexpr int kSmemFloats = 2 * 130 * 16 > 2 * 256 * ATL_WIND_SAT_R ? 2 * 130 * 16 : 2 * 256 * ATL_WIND_SAT_R;
+  static constexpr int kBatch = ATL_WIND_B, kMinBlocks = ATL_WIND_MINB;  // (7 CTAs = 28 warps per SM measured the same)
+  // NaN speeds / roughness propagate like np.interp's in every mode; the saturating table also
+  // turns +-inf speeds into NaN and relies on the cold exact path for them
+  static constexpr bool kHasExact = LMODE == 4;
+  static constexpr bool kSplitMask = true;  // issue-bound: interior tiles skip the out-of-grid selects
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)
 
@@ -131,9 +167,15 @@ struct WindPhys {
     if (METHOD != ATL_WIND_NONE) load4(aux, tb, g, r.a);
   }
   // np.interp for the lane's 4 values at once.
+  template <bool EXACT = false>
   __device__ __forceinline__ void interp4(const Cell& c, const float (&x)[4], float (&r)[4],
                                           const float* sm) const {
-    if constexpr (LMODE >= 1) {
+    if constexpr (LMODE == 4) {
+      const char* lut = reinterpret_cast<const char*>(sm) + c.rep_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = sat_interp<EXACT>(x[i], lut, lut_stride, x_lo, x_hi, inv_w, c0);
+      return;
+    } else if constexpr (LMODE >= 1) {
       const char* lut = reinterpret_cast<const char*>(sm) + lut_stride + c.rep_off;  // skip the guard
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -165,8 +207,25 @@ struct WindPhys {
       r[i] = (x[i] != x[i] && n_knots > 1) ? x[i] : y;  // np.interp: one knot -> constant, even for NaN
     }
   }
-  __device__ void compute(const Cell& c, const Geom&, int, const Raw& r, float (&v)[4],
-                          const float* sm) const {
+  __device__ __forceinline__ void compute(const Cell& c, const Geom&, int, const Raw& r, float (&v)[4],
+                                          const float* sm) const {
+    compute_impl<false>(c, r, v, sm);
+  }
+  // cold, out of line, arguments by value (see PvPhys::exact_by_value)
+  static __device__ __noinline__ float4 exact_by_value(const WindPhys self, const Cell c, const Raw r,
+                                                       const float* sm) {
+    float v[4];
+    self.template compute_impl<true>(c, r, v, sm);
+    return make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ __forceinline__ void compute_exact(const Cell& c, const Geom&, int, const Raw& r,
+                                                float (&v)[4], const float* sm) const {
+    const float4 o = exact_by_value(*this, c, r, sm);
+    v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
+  }
+  template <bool EXACT>
+  __device__ __forceinline__ void compute_impl(const Cell& c, const Raw& r, float (&v)[4],
+                                               const float* sm) const {
     float x[4];
     if (METHOD == ATL_WIND_LOG) {
       // v * ln(to/z0) / ln(from/z0) = v * (lg2 to - lg2 z0) / (lg2 from - lg2 z0)
@@ -174,10 +233,11 @@ struct WindPhys {
       // The subtractions and products run on the packed FP32 pipe, two cells per instruction.
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        const float2 nL = make_float2(-__log2f(r.a[2 * p]), -__log2f(r.a[2 * p + 1]));
-        const float2 num = __fadd2_rn(nL, make_float2(lg2_to, lg2_to));
-        const float2 den = __fadd2_rn(nL, make_float2(lg2_from, lg2_from));
-        const float2 q = __fmul2_rn(num, make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y)));
+        // (L - lg2 to) / (L - lg2 from): both signs flipped, so no negations
+        const float2 L = make_float2(__log2f(r.a[2 * p]), __log2f(r.a[2 * p + 1]));
+        const float2 num = __fadd2_rn(L, make_float2(neg_lg2_to, neg_lg2_to));
+        const float2 den = __fadd2_rn(L, make_float2(neg_lg2_from, neg_lg2_from));
+        const float2 q = __fmul2_rn(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
         const float2 xv = __fmul2_rn(make_float2(r.w[2 * p], r.w[2 * p + 1]), q);
         x[2 * p] = xv.x;
         x[2 * p + 1] = xv.y;
@@ -189,7 +249,7 @@ struct WindPhys {
         if (METHOD == ATL_WIND_POWER) x[i] = x[i] * exp2f(r.a[i] * lg2_ratio);  // v * (to/from)^alpha
       }
     }
-    interp4(c, x, v, sm);
+    interp4<EXACT>(c, x, v, sm);
   }
 };
 
@@ -224,6 +284,8 @@ static WindPhys<VEC, METHOD, LMODE> make_phys(const AtlWindOp* op, const AtlWind
   p.lg2_to = op->lg2_to;
   p.lg2_from = op->lg2_from;
   p.lg2_ratio = op->lg2_ratio;
+  p.neg_lg2_to = -op->lg2_to;
+  p.neg_lg2_from = -op->lg2_from;
   p.x_lo = op->x_lo;
   p.x_hi = op->x_hi;
   p.use_lut = op->use_lut;
@@ -241,13 +303,13 @@ static WindPhys<VEC, METHOD, LMODE> make_phys(const AtlWindOp* op, const AtlWind
   return p;
 }
 
-// compile-time table mode of the operator: 0 generic (binary search / general LUT), 1 + nj lattice
-static int lut_mode(const AtlWindOp* op) { return op->use_lut == 2 ? 1 + op->nj : 0; }
-#define ATL_WIND_ALL_CASES                                                                          \
-  ATL_WIND_CASE(ATL_WIND_NONE, 0) ATL_WIND_CASE(ATL_WIND_NONE, 1) ATL_WIND_CASE(ATL_WIND_NONE, 2)   \
-  ATL_WIND_CASE(ATL_WIND_NONE, 3) ATL_WIND_CASE(ATL_WIND_LOG, 0) ATL_WIND_CASE(ATL_WIND_LOG, 1)     \
-  ATL_WIND_CASE(ATL_WIND_LOG, 2) ATL_WIND_CASE(ATL_WIND_LOG, 3) ATL_WIND_CASE(ATL_WIND_POWER, 0)    \
-  ATL_WIND_CASE(ATL_WIND_POWER, 1) ATL_WIND_CASE(ATL_WIND_POWER, 2) ATL_WIND_CASE(ATL_WIND_POWER, 3)
+// compile-time table mode of the operator: 0 generic (binary search / general LUT), 1 + nj lattice,
+// 4 saturating lattice
+static int lut_mode(const AtlWindOp* op) { return op->use_lut == 3 ? 4 : op->use_lut == 2 ? 1 + op->nj : 0; }
+#define ATL_WIND_METHOD_CASES(M)                                                          \
+  ATL_WIND_CASE(M, 0) ATL_WIND_CASE(M, 1) ATL_WIND_CASE(M, 2) ATL_WIND_CASE(M, 3) ATL_WIND_CASE(M, 4)
+#define ATL_WIND_ALL_CASES \
+  ATL_WIND_METHOD_CASES(ATL_WIND_NONE) ATL_WIND_METHOD_CASES(ATL_WIND_LOG) ATL_WIND_METHOD_CASES(ATL_WIND_POWER)
 
 static int check_fields(const AtlWindOp* op, const AtlWindFields* f) {
   ATL_REQUIRE(op && f && f->wnd, "NULL argument");
@@ -265,7 +327,8 @@ struct CurveTables {
   float k_jump = INFINITY, jump = 0.f, k_end = 0.f, y_end = 0.f;
 };
 
-// force_mode: -1 best available, 0 binary search, 1 general LUT, 2 lattice LUT
+// force_mode: -1 best available, 0 binary search, 1 general LUT, 2 lattice LUT with compares,
+// 3 saturating lattice LUT
 static int build_curve(const double* V, const double* POW, int n, CurveTables& T,
                        int force_mode = -1) {
   const bool force_fallback = force_mode == 0;
@@ -321,7 +384,7 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
   float k_jump = INFINITY, jump = 0.f;
   float k_end = ceil_f(V[n - 1]), y_end = (float)POW[n - 1];
   // ---- lattice LUT: knots on lo + m*w, at most two steps
-  if (n >= 2 && V[n - 1] > V[0] && (force_mode == -1 || force_mode == 2)) {
+  if (n >= 2 && V[n - 1] > V[0] && (force_mode == -1 || force_mode >= 2)) {
     const double lo = V[0], hi = V[n - 1];
     struct Jump { double K, J; };
     std::vector<Jump> jumps;
@@ -337,7 +400,7 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
     for (size_t k = 1; k < last.size(); ++k) dmin = std::min(dmin, V[last[k]] - V[last[k - 1]]);
     int NB = 0;
     double wdt = 0.0;
-    for (int q = 1; q <= 8 && !NB && jumps.size() <= 2; ++q) {
+    for (int q = 1; q <= 8 && !NB; ++q) {
       const double w = dmin / q;
       const double nb = (hi - lo) / w;
       if (nb > 256.5) break;
@@ -384,18 +447,113 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
       nj = (int)jumps.size();
       k_jump = k_end = INFINITY;
       jump = y_end = 0.f;
-      if (nj > 0) {
+      // A step sits on a bucket boundary.  When the bucket function itself -- the kernel's
+      // floor(fmaf(clamp(x), inv_w, c0)), monotone in x -- crosses that boundary EXACTLY at the
+      // step's float threshold k (first float >= the knot), i.e. bucket(k) = m and
+      // bucket(prev(k)) = m - 1, the table can hold the curve WITH its steps and the per-cell
+      // compares go away (nj = 0).  True for the usual curves (knots and bucket widths that are
+      // binary fractions); verified here in the kernel's own float arithmetic, a few ulps of
+      // c0 / inv_w are tried otherwise.  A step at the first knot cannot fold (x < x_lo clamps
+      // onto it).  `sat`: the saturating table's bucket function (no clamp of x, rows shifted by
+      // one, floor saturated to [0, 255]).
+      const float x_lo_f = (float)V[0], x_hi_f = (float)V[n - 1];
+      auto bucket = [&](float x, float iw, float cc, bool sat) {
+        if (sat) return (int)std::fmin(std::fmax(std::floor(std::fmaf(x, iw, cc)), 0.f), 255.f);
+        const float xc = std::fmin(std::fmax(x, x_lo_f), x_hi_f);
+        return (int)std::floor(std::fmaf(xc, iw, cc));
+      };
+      bool foldable = true;
+      for (const Jump& j : jumps) foldable = foldable && j.K > lo && (double)ceil_f(j.K) <= (double)x_hi_f;
+      auto search = [&](bool sat, float& iw_out, float& cc_out) {
+        const float iw0 = (float)(1.0 / wdt), cc0 = (float)(-lo / wdt + (sat ? 1.0 : 0.0));
+        const int sh = sat ? 1 : 0;
+        for (int ti = 0; ti < 25 && foldable; ++ti) {
+          float iw = iw0, cc = cc0;
+          const int di = (ti % 5 + 2) % 5 - 2, dc = (ti / 5 + 2) % 5 - 2;  // 0, 1, 2, -2, -1: exact values first
+          for (int a = 0; a < std::abs(di); ++a) iw = nextafterf(iw, di < 0 ? 0.f : INFINITY);
+          for (int a = 0; a < std::abs(dc); ++a) cc = nextafterf(cc, dc < 0 ? -INFINITY : INFINITY);
+          if (cc != 0.f && std::fabs(cc) < 1.2e-38f) continue;  // flushed to zero on the device
+          bool ok = bucket(x_lo_f, iw, cc, sat) >= sh - 1 && bucket(x_lo_f, iw, cc, sat) <= sh &&
+                    bucket(x_hi_f, iw, cc, sat) >= NB - 1 + sh && bucket(x_hi_f, iw, cc, sat) <= NB + sh;
+          for (const Jump& j : jumps) {
+            const float k = ceil_f(j.K);
+            const int m = (int)std::lround((j.K - lo) / wdt) + sh;
+            ok = ok && bucket(k, iw, cc, sat) == m && bucket(nextafterf(k, -INFINITY), iw, cc, sat) == m - 1;
+          }
+          if (ok) {
+            iw_out = iw;
+            cc_out = cc;
+            return true;
+          }
+        }
+        return false;
+      };
+      // rows of the curve WITH its steps: bucket b in segment [V[z], V[z+1])
+      auto stepped_rows = [&](auto&& emit) {
+        size_t kk = 0;
+        for (int b = 0; b < NB; ++b) {
+          const double mid = lo + (b + 0.5) * wdt;
+          while (kk + 1 < last.size() && V[last[kk + 1]] <= mid) ++kk;
+          const int z = last[kk];
+          const double sl = (POW[z + 1] - POW[z]) / (V[z + 1] - V[z]);
+          emit(b, sl, POW[z] - sl * V[z]);
+        }
+      };
+      bool done = false;
+#ifdef ATL_WIND_NO_SAT  // experiment knob: -1 never picks the saturating table
+      const bool sat_allowed = force_mode == 3;
+#else
+      const bool sat_allowed = force_mode == -1 || force_mode == 3;
+#endif
+      if (sat_allowed && NB + 2 <= 256) {  // ---- saturating lattice LUT
+        float iw, cc;
+        if (search(true, iw, cc)) {
+          const int Rs = ATL_WIND_SAT_R;
+          std::vector<float> ls((size_t)256 * Rs * 2);
+          auto put_s = [&](int row, double sl, double icpt) {
+            const float e[2] = {(float)sl, (float)icpt};
+            for (int r = 0; r < Rs; ++r) std::memcpy(&ls[((size_t)row * Rs + r) * 2], e, 8);
+          };
+          put_s(0, 0.0, POW[0]);
+          stepped_rows([&](int b, double sl, double icpt) { put_s(b + 1, sl, icpt); });
+          for (int row = NB + 1; row < 256; ++row) put_s(row, 0.0, POW[n - 1]);
+          use_lut = 3;
+          lut_stride = 8 * Rs;
+          rep_mask = Rs - 1;
+          inv_w = iw;
+          c0 = cc;
+          nj = 0;
+          lut.swap(ls);
+          done = true;
+        }
+      }
+      if (force_mode == 3 && !done) use_lut = 0;  // forced but not qualified: fall back to the search
+      if (!done && nj > 0 && force_mode == -1) {
+        float iw, cc;
+        if (search(false, iw, cc)) {
+          inv_w = iw;
+          c0 = cc;
+          stepped_rows([&](int b, double sl, double icpt) {
+            put(b + 1, sl, icpt);
+            if (b == 0) put(0, sl, icpt);
+          });
+          put(NB + 1, 0.0, POW[n - 1]);
+          nj = 0;
+        }
+      }
+      if (nj > 0 && nj <= 2) {
         k_jump = ceil_f(jumps[0].K);
         jump = (float)jumps[0].J;
       }
-      if (nj > 1) {
+      if (nj == 2) {
         k_end = ceil_f(jumps[1].K);
         y_end = (float)jumps[1].J;
       }
-      curve.swap(lut);
+      if (use_lut == 2 && nj > 2) use_lut = 0;  // more steps than compares and they do not fold
+      if (use_lut) curve.swap(lut);
     }
   }
-  if (!use_lut && force_mode != 2) {
+  if (!use_lut && force_mode != 2 && force_mode != 3) {
     const double lo = V[0], hi = V[n - 1];
     // jumps of np.interp: a run of equal knots a..z with POW[a] != POW[z]
     int n_interior = 0, jump_first = n;  // knots with index > jump_first sit above the jump
@@ -559,11 +717,18 @@ int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_
                              int32_t* used_lut_out) {
   ATL_REQUIRE(x && y_out && n >= 0, "bad arguments");
   CurveTables T;
-  ATL_REQUIRE(force_mode >= -1 && force_mode <= 2, "force_mode must be -1, 0, 1 or 2");
+  ATL_REQUIRE(force_mode >= -1 && force_mode <= 3, "force_mode must be -1 .. 3");
   if (int rc = build_curve(V, POW_norm, n_knots, T, force_mode)) return rc;
   if (used_lut_out) *used_lut_out = T.use_lut;
   // replicas must be identical copies; evaluate through a different one per element
   for (int64_t i = 0; i < n; ++i) {
+    if (T.use_lut == 3) {  // what the kernels return: the fast value, or the clamped one if that is not finite
+      const char* lut = reinterpret_cast<const char*>(T.curve.data()) + ((int)i & T.rep_mask) * 8;
+      float y = sat_interp<false>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0);
+      if (!(std::fabs(y) <= 3.0e38f)) y = sat_interp<true>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0);
+      y_out[i] = y;
+      continue;
+    }
     if (T.use_lut == 2) {
       const char* lut = reinterpret_cast<const char*>(T.curve.data()) + T.lut_stride + ((int)i & T.rep_mask) * 8;
       y_out[i] = T.nj == 0   ? lattice_interp<0>(x[i], lut, T.lut_stride, T.x_lo, T.x_hi, T.inv_w, T.c0,
@@ -592,6 +757,26 @@ int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_
   return ATL_OK;
 }
 
+int atl_wind_curve_info_host(const double* V, const double* POW_norm, int32_t n_knots,
+                             int32_t force_mode, int32_t info[4]) {
+  ATL_REQUIRE(info, "NULL argument");
+  ATL_REQUIRE(force_mode >= -1 && force_mode <= 3, "force_mode must be -1 .. 3");
+  CurveTables T;
+  if (int rc = build_curve(V, POW_norm, n_knots, T, force_mode)) return rc;
+  int steps = 0;
+  for (int a = 0; a < n_knots;) {
+    int z = a;
+    while (z + 1 < n_knots && V[z + 1] == V[a]) ++z;
+    steps += POW_norm[z] != POW_norm[a];
+    a = z + 1;
+  }
+  info[0] = T.use_lut;
+  info[1] = T.use_lut >= 2 ? T.nj : (T.use_lut == 1 ? (T.k_jump < INFINITY) + 1 : 0);
+  info[2] = steps;
+  info[3] = (int32_t)(T.curve.size() * sizeof(float));
+  return ATL_OK;
+}
+
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx) {
   ATL_REQUIRE(op, "NULL argument");
   if (device) *device = op->device;
@@ -611,11 +796,11 @@ int atl_wind_reduce(const AtlWindOp* op, const AtlPlan* plan, const AtlWindField
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
 #define ATL_WIND_CASE(M, L)                                                               \
-  case 4 * M + L: {                                                                       \
+  case 8 * M + L: {                                                                       \
     auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_reduce(make, plan, al, out_dev, nt, (cudaStream_t)stream);            \
   }
-  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
+  switch (8 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }
@@ -628,11 +813,11 @@ int atl_wind_cells(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, floa
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
 #define ATL_WIND_CASE(M, L)                                                               \
-  case 4 * M + L: {                                                                       \
+  case 8 * M + L: {                                                                       \
     auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_cells(make, op->grid, al, out_dev, nt, false, (cudaStream_t)stream);  \
   }
-  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
+  switch (8 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }
@@ -645,11 +830,11 @@ int atl_wind_timesum(const AtlWindOp* op, const AtlWindFields* f, int64_t nt, fl
   ATL_CUDA(cudaSetDevice(op->device));
   const bool al = aligned16(f->wnd) && aligned16(f->aux);
 #define ATL_WIND_CASE(M, L)                                                               \
-  case 4 * M + L: {                                                                       \
+  case 8 * M + L: {                                                                       \
     auto make = [&](auto vec) { return make_phys<decltype(vec)::value, M, L>(op, f); };   \
     return dispatch_cells(make, op->grid, al, out_dev, nt, true, (cudaStream_t)stream, count_dev);  \
   }
-  switch (4 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
+  switch (8 * op->method + lut_mode(op)) { ATL_WIND_ALL_CASES }
 #undef ATL_WIND_CASE
   return ATL_ERR_INVALID;
 }

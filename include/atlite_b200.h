@@ -382,12 +382,20 @@ int atl_pv_op_info(const AtlPvOp* op, int32_t* device, int32_t* ny, int32_t* nx,
 /* Host-only: evaluates the power-curve interpolation exactly as the kernels do
  * (same tables, same fp32 formula), no CUDA needed; the CPU tests compare it with
  * np.interp.  force_mode: -1 = the table atl_wind_create would pick, 0 = binary
- * search, 1 = general bucket LUT, 2 = lattice LUT (knots on a uniform lattice);
+ * search, 1 = general bucket LUT, 2 = lattice LUT (knots on a uniform lattice) with the
+ * steps added back by compares, 3 = saturating lattice LUT (256 rows, steps folded into
+ * the table, no clamps; what -1 picks when the curve qualifies);
  * *mode_out (optional) = the table actually built (a forced LUT mode the curve does
  * not qualify for falls back to 0). */
 int atl_wind_curve_eval_host(const double* V, const double* POW_norm, int32_t n_knots,
                              int32_t force_mode, const float* x, int64_t n, float* y_out,
                              int32_t* mode_out);
+/* Host-only: which table a power curve gets.  info[0] = table (0 binary search, 1 general
+ * LUT, 2 lattice LUT, 3 saturating lattice LUT), info[1] = steps the kernel adds back by compares (0 when the curve has
+ * none or they are folded into the lattice table), info[2] = steps in the curve (duplicate
+ * knots with different powers), info[3] = bytes staged to shared memory. */
+int atl_wind_curve_info_host(const double* V, const double* POW_norm, int32_t n_knots,
+                             int32_t force_mode, int32_t info[4]);
 int atl_wind_op_info(const AtlWindOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_heat_op_info(const AtlHeatOp* op, int32_t* device, int32_t* ny, int32_t* nx);
 int atl_pointwise_op_info(const AtlPointwiseOp* op, int32_t* device, int32_t* ny, int32_t* nx);

@@ -18,7 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import atlite_b200 as ab  # noqa: E402
-from atlite_b200 import engine, synthetic as syn  # noqa: E402
+from atlite_b200 import _lib, engine, synthetic as syn  # noqa: E402
+
+if os.environ.get("ATL_LIB_PATH"):  # A/B experiments: another build of the library (tools/build_variants.sh)
+    _lib.LIB_PATH = os.path.abspath(os.environ["ATL_LIB_PATH"])
 from atlite_b200.convert import _HeatSpec, _PvSpec, _WindSpec  # noqa: E402
 
 warnings.simplefilter("ignore")
@@ -76,7 +79,8 @@ torch.cuda.synchronize()
 ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
 cts = float(nx) * ny * nt
 print(json.dumps({"kind": kind, "size": size, "variant": os.environ.get("ATL_VARIANT", "0"),
-                  "tb": os.environ.get("ATL_TB", "auto"), "ms": round(ms, 4),
+                  "tb": os.environ.get("ATL_TB", "auto"),
+                  "lib": os.path.basename(os.environ.get("ATL_LIB_PATH", "")) or "default", "ms": round(ms, 4),
                   "cell_ts_per_s": cts / ms * 1e3, "GBs": round(cts * (bpc + out_b) / ms / 1e6, 1),
                   "frac_6573": round(cts * (bpc + out_b) / ms / 1e6 / 6573.5, 4),
                   "plan": plan.info["slots_per_active_tile"]}))
