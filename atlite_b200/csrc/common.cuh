@@ -437,6 +437,82 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
     if ((lane & 15) == 0) atomicAdd(my_row + __ldg(plan.slot_row + s), keep);
   }
 }
+
+// reduce_slots2g with the FIRST group's weights resident in registers (`wres`, loaded once per
+// tile walk by load_group_weights): the weights of a tile do not change along time, and
+// re-reading them every two steps costs as many L1 wavefronts as the fields themselves (wind).
+// Later groups (tiles with more than 4 slots, about a quarter) and the odd last slot load as before.
+__device__ __forceinline__ void load_group_weights(float4 (&wres)[4], int s_beg, const PlanDev& plan, int lane) {
+  const int f = (lane >> 2) & 3;
+  const float4* wp = plan.slot_w4 + (size_t)s_beg * 32 + lane;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wres[i] = __ldg(wp + (f ^ i) * 32);
+}
+template <bool PROBE = true>
+__device__ __forceinline__ void reduce_slots2g_res(const float (&v0)[4], const float (&v1)[4],
+                                                   const float4 (&wres)[4], int s_beg, int s_end,
+                                                   const PlanDev& plan, float* __restrict__ out_row0,
+                                                   int lane) {
+  const float chk = ((v0[0] + v0[1]) + (v0[2] + v0[3])) + ((v1[0] + v1[1]) + (v1[2] + v1[3]));
+  const bool bad = !(fabsf(chk) <= 3.0e38f);
+  if (PROBE && __any_sync(0xffffffffu, bad)) {
+    reduce_slots_exact(v0[0], v0[1], v0[2], v0[3], s_beg, s_end, plan, out_row0, lane);
+    reduce_slots_exact(v1[0], v1[1], v1[2], v1[3], s_beg, s_end, plan, out_row0 + plan.n_bus,
+                       lane);
+    return;
+  }
+  const bool hi = lane >= 16;
+  float* const my_row = out_row0 + (hi ? plan.n_bus : 0);
+  float vk[4], vs[4];
+  float2 ks[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    vk[i] = hi ? v1[i] : v0[i];
+    vs[i] = hi ? v0[i] : v1[i];
+    ks[i] = make_float2(vk[i], vs[i]);
+  }
+  const int f = (lane >> 2) & 3;
+  int s = s_beg;
+  const int32_t* rp = plan.slot_row + s_beg + f;
+  auto group = [&](auto&& weight) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 w = weight(i);
+      const float2 ab = __ffma2_rn(make_float2(w.x, w.x), ks[0],
+                                   __ffma2_rn(make_float2(w.y, w.y), ks[1],
+                                              __ffma2_rn(make_float2(w.z, w.z), ks[2],
+                                                         __fmul2_rn(make_float2(w.w, w.w), ks[3]))));
+      a[i] = ab.x;
+      b[i] = ab.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] += __shfl_xor_sync(0xffffffffu, b[i], 16);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[2], 8);
+    a[1] += __shfl_xor_sync(0xffffffffu, a[3], 8);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[1], 4);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(rp), a[0]);
+  };
+  group([&](int i) { return wres[i]; });  // the resident group (also serves a 1-slot tile)
+  s += 4;
+  rp += 4;
+#pragma unroll 1
+  for (; s_end - s >= 2; s += 4, rp += 4) {
+    const float4* wp = plan.slot_w4 + (size_t)s * 32 + lane;
+    group([&](int i) { return __ldg(wp + (f ^ i) * 32); });
+  }
+  if (s < s_end) {  // one slot left
+    const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);
+    float keep = fmaf(w.x, vk[0], fmaf(w.y, vk[1], fmaf(w.z, vk[2], w.w * vk[3])));
+    const float send = fmaf(w.x, vs[0], fmaf(w.y, vs[1], fmaf(w.z, vs[2], w.w * vs[3])));
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((lane & 15) == 0) atomicAdd(my_row + __ldg(plan.slot_row + s), keep);
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace atl

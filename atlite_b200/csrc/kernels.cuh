@@ -39,6 +39,10 @@ namespace atl {
 // Physics that are issue-bound rather than HBM-bound opt into two copies of the time walk
 // (`static constexpr bool kSplitMask = true`), see fused_v1_walk.
 template <class P, class = void>
+struct resident_weights : std::false_type {};
+template <class P>
+struct resident_weights<P, std::void_t<decltype(P::kResidentWeights)>> : std::bool_constant<P::kResidentWeights> {};
+template <class P, class = void>
 struct split_mask : std::false_type {};
 template <class P>
 struct split_mask<P, std::void_t<decltype(P::kSplitMask)>> : std::bool_constant<P::kSplitMask> {};
@@ -63,6 +67,9 @@ __device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& g
   int64_t sb = (int64_t)t0 * S4;  // byte offset of the next slab to LOAD
   const int nfull = (t1 - t0) / B;
   int t = t0;
+  constexpr bool RES = resident_weights<Phys>::value && G == 1 && (B % 2 == 0);
+  float4 wres[RES ? 4 : 1];
+  if constexpr (RES) load_group_weights(wres, s_beg, plan, lane);
   if (nfull > 0) {
 #pragma unroll
     for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
@@ -100,9 +107,13 @@ __device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& g
           if (bad) {  // cold: what is left non-finite is meant to be; stored entries only
             reduce_slots_exact(v[j][0], v[j][1], v[j][2], v[j][3], s_beg, s_end, plan, o, lane);
             reduce_slots_exact(v[j + 1][0], v[j + 1][1], v[j + 1][2], v[j + 1][3], s_beg, s_end, plan, o + nb, lane);
+          } else if constexpr (RES) {
+            reduce_slots2g_res<false>(v[j], v[j + 1], wres, s_beg, s_end, plan, o, lane);
           } else {
             reduce_slots2g<false>(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
           }
+        } else if constexpr (RES) {
+          reduce_slots2g_res(v[j], v[j + 1], wres, s_beg, s_end, plan, o, lane);
         } else if (G) {  // slots in groups of four (transposed butterfly)
           reduce_slots2g(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
         } else {

@@ -18,6 +18,9 @@
 #define ATL_WIND_B 2
 #define ATL_WIND_MINB 6
 #endif
+#ifndef ATL_WIND_RESIDENT
+#define ATL_WIND_RESIDENT 0
+#endif
 
 namespace atl {
 
@@ -151,6 +154,7 @@ struct WindPhys {
   // NaN speeds / roughness propagate like np.interp's in every mode; the saturating table also
   // turns +-inf speeds into NaN and relies on the cold exact path for them
   static constexpr bool kHasExact = LMODE == 4;
+  static constexpr bool kResidentWeights = ATL_WIND_RESIDENT != 0;  // first slot group's weights in registers
   static constexpr bool kSplitMask = true;  // issue-bound: interior tiles skip the out-of-grid selects
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)
@@ -500,11 +504,9 @@ static int build_curve(const double* V, const double* POW, int n, CurveTables& T
         }
       };
       bool done = false;
-#ifdef ATL_WIND_NO_SAT  // experiment knob: -1 never picks the saturating table
+      // measured slower than the clamped lattice table on B200 (profiles/r2_kernel_experiments.md:
+      // 8 replicas of 256 rows conflict in the banks, 16 replicas cost the L1): only on request
       const bool sat_allowed = force_mode == 3;
-#else
-      const bool sat_allowed = force_mode == -1 || force_mode == 3;
-#endif
       if (sat_allowed && NB + 2 <= 256) {  // ---- saturating lattice LUT
         float iw, cc;
         if (search(true, iw, cc)) {
@@ -664,7 +666,9 @@ int atl_wind_create(int device, const AtlWindConfig* cfg, AtlWindOp** op_out) {
     ATL_REQUIRE(cfg->from_height > 0 && cfg->to_height > 0, "heights must be positive");
 
   CurveTables T;
-  if (int rc = build_curve(cfg->V, cfg->POW_norm, cfg->n_knots, T)) return rc;
+  int table = -1;  // ATL_WIND_TABLE = 0..3 forces a table form (experiments, tests)
+  if (const char* e = getenv("ATL_WIND_TABLE")) table = std::max(-1, std::min(3, atoi(e)));
+  if (int rc = build_curve(cfg->V, cfg->POW_norm, cfg->n_knots, T, table)) return rc;
   const int n = T.n_knots;
   AtlWindOp* op = new AtlWindOp();
   op->device = device;

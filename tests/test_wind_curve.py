@@ -79,10 +79,10 @@ def test_shipped_turbines_use_a_lut_and_match_np_interp(name):
 def test_lattice_mode_is_chosen_for_lattice_curves():
     names = {n: eval_host(*(lambda t: (t["V"], t["POW"] / t["P"]))(resource.get_windturbineconfig(n)),
                           np.zeros(1, np.float32))[1] for n in resource.windturbines}
-    assert names["Vestas_V112_3MW"] == 3 and names["Enercon_E126_7500kW"] == 3
-    assert sum(v == 3 for v in names.values()) >= 20, names
+    assert names["Vestas_V112_3MW"] == 2 and names["Enercon_E126_7500kW"] == 2
+    assert sum(v == 2 for v in names.values()) >= 20, names
     t = resource.windturbine_smooth(resource.get_windturbineconfig("Vestas_V112_3MW"))
-    assert eval_host(t["V"], t["POW"] / t["P"], np.zeros(1, np.float32))[1] in (2, 3)  # linspace(0, 35, 72)
+    assert eval_host(t["V"], t["POW"] / t["P"], np.zeros(1, np.float32))[1] == 2  # linspace(0, 35, 72)
 
 
 def test_smoothed_curve_and_steps():
@@ -94,9 +94,9 @@ def test_smoothed_curve_and_steps():
     # cut-in step AND cut-out step AND a step at the very first knot
     for V, P, auto, general in [
         ([3, 3, 5, 12, 25, 25], [0, 0.1, 0.3, 1, 1, 0], 2, 1),       # a step at the first knot cannot fold
-        ([0, 3, 3, 12, 25, 25], [0, 0, 0.2, 1, 1, 0], 3, 1),
-        ([0, 3, 3, 12, 12, 25], [0, 0, 0.2, 0.9, 1, 1], 3, 0),      # two interior steps
-        ([0, 3, 3, 12, 12, 25, 25], [0, 0, 0.2, 0.9, 1, 1, 0], 3, 0),  # three steps: folded, else search
+        ([0, 3, 3, 12, 25, 25], [0, 0, 0.2, 1, 1, 0], 2, 1),
+        ([0, 3, 3, 12, 12, 25], [0, 0, 0.2, 0.9, 1, 1], 2, 0),      # two interior steps
+        ([0, 3, 3, 12, 12, 25, 25], [0, 0, 0.2, 0.9, 1, 1, 0], 2, 0),  # three steps: folded, else search
         ([2, 2, 2, 10, 25], [0, 0.5, 0.1, 1, 0.2], 2, 1),             # triple knot, no cut-out step
         ([0, 2.37, 9.1, 25.003], [0, 0.1, 0.9, 1.0], 1, 1),           # off-lattice knots
         ([4.0], [0.7], 0, 0),                                         # single knot: constant
@@ -151,7 +151,8 @@ def test_steps_fold_into_the_lattice_table_exactly():
         info = curve_info(V, P)
         if info["table"] not in (2, 3):
             continue
-        assert info["table"] == 3 and info["compares"] == 0, (name, info)
+        assert info["table"] == 2 and info["compares"] == 0, (name, info)
+        assert curve_info(V, P, 3)["table"] == 3  # the saturating variant qualifies too (not the default: slower)
         forced = curve_info(V, P, 2)  # mode 2 keeps the compares: the other code path stays tested
         assert forced["compares"] == info["steps"] <= 2
         folded += info["steps"] > 0
@@ -160,8 +161,9 @@ def test_steps_fold_into_the_lattice_table_exactly():
         y, _ = eval_host(V, P, x)
         y2, _ = eval_host(V, P, x, 2)
         x = np.concatenate([x, np.array([np.inf, -np.inf, 1e30, -1e30, -1.0, 400.0], np.float32)])
-        y, y2 = eval_host(V, P, x)[0], eval_host(V, P, x, 2)[0]
+        y, y2, y3 = eval_host(V, P, x)[0], eval_host(V, P, x, 2)[0], eval_host(V, P, x, 3)[0]
         np.testing.assert_allclose(y, np.interp(x.astype(np.float64), V, P), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(y3, y, rtol=0, atol=1e-5)
         np.testing.assert_allclose(y, y2, rtol=0, atol=1e-5)
     assert folded >= 20
     # a step at the very first knot cannot fold (speeds below it clamp onto it); knots that are
