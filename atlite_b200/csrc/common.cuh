@@ -442,15 +442,18 @@ __device__ __forceinline__ void reduce_slots2g(const float (&v0)[4], const float
 // tile walk by load_group_weights): the weights of a tile do not change along time, and
 // re-reading them every two steps costs as many L1 wavefronts as the fields themselves (wind).
 // Later groups (tiles with more than 4 slots, about a quarter) and the odd last slot load as before.
-__device__ __forceinline__ void load_group_weights(float4 (&wres)[4], int s_beg, const PlanDev& plan, int lane) {
+// `row_res`: the output column (bus) this lane adds the first group's sum to, -1 if none.
+__device__ __forceinline__ void load_group_weights(float4 (&wres)[4], int& row_res, int s_beg, int s_end,
+                                                   const PlanDev& plan, int lane) {
   const int f = (lane >> 2) & 3;
   const float4* wp = plan.slot_w4 + (size_t)s_beg * 32 + lane;
 #pragma unroll
   for (int i = 0; i < 4; ++i) wres[i] = __ldg(wp + (f ^ i) * 32);
+  row_res = ((lane & 3) == 0 && s_beg + f < s_end) ? __ldg(plan.slot_row + s_beg + f) : -1;
 }
 template <bool PROBE = true>
 __device__ __forceinline__ void reduce_slots2g_res(const float (&v0)[4], const float (&v1)[4],
-                                                   const float4 (&wres)[4], int s_beg, int s_end,
+                                                   const float4 (&wres)[4], int row_res, int s_beg, int s_end,
                                                    const PlanDev& plan, float* __restrict__ out_row0,
                                                    int lane) {
   const float chk = ((v0[0] + v0[1]) + (v0[2] + v0[3])) + ((v1[0] + v1[1]) + (v1[2] + v1[3]));
@@ -474,7 +477,7 @@ __device__ __forceinline__ void reduce_slots2g_res(const float (&v0)[4], const f
   const int f = (lane >> 2) & 3;
   int s = s_beg;
   const int32_t* rp = plan.slot_row + s_beg + f;
-  auto group = [&](auto&& weight) {
+  auto group = [&](auto&& weight, auto&& add) {
     float a[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -493,15 +496,17 @@ __device__ __forceinline__ void reduce_slots2g_res(const float (&v0)[4], const f
     a[0] += __shfl_xor_sync(0xffffffffu, a[1], 4);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-    if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(rp), a[0]);
+    add(a[0]);
   };
-  group([&](int i) { return wres[i]; });  // the resident group (also serves a 1-slot tile)
+  // the resident group (also serves a 1-slot tile)
+  group([&](int i) { return wres[i]; }, [&](float sum) { if (row_res >= 0) atomicAdd(my_row + row_res, sum); });
   s += 4;
   rp += 4;
 #pragma unroll 1
   for (; s_end - s >= 2; s += 4, rp += 4) {
     const float4* wp = plan.slot_w4 + (size_t)s * 32 + lane;
-    group([&](int i) { return __ldg(wp + (f ^ i) * 32); });
+    group([&](int i) { return __ldg(wp + (f ^ i) * 32); },
+          [&](float sum) { if ((lane & 3) == 0 && s + f < s_end) atomicAdd(my_row + __ldg(rp), sum); });
   }
   if (s < s_end) {  // one slot left
     const float4 w = __ldg(plan.slot_w4 + (size_t)s * 32 + lane);

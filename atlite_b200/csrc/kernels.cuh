@@ -69,7 +69,8 @@ __device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& g
   int t = t0;
   constexpr bool RES = resident_weights<Phys>::value && G == 1 && (B % 2 == 0);
   float4 wres[RES ? 4 : 1];
-  if constexpr (RES) load_group_weights(wres, s_beg, plan, lane);
+  int row_res = -1;
+  if constexpr (RES) load_group_weights(wres, row_res, s_beg, s_end, plan, lane);
   if (nfull > 0) {
 #pragma unroll
     for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
@@ -108,12 +109,12 @@ __device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& g
             reduce_slots_exact(v[j][0], v[j][1], v[j][2], v[j][3], s_beg, s_end, plan, o, lane);
             reduce_slots_exact(v[j + 1][0], v[j + 1][1], v[j + 1][2], v[j + 1][3], s_beg, s_end, plan, o + nb, lane);
           } else if constexpr (RES) {
-            reduce_slots2g_res<false>(v[j], v[j + 1], wres, s_beg, s_end, plan, o, lane);
+            reduce_slots2g_res<false>(v[j], v[j + 1], wres, row_res, s_beg, s_end, plan, o, lane);
           } else {
             reduce_slots2g<false>(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
           }
         } else if constexpr (RES) {
-          reduce_slots2g_res(v[j], v[j + 1], wres, s_beg, s_end, plan, o, lane);
+          reduce_slots2g_res(v[j], v[j + 1], wres, row_res, s_beg, s_end, plan, o, lane);
         } else if (G) {  // slots in groups of four (transposed butterfly)
           reduce_slots2g(v[j], v[j + 1], s_beg, s_end, plan, o, lane);
         } else {

@@ -14,6 +14,15 @@
 
 #include "kernels.cuh"
 
+// experiment knobs (tools/build_variants.sh)
+#ifndef ATL_SPMM_B
+#define ATL_SPMM_B 4
+#define ATL_SPMM_MINB 6
+#endif
+#ifndef ATL_SPMM_RESIDENT
+#define ATL_SPMM_RESIDENT 0
+#endif
+
 namespace atl {
 
 static thread_local std::string g_err;
@@ -119,10 +128,11 @@ struct IdentityPhys {
     float v[4];
   };
   static constexpr int kSmemFloats = 0;
-  static constexpr int kBatch = 4, kMinBlocks = 6;
+  static constexpr int kBatch = ATL_SPMM_B, kMinBlocks = ATL_SPMM_MINB;
   static constexpr bool kHasExact = false;
+  static constexpr bool kResidentWeights = ATL_SPMM_RESIDENT != 0 && VEC;
   static constexpr bool kStaged = false;
-  static constexpr int kStage = 8, kBatchStaged = kBatch, kMinBlocksStaged = kMinBlocks;
+  static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 6;
   __device__ void stage(float*) const {}
   __device__ void init(Cell&, const Geom&, const float*) const {}
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const { load4(f, tb, g, r.v); }

@@ -19,7 +19,7 @@
 #define ATL_WIND_MINB 6
 #endif
 #ifndef ATL_WIND_RESIDENT
-#define ATL_WIND_RESIDENT 0
+#define ATL_WIND_RESIDENT 1
 #endif
 
 namespace atl {
@@ -154,7 +154,7 @@ struct WindPhys {
   // NaN speeds / roughness propagate like np.interp's in every mode; the saturating table also
   // turns +-inf speeds into NaN and relies on the cold exact path for them
   static constexpr bool kHasExact = LMODE == 4;
-  static constexpr bool kResidentWeights = ATL_WIND_RESIDENT != 0;  // first slot group's weights in registers
+  static constexpr bool kResidentWeights = ATL_WIND_RESIDENT != 0 && VEC;  // first slot group's weights in registers
   static constexpr bool kSplitMask = true;  // issue-bound: interior tiles skip the out-of-grid selects
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)

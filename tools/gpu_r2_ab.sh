@@ -10,6 +10,7 @@ for lib in default build_variants/*.so; do for k in $KINDS; do for s in $SIZES; 
   if [ $lib = default ]; then timeout 120 python tools/prof_pv.py $k $s 9
   else ATL_LIB_PATH=$lib timeout 120 python tools/prof_pv.py $k $s 9; fi
 done; done; done
+if [ -n "$ATL_AB_ENV" ]; then for k in $KINDS; do for s in $SIZES; do env $ATL_AB_ENV timeout 120 python tools/prof_pv.py $k $s 9 | sed "s/\"lib\": \"default\"/\"lib\": \"default $ATL_AB_ENV\"/"; done; done; fi
 done > gpurun_out/prof_$TAG.jsonl 2>gpurun_out/prof_$TAG.err
 python - <<PY
 import json

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only timing / ncu target for the fused kernels on device-resident data.
 
-    ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat|pvsum|pvcube|windsum|windcube] [small|big|odd|oddpad|c5] [reps]
+    ATL_VARIANT=<n> ATL_TB=<tb> python tools/prof_pv.py [pv|wind|heat|spmm|pvsum|pvcube|windsum|windcube] [small|big|odd|oddpad|c5] [reps]
 
 small = 200x200x8760 -> 100 shapes (bench workload); big = 1440x720x438 -> 3000 shapes;
 odd = 201x199x8760 unpadded (scalar lanes); oddpad = the same with rows padded to 204.
@@ -61,6 +61,10 @@ elif kind in ("windsum", "windcube"):
 elif kind == "pv":
     spec = _PvSpec(ab.Dataset(f, coords=coords), ab.get_solarpanelconfig("CSi"), ab.get_orientation("latitude_optimal"))
     fn, bpc = (lambda: spec.op.reduce(plan, spec.fields)), 20
+elif kind == "spmm":  # aggregate_matrix on a pre-computed (time, y, x) field (atl_spmm)
+    out = torch.zeros((nt, nbus), dtype=torch.float32, device=dev)
+    fld = f["temperature"]
+    fn, bpc = (lambda: _lib.check(_lib.load().atl_spmm(plan.handle, fld.data_ptr(), nt, out.data_ptr(), engine._stream_ptr()))), 4
 elif kind == "wind":
     ws = _WindSpec(ab.Dataset(wf, coords=coords), ab.get_windturbineconfig("Vestas_V112_3MW"))
     fn, bpc = (lambda: ws.op.reduce(plan, ws.wnd, ws.aux)), 8
