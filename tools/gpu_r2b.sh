@@ -5,7 +5,7 @@
 TAG=${1:-r2f}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu_$TAG.txt
-for ks in "pv big" "wind big" "heat big" "pv small" "wind small"; do
+for ks in "pv big" "wind big" "heat big" "pv small" "wind small" "spmm big"; do
   set -- $ks
   kn=k_fused_reduce; [ $1 = heat ] && kn=k_heat
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s 3 -c 1 \
