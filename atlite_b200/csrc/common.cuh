@@ -250,6 +250,14 @@ __device__ __forceinline__ void load4(const double* __restrict__ f, int64_t tb,
   for (int r = 0; r < 4; ++r) o[r] = (float)ld_stream(p + r);
 }
 
+// L2 prefetch of the lane's 4 cells of a later time slab (VEC layout: the warp's 32 x 16 B are the
+// same four 128-byte lines the LDG.128 will read).  Costs no registers: this is how a kernel that
+// is at its register budget gets more bytes in flight.
+__device__ __forceinline__ void prefetch4_l2(const float* __restrict__ f, int64_t tb, const TileGeomT<true>& g) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(at_bytes(f, tb + g.boff)));
+}
+__device__ __forceinline__ void prefetch4_l2(const float* __restrict__, int64_t, const TileGeomT<false>&) {}
+
 // Store the lane's 4 per-cell values into a (y, x) plane.
 __device__ __forceinline__ void store4(float* __restrict__ plane, const GridDev& gd,
                                        const TileGeomT<false>& g, const float (&v)[4]) {

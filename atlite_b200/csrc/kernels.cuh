@@ -43,6 +43,10 @@ struct resident_weights : std::false_type {};
 template <class P>
 struct resident_weights<P, std::void_t<decltype(P::kResidentWeights)>> : std::bool_constant<P::kResidentWeights> {};
 template <class P, class = void>
+struct l2_prefetch : std::integral_constant<int, 0> {};
+template <class P>
+struct l2_prefetch<P, std::void_t<decltype(P::kL2Prefetch)>> : std::integral_constant<int, P::kL2Prefetch> {};
+template <class P, class = void>
 struct split_mask : std::false_type {};
 template <class P>
 struct split_mask<P, std::void_t<decltype(P::kSplitMask)>> : std::bool_constant<P::kSplitMask> {};
@@ -100,6 +104,14 @@ __device__ __forceinline__ void fused_v1_walk(const Phys& phys, const GridDev& g
 #pragma unroll
         for (int j = 0; j < B; ++j) phys.load(c, g, sb + j * S4, r[j]);
         sb += B * S4;
+        // kL2Prefetch = D > 0: the batch D batches past the one just requested goes to L2 now
+        if constexpr (l2_prefetch<Phys>::value > 0) {
+          constexpr int D = l2_prefetch<Phys>::value;
+          if (k + 1 + D < nfull) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) phys.prefetch(c, g, sb + ((D - 1) * B + j) * S4);
+          }
+        }
       }
 #pragma unroll
       for (int j = 0; j + 1 < B; j += 2) {

@@ -19,6 +19,9 @@
 #define ATL_SPMM_B 4
 #define ATL_SPMM_MINB 6
 #endif
+#ifndef ATL_SPMM_PREFETCH
+#define ATL_SPMM_PREFETCH 0  // L2 prefetch distance in batches (0 = off)
+#endif
 #ifndef ATL_SPMM_RESIDENT
 #define ATL_SPMM_RESIDENT 1  // measured (profiles/r2_variants_spmm.jsonl): 0.60 / 0.59 -> 0.70 / 0.67 of the HBM peak
 #endif
@@ -131,6 +134,8 @@ struct IdentityPhys {
   static constexpr int kBatch = ATL_SPMM_B, kMinBlocks = ATL_SPMM_MINB;
   static constexpr bool kHasExact = false;
   static constexpr bool kResidentWeights = ATL_SPMM_RESIDENT != 0 && VEC;
+  static constexpr int kL2Prefetch = VEC ? ATL_SPMM_PREFETCH : 0;
+  __device__ void prefetch(const Cell&, const Geom& g, int64_t tb) const { prefetch4_l2(f, tb, g); }
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 6;
   __device__ void stage(float*) const {}

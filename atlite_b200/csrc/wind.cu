@@ -18,6 +18,9 @@
 #define ATL_WIND_B 2
 #define ATL_WIND_MINB 6
 #endif
+#ifndef ATL_WIND_PREFETCH
+#define ATL_WIND_PREFETCH 0  // L2 prefetch distance in batches (0 = off)
+#endif
 #ifndef ATL_WIND_RESIDENT
 #define ATL_WIND_RESIDENT 1
 #endif
@@ -155,6 +158,7 @@ struct WindPhys {
   // turns +-inf speeds into NaN and relies on the cold exact path for them
   static constexpr bool kHasExact = LMODE == 4;
   static constexpr bool kResidentWeights = ATL_WIND_RESIDENT != 0 && VEC;  // first slot group's weights in registers
+  static constexpr int kL2Prefetch = VEC ? ATL_WIND_PREFETCH : 0;
   static constexpr bool kSplitMask = true;  // issue-bound: interior tiles skip the out-of-grid selects
   static constexpr bool kStaged = false;
   static constexpr int kStage = 8, kBatchStaged = 4, kMinBlocksStaged = 5;  // staged: 4 register sets, 5 CTAs (smem)
@@ -169,6 +173,10 @@ struct WindPhys {
   __device__ void load(const Cell&, const Geom& g, int64_t tb, Raw& r) const {
     load4(wnd, tb, g, r.w);
     if (METHOD != ATL_WIND_NONE) load4(aux, tb, g, r.a);
+  }
+  __device__ void prefetch(const Cell&, const Geom& g, int64_t tb) const {
+    prefetch4_l2(wnd, tb, g);
+    if (METHOD != ATL_WIND_NONE) prefetch4_l2(aux, tb, g);
   }
   // np.interp for the lane's 4 values at once.
   template <bool EXACT = false>
