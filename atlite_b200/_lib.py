@@ -247,9 +247,11 @@ _lib = None
 
 def load():
     """Load the shared library (once).  Raises if it has not been built."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is not None:
         return _lib
+    if os.environ.get("ATL_LIB_PATH"):  # another build of the same library (A/B experiments, tools/build_variants.sh)
+        LIB_PATH = os.path.abspath(os.environ["ATL_LIB_PATH"])
     if not os.path.exists(LIB_PATH):
         raise AtlError(
             f"{LIB_PATH} not found: build the CUDA library first "

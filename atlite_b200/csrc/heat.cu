@@ -7,6 +7,10 @@
 
 #include "kernels.cuh"
 
+#ifndef ATL_HEAT_PREFETCH
+#define ATL_HEAT_PREFETCH 0  // experiment knob (tools/build_variants.sh): L2 prefetch of the next day
+#endif
+
 namespace atl {
 
 struct HeatParams {
@@ -39,13 +43,21 @@ __device__ __forceinline__ void heat_load_chunk(const HeatParams& hp, const Tile
 
 // daily mean + degree-day formula for the lane's 4 cells of day d.  The loads of
 // chunk k+1 are issued before chunk k is accumulated (register double buffer).
+// `s_last` = number of steps of the slab (L2 prefetch of the NEXT day's steps stops there).
 template <bool VEC>
 __device__ __forceinline__ void heat_day(const HeatParams& hp, const TileGeomT<VEC>& g, int d,
-                                         float (&v)[4]) {
+                                         float (&v)[4], int s_last) {
   const int s0 = __ldg(hp.day_start + d) - hp.base, s1 = __ldg(hp.day_start + d + 1) - hp.base;
   float sum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
   float x[HEAT_UNROLL][4], y[HEAT_UNROLL][4];
   heat_load_chunk(hp, g, s0, s1, x);
+#if ATL_HEAT_PREFETCH
+  {  // the next day's slabs go to L2 while this day is summed (no registers: the kernel is latency-bound)
+    const int e = min(s1 + (s1 - s0), s_last);
+#pragma unroll 4
+    for (int s = s1; s < e; ++s) prefetch4_l2(hp.temp, (int64_t)s * (hp.S * 4), g);
+  }
+#endif
 #pragma unroll 1
   for (int s = s0; s < s1; s += HEAT_UNROLL) {
     const bool more = s + HEAT_UNROLL < s1;
@@ -96,6 +108,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 6)  // latency-bound (ncu: long_s
   }
   const TileGeomT<VEC> g = make_geom<VEC>(tile, lane, gd);
   const int d0 = blockIdx.y * db, d1 = min(n_days, d0 + db);
+  const int s_last = ATL_HEAT_PREFETCH ? __ldg(hp.day_start + n_days) - hp.base : 0;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
   float v[4];
   if (MODE == 0) {
@@ -109,7 +122,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 6)  // latency-bound (ncu: long_s
     for (int dc = d0; dc < d1; dc += HEAT_STAGE) {
       const int n = min(HEAT_STAGE, d1 - dc);
       for (int k = 0; k < n; ++k) {
-        heat_day(hp, g, dc + k, v);
+        heat_day(hp, g, dc + k, v, s_last);
         zero_invalid(g, v);
         stage_store1<HEAT_STAGE>(stage, lane, k, v);
       }
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 6)  // latency-bound (ncu: long_s
     return;
   }
   for (int d = d0; d < d1; ++d) {
-    heat_day(hp, g, d, v);
+    heat_day(hp, g, d, v, s_last);
     if (MODE == 1) {
       store4(out + (int64_t)d * gd.S_out, gd, g, v);
     } else {

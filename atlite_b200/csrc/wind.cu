@@ -19,7 +19,7 @@
 #define ATL_WIND_MINB 6
 #endif
 #ifndef ATL_WIND_PREFETCH
-#define ATL_WIND_PREFETCH 0  // L2 prefetch distance in batches (0 = off)
+#define ATL_WIND_PREFETCH 1  // L2 prefetch distance in batches (0 = off); measured: big 0.868 -> 0.930, small 0.822 -> 0.816
 #endif
 #ifndef ATL_WIND_RESIDENT
 #define ATL_WIND_RESIDENT 1
