@@ -37,9 +37,11 @@ elif size in ("odd", "oddpad"):  # nx % 4 != 0: SCALAR lane layout / rows padded
     nx, ny, nt, nbus, x0, y0 = 201, 199, 8760, 100, 0.0, 30.0
 else:
     nx, ny, nt, nbus, x0, y0 = 1440, 720, 432, 3000, -180.0, -90.0
+nt = int(os.environ.get("ATL_NT", nt))  # e.g. ATL_NT=8760 with size big: the full year (wind / heat / spmm only)
 x, y = syn.make_coords(nx, ny, x0, y0, *((0.05, 0.05) if size == "c5" else ()))
 tm = syn.make_time(nt + 24 * 170)[24 * 170:] if size == "big" else syn.make_time(nt)
-f = syn.make_pv_fields_device(tm, x, y, dev, seed=7)
+need = None if kind.startswith("pv") else (["temperature"] if kind in ("heat", "spmm") else [])
+f = syn.make_pv_fields_device(tm, x, y, dev, seed=7, **({} if need is None else {"names": need})) if need != [] else {}
 wf = syn.make_wind_fields_device(nt, ny, nx, dev, seed=7) if kind.startswith("wind") else None
 pitch = nx
 if size == "oddpad":  # what Cutout.to_device() does
@@ -83,7 +85,7 @@ torch.cuda.synchronize()
 ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
 cts = float(nx) * ny * nt
 print(json.dumps({"kind": kind, "size": size, "variant": os.environ.get("ATL_VARIANT", "0"),
-                  "tb": os.environ.get("ATL_TB", "auto"),
+                  "tb": os.environ.get("ATL_TB", "auto"), "nt": nt,
                   "lib": os.path.basename(os.environ.get("ATL_LIB_PATH", "")) or "default", "ms": round(ms, 4),
                   "cell_ts_per_s": cts / ms * 1e3, "GBs": round(cts * (bpc + out_b) / ms / 1e6, 1),
                   "frac_6573": round(cts * (bpc + out_b) / ms / 1e6 / 6573.5, 4),
