@@ -26,8 +26,9 @@ KERNELS = {
     "pv_fused_era5_inputs_runtime_switches (mode 4)": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi4ELb1EEELi2ELi4ELi1"),
     "pv_fused_general (mode 0)": ("pv.o", r"k_fused_reduce_v1INS_6PvPhysILi0ELb1EEELi1ELi4ELi1"),
     "pv_fused_staged_variant": ("pv.o", r"k_fused_reduceINS_6PvPhysILi1ELb1EEELi2ELi5ELi8"),
-    "wind_fused_log_lattice1 (shuffle reduce)": ("wind.o", r"k_fused_reduce_v1INS_8WindPhysILb1ELi1ELi2EEELi2ELi6ELi1"),
-    "wind_fused_staged_variant": ("wind.o", r"k_fused_reduceINS_8WindPhysILb1ELi1ELi2EEELi4ELi5ELi8"),
+    "wind_fused_log_lattice_folded (shuffle reduce, resident weights, L2 prefetch)": ("wind.o", r"k_fused_reduce_v1INS_8WindPhysILb1ELi1ELi1EEELi2ELi6ELi1"),
+    "wind_fused_log_saturating_table (ATL_WIND_TABLE=3)": ("wind.o", r"k_fused_reduce_v1INS_8WindPhysILb1ELi1ELi4EEELi2ELi6ELi1"),
+    "wind_fused_staged_variant": ("wind.o", r"k_fused_reduceINS_8WindPhysILb1ELi1ELi1EEELi4ELi5ELi8"),
     "heat_fused (staged reduce)": ("heat.o", r"k_heatILi0ELb1"),
     "spmm_fused": ("plan.o", r"k_fused_reduce_v1INS_12IdentityPhysILb1EEELi4"),
     "pv_cells_timesum": ("pv.o", r"7k_cellsINS_6PvPhysILi1ELb1EEELi1"),
@@ -44,6 +45,7 @@ CLASSES = [
     ("shared_store", r"^STS"),
     ("const_uniform", r"^(LDC|LDCU|ULDC|UMOV|UIADD3|ULEA|UISETP|UIMAD|USHF|ULOP3|S2UR|S2R|R2UR|UPRMT|USEL|UFLO|UPOPC|CS2R)"),
     ("shuffle_vote", r"^(SHFL|VOTE|MATCH|REDUX)"),
+    ("l2_prefetch", r"^CCTL\.E\.PF2"),
     ("control", r"^(BRA|BSSY|BSYNC|EXIT|CALL|RET|WARPSYNC|BAR|NOP|YIELD|BREAK|BMOV|DEPBAR|ERRBAR|MEMBAR|CCTL|NANOSLEEP|BPT|KILL|RPCMOV|ENDCOLLECTIVE)"),
     ("local_mem", r"^(LDL|STL)"),
 ]
