@@ -103,6 +103,40 @@ def test_wind_interp_edges():
     assert_parity(got, want, cap_of(m), what="NaN routing")
 
 
+@pytest.mark.parametrize("table", [0, 1, 2, 3])
+def test_wind_every_table_form(monkeypatch, table):
+    """ATL_WIND_TABLE forces the power-curve table form (binary search, general LUT, lattice LUT with
+    compares, saturating lattice LUT): each one is np.interp -- at the knots, one float either side, beyond
+    the ends, for +-inf (the saturating table serves those through the cold exact path) and NaN -- in the
+    per-cell kernel and in the fused reduce (resident weights, several slot groups per tile)."""
+    monkeypatch.setenv("ATL_WIND_TABLE", str(table))
+    nx, ny, nt = 132, 6, 5
+    ds = syn.make_dataset(nx, ny, nt, kinds=("wind",))
+    t = dict(ab.get_windturbineconfig("Vestas_V112_3MW"), hub_height=100)  # no extrapolation
+    w = ds.raw("wnd100m")
+    f32 = np.float32
+    specials = np.array([0.0, 2.0, np.nextafter(f32(3.0), f32(0)), 3.0, np.nextafter(f32(3.0), f32(9)), 12.999999, 13.0,
+                         np.nextafter(f32(25.0), f32(0)), 25.0, np.nextafter(f32(25.0), f32(26)), 30.0, 1e6, 1e30,
+                         np.inf, -np.inf, -1.0, -1e30, 1e-30], dtype=np.float32)
+    w[0, 0, : len(specials)] = specials
+    w[2, 3, 40: 40 + len(specials)] = specials
+    c = ab.Cutout(data=ds).to_device()
+    with np.errstate(invalid="ignore"):
+        got = np.asarray(c.wind(t, aggregate_time=None).values)
+        want = O.convert_wind(oracle_ds(ds), t)
+    assert_parity(got, want, what=f"table {table}: per-cell")
+    assert got[0, 0, 8] == 0.0 and got[0, 0, 7] == 1.0 and got[0, 0, 13] == 0.0 and got[0, 0, 14] == 0.0
+    w[1, 2, 3] = np.nan
+    m = syn.make_shapes(nx, ny, 40)  # many small shapes: tiles with more than one slot group
+    for hub in (100, 80):
+        tt = dict(t, hub_height=hub)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            got = bt(ab.Cutout(data=ds).wind(tt, matrix=m, aggregate_time=None))
+            want = O.convert_and_aggregate(oracle_ds(ds), O.convert_wind, matrix=m, aggregate_time=None, turbine=tt)
+        assert np.isnan(want[1]).any() and not np.isnan(want[0]).any()
+        assert_parity(got, want, cap_of(m), what=f"table {table}: reduce, hub {hub}")
+
+
 def test_wind_interp_binary_search_fallback():
     """Knots too close for the uniform-bucket LUT -> branch-free binary search path."""
     ds = syn.make_dataset(40, 8, 6, kinds=("wind",))
