@@ -641,6 +641,19 @@ def wind_heat_sharded(comm, shard, plan, x, y, time_axis, args, peak):
     if shard is not None:
         check_gather(comm, r, sum(counts[:rank]), sum(counts[:rank + 1]))
     out["wind_c2_1440x720x8760_3000"] = entry(r, hi - lo, 8)
+    if world == 1:
+        # the same kernel on a quarter-year slab (what each rank of a 4-GPU run processes): the 72.6 GB
+        # full-year launch sits under the power cap, shorter slabs do not (profiles/r2_wind_slab_length.jsonl)
+        try:
+            nq = min(2190, hi - lo)
+            wq, aq = ws.wnd[:nq], ws.aux[:nq]
+            ms, _ = _timeit(torch, lambda: ws.op.reduce(plan, wq, aq), 7)
+            out["wind_c2_quarter_year_slab_1440x720x2190_3000"] = {
+                "steps": nq, "kernel_ms": ms, "cell_ts_per_s": S * nq / ms * 1e3,
+                "achieved_GBs": S * nq * 8 / ms / 1e6, "frac_of_hbm_peak": S * nq * 8 / ms / 1e6 / peak}
+            del wq, aq
+        except Exception as e:  # noqa: BLE001 -- an extra data point must never cost the bench line
+            out["wind_c2_quarter_year_slab_1440x720x2190_3000"] = {"error": repr(e)[:200]}
     del ws, r, f
     torch.cuda.empty_cache()
 
