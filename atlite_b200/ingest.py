@@ -64,12 +64,11 @@ class ChunkedVariable:
         lo, hi = int(lo), int(hi)
         nt, (_, ny, nx) = hi - lo, self.shape
         raw_dt = self.dtype.newbyteorder("=")
-        keep = None
         if pinned:
             import torch
 
             t = torch.empty((nt, ny, nx), dtype=getattr(torch, raw_dt.name), pin_memory=True)
-            out, keep = t.numpy(), t
+            out = t.numpy()
         else:
             out = np.empty((nt, ny, nx), dtype=raw_dt)
         if nt > 0:
@@ -99,17 +98,13 @@ class ChunkedVariable:
                 res *= np.float32(self.scale_factor)
             if self.add_offset is not None:
                 res += np.float32(self.add_offset)
-        if keep is not None and res is out:
-            _PINNED[id(res)] = keep  # the tensor owns the page-locked memory
-        return res
+        return res  # a page-locked `out` stays alive through the array's base (the tensor's storage)
 
     def _covers(self, orig, lo, hi):
         nty = -(-(min(hi, self.shape[0]) - (lo // self.chunk[0]) * self.chunk[0]) // self.chunk[0])
         want = nty * -(-self.shape[1] // self.chunk[1]) * -(-self.shape[2] // self.chunk[2])
         return len(orig) >= want
 
-
-_PINNED = {}
 
 
 def _lazy(variables, coords, static, attrs, time_chunk, pinned=False):
