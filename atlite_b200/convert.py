@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import logging
 import re
+import types
 import warnings
 from pathlib import Path
 
@@ -656,7 +657,12 @@ def _run_partitioned(ds, spec_cls, convert_kwds, parts, run, workers_per_device)
     def work(lo, hi, dev):
         torch.cuda.set_device(dev)  # per-thread current device
         spec = spec_cls(_time_slice(ds, lo, hi), **convert_kwds)
-        return run(spec, dev), spec
+        res = run(spec, dev)
+        # only the labels travel on: the spec owns the part's input (up to PART_BYTES of decoded
+        # fields, or its device copy), which must not outlive the part -- a lazily loaded cutout
+        # larger than the host memory is the point of converting part by part
+        return res, types.SimpleNamespace(units=getattr(spec, "units", None), name=spec.name,
+                                          time_labels=spec.time_labels)
 
     try:
         futs = [pools[d].submit(work, lo, hi, d) for lo, hi, d in parts]
