@@ -191,3 +191,56 @@ def test_time_shard_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_run_partitioned_returns_results_in_order_and_releases_part_inputs(monkeypatch):
+    """The partitioned runner (convert._run_partitioned) on a fake device layer: results come back in time
+    order with the labels the orchestration needs, and a part's input dataset does not outlive the part --
+    otherwise a lazily loaded cutout larger than the host memory would pile up in RAM part by part."""
+    import gc
+    import types
+    import weakref
+
+    import numpy as np
+
+    from atlite_b200 import convert, engine
+
+    fake_torch = types.SimpleNamespace(cuda=types.SimpleNamespace(set_device=lambda d: None))
+    monkeypatch.setattr(engine, "_torch", lambda: fake_torch)
+    alive = []
+
+    class Part:  # what LazyDataset.isel_time hands out: owns the decoded arrays of one part
+        def __init__(self, lo, hi):
+            self.lo, self.hi, self.payload = lo, hi, np.zeros(1000)
+
+    class Source:
+        lazy = True
+
+        def isel_time(self, lo, hi):
+            p = Part(lo, hi)
+            alive.append(weakref.ref(p))
+            return p
+
+    peak = []
+
+    class Spec:
+        name, units = "thing", "MW"
+
+        def __init__(self, part, scale=1.0):
+            self.part, self.scale = part, scale
+            self.time_labels = np.arange(part.lo, part.hi)
+
+    def run(spec, dev):
+        gc.collect()
+        peak.append(sum(r() is not None for r in alive))
+        return np.full((spec.part.hi - spec.part.lo, 2), dev * 100.0 + spec.part.lo) * spec.scale
+
+    parts = [(0, 3, 0), (3, 5, 1), (5, 9, 0), (9, 10, 1)]
+    out = convert._run_partitioned(Source(), Spec, dict(scale=2.0), parts, run, 1)
+    assert [v.shape[0] for v, _ in out] == [3, 2, 4, 1]
+    assert [float(v[0, 0]) for v, _ in out] == [0.0, 206.0, 10.0, 218.0]
+    assert np.array_equal(np.concatenate([m.time_labels for _, m in out]), np.arange(10))
+    assert out[0][1].name == "thing" and out[0][1].units == "MW"
+    gc.collect()
+    assert not any(r() is not None for r in alive), "part inputs must be released"
+    assert max(peak) <= 2  # one part per device thread at a time (two devices here)
