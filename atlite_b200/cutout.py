@@ -12,6 +12,9 @@ calls read them straight from HBM.
 
 from __future__ import annotations
 
+from collections import namedtuple
+from pathlib import Path
+
 import numpy as np
 import pandas as pd
 
@@ -20,6 +23,19 @@ from .labelled import HAVE_XARRAY, Dataset, make_dataarray
 
 if HAVE_XARRAY:  # pragma: no cover
     import xarray as xr
+
+
+_AffineTuple = namedtuple("Affine", "a b c d e f")
+
+
+def _affine(a, b, c, d, e, f):
+    """x = a*col + b*row + c, y = d*col + e*row + f (rasterio.Affine when rasterio is there)."""
+    try:
+        from rasterio import Affine  # pragma: no cover
+
+        return Affine(a, b, c, d, e, f)  # pragma: no cover
+    except ImportError:
+        return _AffineTuple(float(a), float(b), float(c), float(d), float(e), float(f))
 
 
 class _Registered:
@@ -129,6 +145,28 @@ class Cutout:
             raise RuntimeError("no CUDA device visible (atlite_b200 has no CPU fallback)")
         return d
 
+    # ---- identity (cutout.py:211-256)
+    @property
+    def name(self):
+        """Stem of the cutout's path (cutout.py:212-216); None for a cutout built from data only."""
+        return None if self.path is None else Path(self.path).stem
+
+    @property
+    def module(self):
+        return getattr(self.data, "attrs", {}).get("module")  # cutout.py:219-223
+
+    @property
+    def chunks(self):
+        """{dim: size} from the ``chunksize_*`` attributes of a prepared cutout (cutout.py:240-249)."""
+        attrs = getattr(self.data, "attrs", {})
+        chunks = {k[len("chunksize_"):]: v for k, v in attrs.items() if k.startswith("chunksize_")}
+        return chunks or None
+
+    @property
+    def dt(self):
+        """Time resolution as a pandas frequency string (cutout.py:328-332)."""
+        return pd.infer_freq(pd.DatetimeIndex(np.asarray(self.coords["time"])))
+
     # ---- geometry (cutout.py:300-376)
     @property
     def coords(self):
@@ -157,6 +195,108 @@ class Cutout:
         x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
         return np.array([x.min() - self.dx / 2, x.max() + self.dx / 2,
                          y.min() - self.dy / 2, y.max() + self.dy / 2])
+
+    @property
+    def bounds(self):
+        """(x, y, X, Y) of the covered area (cutout.py:277-281)."""
+        return self.extent[[0, 2, 1, 3]]
+
+    @property
+    def transform(self):
+        """Affine coefficients (a, b, c, d, e, f) of the grid, cell (col, row) -> (x, y) of its lower-left
+        corner (cutout.py:284-295; a ``rasterio.Affine`` when rasterio is installed)."""
+        x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
+        return _affine(self.dx, 0.0, x[0] - self.dx / 2, 0.0, self.dy, y[0] - self.dy / 2)
+
+    @property
+    def transform_r(self):
+        """The same with the y axis reversed (cutout.py:298-309)."""
+        x, y = np.asarray(self.coords["x"]), np.asarray(self.coords["y"])
+        return _affine(self.dx, 0.0, x[0] - self.dx / 2, 0.0, -self.dy, y[-1] + self.dy / 2)
+
+    def area(self, crs=None):
+        """Area per grid cell in the units of the cutout's CRS (cutout.py:539-562: ``grid.to_crs(crs).area``
+        with crs = the cutout's own -- for a regular grid every cell is dx * dy).  Another CRS needs
+        a reprojection library, which is outside this package."""
+        if crs is not None and str(crs).upper().replace("EPSG:", "") != str(self.crs).upper().replace("EPSG:", ""):
+            raise NotImplementedError(f"area(crs={crs!r}): reprojection is outside this package; cutout CRS is {self.crs}")
+        ny, nx = self.shape
+        return make_dataarray(np.full((ny, nx), abs(self.dx * self.dy)), ("y", "x"),
+                              {"y": np.asarray(self.coords["y"]), "x": np.asarray(self.coords["x"])})
+
+    def uniform_density_layout(self, capacity_density, crs=None):
+        """capacity_density * area per cell (cutout.py:570-589)."""
+        return capacity_density * self.area(crs)
+
+    def layout_from_capacity_list(self, data, col="Capacity"):
+        """(y, x) capacity layout from a table with columns ``x``, ``y`` and ``col``: every entry is
+        added to its nearest grid cell (cutout.py:600-651).  Follows the reference's index
+        arithmetic step by step -- searchsorted(left), clip, "move to best distance" with
+        ``x_grid[ix - 1]`` -- including its wrap-around for entries at or left of the first
+        coordinate (ix - 1 = -1 there), so that layouts agree cell by cell; NaN capacities count
+        as 0 (pandas' groupby sum)."""
+        xg, yg = np.asarray(self.coords["x"], dtype=np.float64), np.asarray(self.coords["y"], dtype=np.float64)
+        px, py = np.asarray(data["x"], dtype=np.float64), np.asarray(data["y"], dtype=np.float64)
+        cap = np.nan_to_num(np.asarray(data[col], dtype=np.float64), nan=0.0)
+        ix = np.clip(np.searchsorted(xg, px, side="left"), 0, len(xg) - 1)
+        iy = np.clip(np.searchsorted(yg, py, side="left"), 0, len(yg) - 1)
+        ix = ix - (px - xg[ix - 1] < xg[ix] - px)
+        iy = iy - (py - yg[iy - 1] < yg[iy] - py)
+        ok = ~(np.isnan(px) | np.isnan(py))  # groupby drops NaN keys
+        lay = np.zeros(self.shape)
+        np.add.at(lay, (iy[ok] % len(yg), ix[ok] % len(xg)), cap[ok])
+        return make_dataarray(lay, ("y", "x"), {"y": yg, "x": xg})
+
+    def sel(self, path=None, bounds=None, buffer=0, **kwargs):
+        """Sub-cutout (cutout.py:378-413): ``bounds`` = (x1, y1, x2, y2), widened by ``buffer``;
+        further keyword arguments select by coordinate labels with inclusive slices, e.g.
+        ``time=slice("2013-01", "2013-03")``.  Host-resident data is sliced as views, lazily
+        loaded data stays lazy."""
+        if bounds is not None:
+            x1, y1, x2, y2 = (float(v) for v in np.asarray(bounds, dtype=np.float64).ravel())
+            if buffer > 0:  # box(*bounds).buffer(buffer).bounds
+                x1, y1, x2, y2 = x1 - buffer, y1 - buffer, x2 + buffer, y2 + buffer
+            kwargs.update(x=slice(x1, x2), y=slice(y1, y2))
+        return Cutout(path, data=self.data.sel(**kwargs), devices=self._devices)
+
+    def equals(self, other):
+        """Same coordinates and variables, the path aside (cutout.py:591-598)."""
+        if not isinstance(other, Cutout):
+            return NotImplemented
+        if hasattr(self.data, "equals") and not isinstance(self.data, Dataset):
+            return bool(self.data.equals(other.data))
+        a, b = self.data, other.data
+        if not isinstance(b, Dataset) or getattr(a, "lazy", False) or getattr(b, "lazy", False):
+            return False
+        if set(a.keys()) != set(b.keys()) or set(a.coords) != set(b.coords):
+            return False
+        if any(not np.array_equal(np.asarray(a.coords[k]), np.asarray(b.coords[k])) for k in a.coords):
+            return False
+        host = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)  # noqa: E731
+        return all(a.dims_of(k) == b.dims_of(k) and np.array_equal(host(a.raw(k)), host(b.raw(k)), equal_nan=True)
+                   for k in a.keys())
+
+    def to_file(self, fn=None):
+        """Save the cutout (cutout.py:453-465): NetCDF through xarray when the data is an xarray
+        dataset, else this package's chunk container (zlib + byte shuffle, ``ingest.write_chunked``),
+        which ``Cutout(path)`` opens lazily."""
+        fn = self.path if fn is None else fn
+        if fn is None:
+            raise ValueError("no file name: the cutout has no path")
+        if not isinstance(self.data, Dataset):
+            self.data.to_netcdf(fn)
+            return
+        from . import ingest
+
+        d = self.data
+        if getattr(d, "lazy", False):
+            d = d.isel_time(0, len(np.asarray(d.coords["time"])))
+        host = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)  # noqa: E731
+        nx = len(np.asarray(d.coords["x"]))
+        var3 = {k: host(d.raw(k))[..., :nx] for k in d.keys() if len(d.dims_of(k)) == 3}
+        static = {k: host(d.raw(k))[..., :nx] for k in d.keys() if len(d.dims_of(k)) == 2}
+        ingest.write_chunked(fn, var3, {k: np.asarray(v) for k, v in d.coords.items()}, static=static,
+                             attrs=dict(getattr(d, "attrs", {})))
 
     @property
     def grid(self):

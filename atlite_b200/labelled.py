@@ -273,6 +273,55 @@ class Dataset:
             out._vars[name] = (dims, arr[lo:hi] if dims and dims[0] == "time" else arr)
         return out
 
+    # ---- selection (what Cutout.sel needs of xarray.Dataset.sel: cutout.py:378-413)
+    _AXIS_COORDS = {"time": ("time",), "y": ("y", "lat"), "x": ("x", "lon")}
+
+    def _positions(self, indexers):
+        """{dim: slice of integer positions} from integer slices (isel)."""
+        out = {}
+        for d, sl in indexers.items():
+            if d not in self._AXIS_COORDS:
+                raise KeyError(f"cannot select along {d!r}; dimensions are time, y, x")
+            if not isinstance(sl, slice):
+                raise TypeError(f"{d}: pass a slice (single labels would drop the dimension a cutout needs)")
+            out[d] = slice(*sl.indices(len(self.coords[d])))
+            if out[d].step != 1:
+                raise ValueError(f"{d}: only contiguous selections keep the regular grid")
+        return out
+
+    def _sel_coords(self, pos):
+        coords = {}
+        for k, v in self.coords.items():
+            dim = next((d for d, names in self._AXIS_COORDS.items() if k in names), None)
+            coords[k] = v[pos[dim]] if dim in pos and np.ndim(v) == 1 else v
+        return coords
+
+    def isel(self, **indexers):
+        """Contiguous positional selection along time / y / x (views of host arrays and of time
+        slices of device tensors).  A device-resident cutout can only be cut along time: its
+        rows may be padded to the kernels' pitch -- select before ``to_device()``."""
+        pos = self._positions(indexers)
+        out = Dataset(coords=self._sel_coords(pos), attrs=self.attrs)
+        for name, (dims, arr) in self._vars.items():
+            if any(d in pos and d in dims for d in ("y", "x")) and not isinstance(arr, np.ndarray):
+                raise NotImplementedError("spatial selection of a device-resident cutout: select first, then to_device()")
+            out._vars[name] = (dims, arr[tuple(pos.get(d, slice(None)) for d in dims)])
+        return out
+
+    def sel(self, **indexers):
+        """Label-based selection with INCLUSIVE slice ends (xarray / pandas semantics) along
+        time / y / x, e.g. ``ds.sel(x=slice(5, 15), y=slice(47, 55), time=slice("2013-01", "2013-02"))``."""
+        pos = {}
+        for d, sl in indexers.items():
+            if d not in self._AXIS_COORDS:
+                raise KeyError(f"cannot select along {d!r}; dimensions are time, y, x")
+            idx = self.coords[d] if isinstance(self.coords[d], pd.Index) else pd.Index(self.coords[d])
+            if not isinstance(sl, slice):
+                sl = slice(sl, sl)
+            loc = idx.slice_indexer(sl.start, sl.stop)
+            pos[d] = slice(loc.start, loc.stop)
+        return self.isel(**pos)
+
     def __getitem__(self, name):
         if name in self._vars:
             dims, arr = self._vars[name]
@@ -352,6 +401,21 @@ class LazyDataset(Dataset):
             n = len(self.coords["time"])
             return self.isel_time(0, n)[name]
         return super().__getitem__(name)
+
+    def isel(self, **indexers):
+        """Still lazy: the loaders of the selection read [lo + t0, hi + t0) and crop y / x."""
+        pos = self._positions(indexers)
+        t0 = pos["time"].start if "time" in pos else 0
+        ys, xs = pos.get("y", slice(None)), pos.get("x", slice(None))
+
+        def cropped(load):
+            return lambda lo, hi: np.asarray(load(lo + t0, hi + t0))[:, ys, xs]
+
+        static = {n: (dims, arr[tuple(pos.get(d, slice(None)) for d in dims)]) for n, (dims, arr) in self._vars.items()}
+        out = LazyDataset({n: cropped(ld) for n, ld in self._loaders.items()}, self._sel_coords(pos),
+                          attrs=self.attrs, time_chunk=self.time_chunk, dtypes=self._dtypes)
+        out._vars.update(static)
+        return out
 
     def isel_time(self, lo, hi):
         out = Dataset(coords={k: (v[lo:hi] if k == "time" else v) for k, v in self.coords.items()},
