@@ -176,6 +176,7 @@ class CspFields(C.Structure):
 _P = C.c_void_p
 _SIGNATURES = {
     "atl_abi_version": (C.c_int, []),
+    "atl_hash128": (C.c_int, [_P, C.c_int64, C.c_uint64, _P]),
     "atl_last_error": (C.c_char_p, []),
     "atl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "atl_launch_count": (C.c_int64, []),

@@ -156,6 +156,49 @@ using namespace atl;
 extern "C" {
 
 int atl_abi_version(void) { return ATL_ABI_VERSION; }
+
+int atl_hash128(const void* data, int64_t nbytes, uint64_t seed, uint64_t out[2]) {
+  ATL_REQUIRE(out && nbytes >= 0 && (data || nbytes == 0), "bad arguments");
+  auto rotl = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
+  auto fmix = [](uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+  };
+  const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+  uint64_t h1 = seed, h2 = seed ^ 0x9e3779b97f4a7c15ULL;
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  const int64_t nblocks = nbytes / 16;
+  for (int64_t i = 0; i < nblocks; ++i) {
+    uint64_t k1, k2;
+    std::memcpy(&k1, p + 16 * i, 8);
+    std::memcpy(&k2, p + 16 * i + 8, 8);
+    k1 *= c1; k1 = rotl(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = rotl(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+    k2 *= c2; k2 = rotl(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = rotl(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+  }
+  unsigned char tail[16] = {0};
+  const int64_t rest = nbytes - 16 * nblocks;
+  if (rest > 0) {
+    std::memcpy(tail, p + 16 * nblocks, (size_t)rest);
+    uint64_t k1, k2;
+    std::memcpy(&k1, tail, 8);
+    std::memcpy(&k2, tail + 8, 8);
+    k2 *= c2; k2 = rotl(k2, 33); k2 *= c1; h2 ^= k2;
+    k1 *= c1; k1 = rotl(k1, 31); k1 *= c2; h1 ^= k1;
+  }
+  h1 ^= (uint64_t)nbytes; h2 ^= (uint64_t)nbytes;
+  h1 += h2; h2 += h1;
+  h1 = fmix(h1); h2 = fmix(h2);
+  h1 += h2; h2 += h1;
+  out[0] = h1;
+  out[1] = h2;
+  return ATL_OK;
+}
 int atl_set_deterministic(int on) {
   const int prev = g_deterministic ? 1 : 0;
   g_deterministic = on != 0;

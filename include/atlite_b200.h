@@ -66,6 +66,11 @@ extern "C" {
 int atl_abi_version(void);
 const char* atl_last_error(void);
 int atl_device_count(int* count_out);
+/* Host-only: 128-bit content hash of a byte range (MurmurHash3-style mixing, ~5 GB/s).  The
+ * Python layer keys its plan cache on it: the reference rebuilds nothing per call, here a
+ * matrix that is already planned must be recognised faster than it could be re-planned
+ * (convert.py:213-249 hands over a fresh scipy matrix every call). */
+int atl_hash128(const void* data, int64_t nbytes, uint64_t seed, uint64_t out[2]);
 /* Deterministic reduce mode (default off, or env ATL_DETERMINISTIC=1): the fused
  * kernels accumulate every (tile, bus) partial in a private slot and a second
  * kernel sums each bus's slots in a fixed order -> bitwise-repeatable results at

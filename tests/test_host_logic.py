@@ -244,3 +244,45 @@ def test_run_partitioned_returns_results_in_order_and_releases_part_inputs(monke
     gc.collect()
     assert not any(r() is not None for r in alive), "part inputs must be released"
     assert max(peak) <= 2  # one part per device thread at a time (two devices here)
+
+
+def test_matrix_digest_is_a_content_key():
+    """The plan-cache key (engine.matrix_digest over atl_hash128): equal for equal matrices, different
+    for any changed value, index, dtype or shape, and for every one-bit / one-byte-length change of
+    the hashed bytes."""
+    import ctypes as C
+
+    import numpy as np
+    import scipy.sparse as sp
+
+    from atlite_b200 import _lib, engine
+
+    m = sp.random(40, 900, density=0.05, random_state=3, format="csr")
+    d = engine.matrix_digest(m)
+    assert engine.matrix_digest(m.copy()) == d and engine.matrix_digest(sp.csr_matrix(m.toarray())) == d
+    for change in ("data", "indices", "dtype", "shape"):
+        m2 = m.copy()
+        if change == "data":
+            m2.data[17] = np.nextafter(m2.data[17], 2.0)
+        elif change == "indices":
+            m2.indices[5], m2.indices[6] = m2.indices[6], m2.indices[5]
+        elif change == "dtype":
+            m2.data = m2.data.astype(np.float32)
+        else:
+            m2 = sp.csr_matrix((m.data, m.indices, m.indptr), shape=(40, 901))
+        assert engine.matrix_digest(m2) != d, change
+
+    def h(x, seed=0):
+        out = (C.c_uint64 * 2)()
+        _lib.check(_lib.load().atl_hash128(x.ctypes.data_as(C.c_void_p), x.nbytes, seed, out))
+        return out[0], out[1]
+
+    b = np.random.default_rng(0).integers(0, 255, 777, dtype=np.uint8)
+    seen = {h(b)}
+    for i in range(777):
+        c = b.copy()
+        c[i] ^= 1 << (i % 8)
+        seen.add(h(c))
+    for n in range(64):
+        seen.add(h(b[:n]))
+    assert len(seen) == 1 + 777 + 64 and h(b, 1) != h(b, 0)
