@@ -286,3 +286,31 @@ def test_matrix_digest_is_a_content_key():
     for n in range(64):
         seen.add(h(b[:n]))
     assert len(seen) == 1 + 777 + 64 and h(b, 1) != h(b, 0)
+
+
+def test_finish_results_device_path_equals_the_numpy_path():
+    """convert._finish_results: the tail of convert_and_aggregate (float64, per-unit with zero-capacity
+    buses, NaN -> 0 but inf kept, NaN-skipping time aggregation, (bus, time) layout) computed with torch
+    ops -- what runs on the GPU for device results -- against the NumPy statement of the same lines."""
+    import numpy as np
+    import torch
+
+    from atlite_b200 import convert
+
+    rng = np.random.default_rng(0)
+    res = rng.uniform(0, 5, (37, 11)).astype(np.float32)
+    res[3, 2] = np.nan
+    res[5, 4] = np.inf
+    res[:, 7] = np.nan          # a bus that is NaN throughout: nanmean -> NaN, nansum -> 0
+    caps = rng.uniform(1, 3, 11)
+    caps[1] = 0.0               # zero capacity: x / NaN -> NaN -> 0
+    for c in (None, caps):
+        for agg in (None, "sum", "mean"):
+            for bus_major in (False, True):
+                want = convert._finish_results(res, c, agg, bus_major)
+                got = convert._finish_results(torch.from_numpy(res), c, agg, bus_major)
+                assert got.dtype == np.float64 and got.shape == want.shape and got.flags["C_CONTIGUOUS"]
+                np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+                np.testing.assert_allclose(got, want, rtol=1e-15, atol=0)
+    w = convert._finish_results(res, caps, None, True)
+    assert w.shape == (11, 37) and w[1].tolist() == [0.0] * 37 and np.isinf(w[4, 5]) and w[2, 3] == 0.0
