@@ -172,3 +172,38 @@ def test_bad_input_is_rejected():
     dat = np.array([1.0])
     rc = lib.atl_plan_tiling_host(2, 4, 1, _lib.ptr(indptr), _lib.ptr(idx), _lib.ptr(dat), C.byref(info), None, None, None, 0)
     assert rc == -1 and b"out of range" in lib.atl_last_error()
+
+
+def test_unsorted_columns_and_duplicates_take_the_general_ordering_path():
+    """build_tiling orders a bus's entries of a tile by a 4-way de-interleave when the CSR row has
+    ascending columns (scipy's canonical form) and by an insertion sort otherwise; a hand-made CSR
+    with shuffled columns and duplicates must give the plan of its canonical form."""
+    rng = np.random.default_rng(5)
+    ny, nx, nb = 37, 261, 9
+    rows, cols, vals = [], [], []
+    for r in range(nb):
+        c = rng.integers(0, ny * nx, 400)
+        rows += [r] * 400
+        cols += list(c)
+        vals += list(rng.uniform(0, 1, 400))
+    canonical = sp.csr_matrix((vals, (rows, cols)), shape=(nb, ny * nx))
+    indptr, idx, dat = [0], [], []
+    for r in range(nb):
+        sel = [i for i, rr in enumerate(rows) if rr == r]
+        rng.shuffle(sel)
+        idx += [cols[i] for i in sel]
+        dat += [vals[i] for i in sel]
+        indptr.append(len(idx))
+    raw = sp.csr_matrix((np.array(dat), np.array(idx, dtype=np.int32), np.array(indptr)), shape=(nb, ny * nx))
+    assert not raw.has_sorted_indices
+    info, tsp, row, w = tiling(raw, ny, nx)
+    info_c, tsp_c, row_c, w_c = tiling(canonical, ny, nx)
+    assert np.array_equal(tsp, tsp_c) and np.array_equal(row, row_c)
+    np.testing.assert_allclose(w, w_c, rtol=0, atol=5e-7)  # duplicates summed in another order, in fp32
+    np.testing.assert_allclose(dense_from_tiling(info, tsp, row, w, nb, ny, nx), canonical.toarray(), atol=5e-7)
+    n_raw, n_can = len(row), len(row_c)
+    assert n_raw == n_can
+    p1, c1, w1 = pair_lists(raw, ny, nx, n_raw)[:3]
+    p2, c2, w2 = pair_lists(canonical, ny, nx, n_can)[:3]
+    assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+    np.testing.assert_allclose(w1, w2, rtol=0, atol=5e-7)
