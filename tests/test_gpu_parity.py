@@ -103,6 +103,43 @@ def test_wind_interp_edges():
     assert_parity(got, want, cap_of(m), what="NaN routing")
 
 
+def test_result_tail_on_the_device_equals_the_numpy_statement():
+    """convert._finish_results on a CUDA tensor (float64, per-unit with a zero-capacity bus, NaN -> 0,
+    inf kept, NaN-skipping aggregation, (bus, time) layout) against the NumPy statement of
+    convert.py:259-271; and through the public call: per_unit + return_capacity + aggregate_time on a
+    device-resident cutout equal the host-resident cutout's results."""
+    import torch
+
+    from atlite_b200 import convert
+
+    rng = np.random.default_rng(0)
+    res = rng.uniform(0, 5, (53, 17)).astype(np.float32)
+    res[3, 2], res[5, 4] = np.nan, np.inf
+    res[:, 7] = np.nan
+    caps = rng.uniform(1, 3, 17)
+    caps[1] = 0.0
+    for c in (None, caps):
+        for agg in (None, "sum", "mean"):
+            for bus_major in (False, True):
+                want = convert._finish_results(res, c, agg, bus_major)
+                got = convert._finish_results(torch.from_numpy(res).cuda(), c, agg, bus_major)
+                assert got.dtype == np.float64 and got.shape == want.shape
+                np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+                np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+    ds = syn.make_dataset(40, 24, 30, x0=0.0, y0=30.0)
+    m = syn.make_shapes(40, 24, 6).tolil()
+    m[2, :] = 0  # a bus without cells: capacity 0 -> per-unit 0
+    m = m.tocsr()
+    for kw in (dict(aggregate_time=None), dict(aggregate_time="mean"), dict(aggregate_time="sum")):
+        host, cap_h = ab.Cutout(data=ds).wind("Vestas_V112_3MW", matrix=m, per_unit=True, return_capacity=True, **kw)
+        dev, cap_d = ab.Cutout(data=ds).to_device().wind("Vestas_V112_3MW", matrix=m, per_unit=True,
+                                                         return_capacity=True, **kw)
+        assert host.dims == dev.dims and host.attrs["units"] == dev.attrs["units"] == "p.u."
+        np.testing.assert_allclose(np.asarray(dev.values), np.asarray(host.values), rtol=1e-4, atol=1e-6)
+        np.testing.assert_array_equal(np.asarray(cap_d.values), np.asarray(cap_h.values))
+        assert np.all(np.asarray(dev.values)[2] == 0.0) if kw["aggregate_time"] is None else np.asarray(dev.values)[2] == 0.0
+
+
 @pytest.mark.parametrize("table", [0, 1, 2, 3])
 def test_wind_every_table_form(monkeypatch, table):
     """ATL_WIND_TABLE forces the power-curve table form (binary search, general LUT, lattice LUT with
